@@ -1,0 +1,289 @@
+/*
+ * ohp.h -- C-ABI of the B200-native P1 Poisson hot path (omegahPetsc ex12 pipeline).
+ *
+ * Every entry point is `extern "C"`, takes plain pointers / sizes / opaque handles and
+ * returns an int error code (0 = success, PetscErrorCode convention, ex12.cpp:1491-1501
+ * `ierr = f();CHKERRQ(ierr);`).  ohp_last_error() gives the message of the last failure on
+ * the calling thread.  Nothing here is a torch type; data handed in is HOST memory unless the
+ * parameter name ends in `_dev`.
+ *
+ * Each function cites the reference interface (paths relative to the reference checkout)
+ * that it replaces.  "PETSc-internal"/"Omega_h-internal" = behaviour of the un-vendored
+ * library reached from the cited call site.
+ *
+ * Types: PetscInt = int32 (ex12.cpp:915,939 pass int* as PetscInt*), PetscScalar =
+ * PetscReal = double, Omega_h::LO = int32, GO = int64.
+ */
+#ifndef OHP_H
+#define OHP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OHP_VERSION 1
+
+typedef struct ohp_context_s *ohp_context; /* device, stream, optional NCCL communicator   */
+typedef struct ohp_osh_s *ohp_osh;         /* one decoded `.osh` stream, host memory        */
+typedef struct ohp_mesh_s *ohp_mesh;       /* DM: Plex-shaped mesh + section + CSR pattern  */
+typedef struct ohp_vec_s *ohp_vec;         /* Vec (device resident, FP64)                    */
+typedef struct ohp_mat_s *ohp_mat;         /* Mat (AIJ / CSR values on the DM's pattern)     */
+
+/* error codes (subset of PETSc's petscerror.h numbering) */
+enum {
+  OHP_OK = 0,
+  OHP_ERR_MEM = 55,          /* PETSC_ERR_MEM */
+  OHP_ERR_SUP = 56,          /* PETSC_ERR_SUP */
+  OHP_ERR_ARG_SIZ = 60,      /* PETSC_ERR_ARG_SIZ */
+  OHP_ERR_ARG_WRONG = 62,    /* PETSC_ERR_ARG_WRONG */
+  OHP_ERR_ARG_OUTOFRANGE = 63,
+  OHP_ERR_FILE_OPEN = 65,
+  OHP_ERR_FILE_READ = 66,
+  OHP_ERR_FILE_UNEXPECTED = 79,
+  OHP_ERR_LIB = 76,          /* PETSC_ERR_LIB: CUDA / NCCL / zlib failure */
+  OHP_ERR_ORDER = 58,        /* PETSC_ERR_ORDER: object used before set up */
+  OHP_ERR_GPU = 97           /* PETSC_ERR_GPU: no usable device (there is NO CPU fallback) */
+};
+
+const char *ohp_last_error(void);
+int ohp_version(void);
+
+/* ------------------------------------------------------------------------------------ */
+/* Context.  Replaces PetscInitialize / Omega_h::Library / MPI_Comm plumbing              */
+/* (ex12.cpp:1485,1494).  One context per process = one GPU = one rank.                  */
+/* ------------------------------------------------------------------------------------ */
+int ohp_init(int device, ohp_context *ctx);
+int ohp_finalize(ohp_context ctx);
+int ohp_device_name(ohp_context ctx, char *buf, int buflen);
+int ohp_sync(ohp_context ctx);
+/* cudaStream_t the context launches on, as a void* (for CUDA-event timing by the caller) */
+int ohp_stream(ohp_context ctx, void **stream);
+/* cumulative number of kernel launches issued by this library on this context */
+int ohp_launch_count(ohp_context ctx, int64_t *count);
+
+/* Multi-GPU: MPI_Comm_rank/size (ex12.cpp:800-801) + the communicator PETSc/Omega_h use
+ * for halo exchange and dot products.  `unique_id` is the 128-byte ncclUniqueId made by
+ * ohp_comm_unique_id() on rank 0 and broadcast by the host launcher. */
+int ohp_comm_unique_id(void *unique_id128);
+int ohp_comm_init(ohp_context ctx, int nranks, int rank, const void *unique_id128);
+int ohp_comm_rank_size(ohp_context ctx, int *rank, int *nranks);
+
+/* ------------------------------------------------------------------------------------ */
+/* `.osh` loading -- Omega_h::binary::read (ex12.cpp:813,818) + Mesh::ask_elem_verts     */
+/* (ex12.cpp:591,634,784) + mesh.coords() / get_array<>(dim,name) (ex12.cpp:593-594,     */
+/* 627-628,703-705).  Host only: needs no GPU.                                           */
+/* ------------------------------------------------------------------------------------ */
+int ohp_osh_read(const char *dir, int part, ohp_osh *osh);
+int ohp_osh_free(ohp_osh osh);
+int ohp_osh_info(ohp_osh osh, int *dim, int *nverts, int *nelems, int *version, int *nparts);
+/* element->vertex connectivity, derived from the stored downward adjacencies + codes;
+ * borrowed pointer, (dim+1)*nelems int32, valid until ohp_osh_free */
+int ohp_osh_elem_verts(ohp_osh osh, const int32_t **ev);
+int ohp_osh_coords(ohp_osh osh, const double **coords); /* dim*nverts doubles, borrowed */
+/* tag lookup: type code 0=i8 2=i32 3=i64 5=f64 (Omega_h_defines.h); returns
+ * OHP_ERR_ARG_WRONG if the tag is absent */
+int ohp_osh_tag(ohp_osh osh, int ent_dim, const char *name, int *ncomps, int *type,
+                int64_t *count, const void **data);
+int ohp_osh_nents(ohp_osh osh, int ent_dim, int *n);
+
+/* ------------------------------------------------------------------------------------ */
+/* picpart core extraction -- getPicPartCoreVtxCoords (ex12.cpp:623-672, kernels K2,K3), */
+/* getPicPartCoreElmToVtxArray (ex12.cpp:584-619, K1), ghost list of                     */
+/* getPicPartCoreVtxOwnerIdx (ex12.cpp:694-730, K4,K5).  Runs on the device (mask,       */
+/* scan, compaction); results returned in caller-provided host arrays sized by the       */
+/* part's counts.  `with_overlap` = 0 reproduces the reference's core (owned elements);  */
+/* 1 adds every element touching an owned vertex (the assembly closure this library      */
+/* needs for communication-free row assembly).                            */
+/* ------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t n_core_elems;   /* elements kept                                     */
+  int32_t n_core_verts;   /* vertices of kept elements                         */
+  int32_t n_owned_verts;  /* core vertices with owner == rank                  */
+  int32_t n_ghost_verts;  /* core vertices with owner != rank                  */
+} ohp_core_counts;
+
+int ohp_picpart_extract(ohp_context ctx, int dim, int rank, int with_overlap, int32_t n_elems,
+                        int32_t n_verts, const int32_t *elem_verts, const double *coords,
+                        const int32_t *elem_owner, const int32_t *vert_owner,
+                        const int64_t *vert_gid, ohp_core_counts *counts,
+                        int32_t *core_elem_verts /* (dim+1)*n_elems cap */,
+                        double *core_coords /* dim*n_verts cap */,
+                        int32_t *part2core /* n_verts, -1 if not core */,
+                        int32_t *ghost_core_idx /* n_verts cap */,
+                        int64_t *ghost_gid /* n_verts cap */,
+                        int32_t *ghost_owner /* n_verts cap */,
+                        int64_t *core_gid /* n_verts cap */);
+
+/* ------------------------------------------------------------------------------------ */
+/* DM.  ohp_mesh_create = DMPlexCreateFromCellListPetsc(comm,dim,nC,nV,nCorners,interp,  */
+/* cells,spaceDim,coords,&dm) (ex12.cpp:859,933): cells and coords are COPIED (to HBM).  */
+/* Points follow Plex numbering: cells [0,nC), vertices [nC,nC+nV).                      */
+/* ------------------------------------------------------------------------------------ */
+int ohp_mesh_create(ohp_context ctx, int dim, int32_t n_cells, int32_t n_verts,
+                    const int32_t *cells, const double *coords, ohp_mesh *mesh);
+int ohp_mesh_destroy(ohp_mesh mesh);
+
+/* PetscSFSetGraph on the DM's point SF (ex12.cpp:873-876, 937-939): leaf i = local vertex
+ * ghost_vertex[i] (0-based VERTEX index, i.e. Plex point minus nC), root = vertex
+ * owner_vertex[i] on rank owner_rank[i].  Arrays are copied (the caller keeps ownership,
+ * unlike PETSC_OWN_POINTER). Collective when a communicator is attached. */
+int ohp_mesh_set_ghosts(ohp_mesh mesh, int32_t n_leaves, const int32_t *ghost_vertex,
+                        const int32_t *owner_rank, const int32_t *owner_vertex);
+
+/* Everything ex12 does between mesh creation and the first solve, on the device:
+ *   DMPlexInterpolate + boundary marking, facets with support size 1 -> label "marker"
+ *     (ex12.cpp:958-1033),
+ *   PetscFECreateDefault(dim,1,simplex,-1) / DMCreateDS / DMAddBoundary(ESSENTIAL,"marker",1)
+ *     -> local + global section (ex12.cpp:1309-1321,1237-1239),
+ *   DMCreateMatrix preallocation -> CSR pattern (ex12.cpp:1508),
+ *   and the row->element gather map used by the assembly kernels.
+ * Collective when a communicator is attached. */
+int ohp_mesh_setup(ohp_mesh mesh);
+
+typedef struct {
+  int32_t dim, n_cells, n_verts;
+  int32_t n_boundary_verts; /* vertices labelled "marker"=1                              */
+  int32_t n_owned;          /* owned unconstrained dofs = local rows (DMCreateGlobalVector) */
+  int32_t n_ghost;          /* unconstrained ghost dofs = off-process columns              */
+  int64_t n_global;         /* global unconstrained dofs                                   */
+  int64_t row_start;        /* first global row of this rank                               */
+  int64_t nnz;              /* local CSR entries (diag + off-diag block)                   */
+  int32_t max_row;          /* longest row                                                 */
+} ohp_mesh_info;
+int ohp_mesh_get_info(ohp_mesh mesh, ohp_mesh_info *info);
+
+/* label "marker" (ex12.cpp:1023-1026): bnd[v] in {0,1}, n_verts bytes */
+int ohp_mesh_get_boundary(ohp_mesh mesh, uint8_t *bnd);
+/* global section: gidx[v] = global dof of vertex v, -1 if constrained; n_verts int64 */
+int ohp_mesh_get_numbering(ohp_mesh mesh, int64_t *gidx);
+/* CSR pattern: rowptr[n_owned+1]; colidx[nnz] in GLOBAL dof numbers, ascending per row */
+int ohp_mesh_get_csr(ohp_mesh mesh, int32_t *rowptr, int64_t *colidx);
+
+/* ------------------------------------------------------------------------------------ */
+/* Problems = the PetscDS registration of SetupProblem (ex12.cpp:1162-1243).             */
+/* Built-in ids restate ex12's callback sets with the callbacks inlined into the kernels: */
+/*   OHP_PROBLEM_COEFF_NONE : f0_u, f1_u, g3_uu            (ex12.cpp:147,198,209)          */
+/*   OHP_PROBLEM_ANALYTIC   : f0/f1/g3_analytic_u          (ex12.cpp:283,292,313)          */
+/*   OHP_PROBLEM_NONLINEAR  : f0/f1/g3_analytic_nonlinear_u (ex12.cpp:341,350,369)         */
+/* Dirichlet / exact data: quadratic_u_2d / quadratic_u_3d (ex12.cpp:113,408).           */
+/* User callbacks compiled by nvcc are registered through ohp_problem_register (see      */
+/* include/ohp_petsc.h, which turns PetscDSSetResidual/Jacobian into this call).         */
+/* ------------------------------------------------------------------------------------ */
+enum { OHP_PROBLEM_COEFF_NONE = 0, OHP_PROBLEM_ANALYTIC = 1, OHP_PROBLEM_NONLINEAR = 2 };
+
+/* device view handed to registered assembly launchers (all pointers are DEVICE pointers) */
+typedef struct {
+  int32_t dim, n_cells, n_verts, n_rows;
+  const int32_t *cells_dev;    /* (dim+1)*n_cells                                       */
+  const double *coords_dev;    /* dim*n_verts                                           */
+  const int32_t *lidx_dev;     /* n_verts: local dof (owned rows first, then ghosts), -1 constrained */
+  const int32_t *row_vertex_dev; /* n_rows: vertex of each local row                    */
+  const int32_t *v2c_ptr_dev;  /* n_verts+1: star(v) as a CSR over vertices              */
+  const int32_t *v2c_dev;      /* entries cell*4 + (position of v in the cell), ascending */
+  const uint8_t *slot_dev;     /* (dim+1) per v2c entry: column slot within the row, 255 = constrained */
+  const int32_t *rowptr_dev;   /* n_rows+1                                              */
+  const double *u_dev;         /* local solution: n_rows owned + ghost dofs             */
+  double *out_dev;             /* residual: F[n_rows]; Jacobian: vals[nnz]              */
+  void *stream;                /* cudaStream_t                                          */
+} ohp_assembly_view;
+
+typedef int (*ohp_assembly_launcher)(const ohp_assembly_view *view);
+int ohp_problem_register(ohp_assembly_launcher residual, ohp_assembly_launcher jacobian,
+                         ohp_assembly_launcher project_exact, int *problem_id);
+
+/* ------------------------------------------------------------------------------------ */
+/* Vec (VecCreate via DMCreateGlobalVector ex12.cpp:1505; VecSet/AXPY/Norm/Chop/Duplicate */
+/* ex12.cpp:1626-1660).  Length = n_owned (+ ghost tail kept internally).                */
+/* ------------------------------------------------------------------------------------ */
+int ohp_vec_create(ohp_mesh mesh, ohp_vec *v);
+int ohp_vec_duplicate(ohp_vec v, ohp_vec *w);
+int ohp_vec_destroy(ohp_vec v);
+int ohp_vec_size(ohp_vec v, int32_t *n_local);
+int ohp_vec_set(ohp_vec v, double alpha);
+int ohp_vec_copy(ohp_vec src, ohp_vec dst);
+int ohp_vec_from_host(ohp_vec v, const double *host);
+int ohp_vec_to_host(ohp_vec v, double *host);
+int ohp_vec_axpy(ohp_vec y, double alpha, ohp_vec x);              /* y += alpha x   */
+int ohp_vec_aypx(ohp_vec y, double alpha, ohp_vec x);              /* y = x + alpha y */
+int ohp_vec_dot(ohp_vec x, ohp_vec y, double *result);             /* global         */
+int ohp_vec_norm2(ohp_vec x, double *result);                      /* NORM_2, global */
+int ohp_vec_chop(ohp_vec v, double tol);                           /* VecChop        */
+void *ohp_vec_device_ptr(ohp_vec v);
+
+/* ------------------------------------------------------------------------------------ */
+/* Mat (DMCreateMatrix ex12.cpp:1508; MatMult ex12.cpp:1655)                             */
+/* ------------------------------------------------------------------------------------ */
+int ohp_mat_create(ohp_mesh mesh, ohp_mat *A);
+int ohp_mat_destroy(ohp_mat A);
+int ohp_mat_zero(ohp_mat A);
+int ohp_mat_get_values(ohp_mat A, double *vals /* nnz, pattern order */);
+int ohp_mat_mult(ohp_mat A, ohp_vec x, ohp_vec y); /* y = A x (halo exchange inside) */
+
+/* ------------------------------------------------------------------------------------ */
+/* FEM evaluators installed by DMPlexSetSNESLocalFEM (ex12.cpp:1540) and called through   */
+/* SNESComputeFunction / SNESComputeJacobian (ex12.cpp:1624,1641,1651).                  */
+/* ------------------------------------------------------------------------------------ */
+int ohp_residual(ohp_mesh mesh, int problem, ohp_vec u, ohp_vec F);
+int ohp_jacobian(ohp_mesh mesh, int problem, ohp_vec u, ohp_mat J);
+/* DMProjectFunction (ex12.cpp:1546,1602): which = 0 zero (ex12.cpp:76), 1 the problem's
+ * exact solution sampled at the vertices (P1 dual basis = point evaluation) */
+int ohp_project(ohp_mesh mesh, int problem, int which, ohp_vec u);
+/* DMComputeL2Diff against the exact solution (ex12.cpp:1611,1637) */
+int ohp_l2_error(ohp_mesh mesh, int problem, ohp_vec u, double *err);
+
+/* ------------------------------------------------------------------------------------ */
+/* KSP CG (PETSc-internal KSPSolve_CG selected by -ksp_type cg at ex12.cpp:1543).        */
+/* ------------------------------------------------------------------------------------ */
+enum { OHP_PC_NONE = 0, OHP_PC_JACOBI = 1 };
+typedef struct {
+  double rtol, abstol, dtol; /* -ksp_rtol (1e-5; CTests 1e-9 CMakeLists.txt:53) -ksp_atol 1e-50 -ksp_divtol 1e5 */
+  int32_t max_it;            /* -ksp_max_it 10000 */
+  int32_t pc;                /* -pc_type none|jacobi */
+  int32_t check_every;       /* iterations between host polls of the device-side converged flag (0 = default) */
+  int32_t history_cap;       /* length of `history` (0 = none) */
+  double *history;           /* host array receiving the monitored norm per iteration (-ksp_monitor) */
+  int32_t profile;           /* >0: bracket up to this many SpMV launches with CUDA events (-log_view analogue) */
+} ohp_ksp_options;
+typedef struct {
+  int32_t its;
+  int32_t reason; /* KSPConvergedReason: 2 RTOL, 3 ATOL, -3 ITS, -4 DTOL, -8 INDEFINITE_MAT, -9 NANORINF */
+  double rnorm;
+  double rnorm0;
+  float spmv_ms;        /* mean device time of the profiled SpMV launches (0 if profile == 0) */
+  int32_t spmv_samples; /* how many launches that mean is over */
+  float total_ms;       /* device time of the whole solve (CUDA events) */
+} ohp_ksp_result;
+int ohp_ksp_default_options(ohp_ksp_options *o);
+int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *opts, ohp_ksp_result *res);
+
+/* ------------------------------------------------------------------------------------ */
+/* SNES newtonls + bt (PETSc-internal SNESSolve_NEWTONLS reached from SNESSolve          */
+/* ex12.cpp:1609)                                                                        */
+/* ------------------------------------------------------------------------------------ */
+typedef struct {
+  double rtol, abstol, stol; /* -snes_rtol 1e-8 -snes_atol 1e-50 -snes_stol 1e-8 */
+  int32_t max_it;            /* -snes_max_it 50 */
+  ohp_ksp_options ksp;
+} ohp_snes_options;
+typedef struct {
+  int32_t its;          /* Newton iterations */
+  int32_t ksp_its;      /* total linear iterations */
+  int32_t reason;       /* SNESConvergedReason: 2 FNORM_ABS 3 FNORM_RELATIVE 4 SNORM_RELATIVE -3 LINEAR_SOLVE -5 MAX_IT */
+  int32_t n_residual;   /* residual evaluations */
+  int32_t n_jacobian;   /* Jacobian evaluations */
+  double fnorm0, fnorm; /* ||F(u0)||, ||F(u_final)|| */
+  float ms_residual, ms_jacobian, ms_ksp; /* device time per phase (CUDA events), summed */
+  float spmv_ms;        /* from the last linear solve, see ohp_ksp_result */
+  int32_t spmv_samples;
+} ohp_snes_result;
+int ohp_snes_default_options(ohp_snes_options *o);
+int ohp_snes_solve(ohp_mesh mesh, int problem, ohp_mat J, ohp_vec u, const ohp_snes_options *opts,
+                   ohp_snes_result *res);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OHP_H */

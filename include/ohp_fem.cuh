@@ -1,0 +1,377 @@
+/*
+ * ohp_fem.cuh -- sm_100a assembly kernels of the P1 Poisson path, templated on the problem
+ * (the PetscDS pointwise callbacks).  libohp.so instantiates them for ex12's built-in
+ * callback sets; a user translation unit compiled by nvcc instantiates them for its own
+ * __host__ __device__ callbacks through include/ohp_petsc.h and registers the launchers
+ * with ohp_problem_register().
+ *
+ * What is restated here [PETSc-internal, reached from DMPlexSetSNESLocalFEM ex12.cpp:1540]:
+ *   DMPlexComputeCellGeometryFEM (affine simplex: v0, J, invJ, detJ on the biunit reference
+ *   cell), PetscFE P1 tabulation, PetscFEIntegrateResidual_Basic / IntegrateJacobian_Basic,
+ *   DMPlexInsertBoundaryValues (essential values from the BC function at the vertices),
+ *   DMPlexVecSetClosure / DMPlexMatSetClosure (ADD, constrained dofs dropped).
+ *
+ * Parallelisation: "owner computes", colour-free and atomic-free.  One thread owns one matrix
+ * row (= one unconstrained owned vertex v) and walks star(v) in ascending cell order, so the
+ * per-slot summation order equals PETSc's cell-loop order and results are bitwise reproducible
+ * run to run.  Row values are accumulated in shared memory (each thread touches only its own
+ * row's slots) and flushed to HBM as one coalesced stream per block.
+ */
+#ifndef OHP_FEM_CUH
+#define OHP_FEM_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ohp.h"
+
+#ifndef OHP_HD
+#define OHP_HD __host__ __device__ __forceinline__
+#endif
+
+namespace ohp {
+
+/* PetscDS pointwise-callback argument lists (ex12.cpp:147-150 and :209-212) */
+#define OHP_PF_ARGS                                                                              \
+  int dim, int Nf, int NfAux, const int uOff[], const int uOff_x[], const double u[],            \
+      const double u_t[], const double u_x[], const int aOff[], const int aOff_x[],              \
+      const double a[], const double a_t[], const double a_x[], double t, const double x[],      \
+      int numConstants, const double constants[]
+#define OHP_PJ_ARGS                                                                              \
+  int dim, int Nf, int NfAux, const int uOff[], const int uOff_x[], const double u[],            \
+      const double u_t[], const double u_x[], const int aOff[], const int aOff_x[],              \
+      const double a[], const double a_t[], const double a_x[], double t, double u_tShift,       \
+      const double x[], int numConstants, const double constants[]
+
+/* Stroud conical quadrature, 2 Gauss-Jacobi points per direction, on the biunit simplex
+ * [PETSc-internal: PetscFECreateDefault(..., qorder=-1) at ex12.cpp:1309 ->
+ * PetscDTStroudConicalQuadrature]; sum of weights 2 (2-D), 4/3 (3-D). */
+template <int DIM> struct Quadrature;
+template <> struct Quadrature<2> {
+  static constexpr int NQ = 4;
+  OHP_HD static double xi(int q, int d) {
+    constexpr double P[4][2] = {{-6.42882543472767187254e-01, -6.89897948556635665085e-01},
+                                {-8.49937779554783778835e-01, 2.89897948556635642881e-01},
+                                {3.32780492029402796827e-01, -6.89897948556635665085e-01},
+                                {-4.39960169001851864046e-01, 2.89897948556635642881e-01}};
+    return P[q][d];
+  }
+  OHP_HD static double w(int q) {
+    constexpr double W[4] = {6.36082763487954339077e-01, 3.63917236512045660923e-01,
+                             6.36082763487954339077e-01, 3.63917236512045660923e-01};
+    return W[q];
+  }
+};
+template <> struct Quadrature<3> {
+  static constexpr int NQ = 8;
+  OHP_HD static double xi(int q, int d) {
+    constexpr double P[8][3] = {
+        {-6.86634725326363382081e-01, -7.27890046394307987931e-01, -7.54970354689117217895e-01},
+        {-8.37208665970659460243e-01, -8.58640551681206232182e-01, 8.83036880224505743575e-02},
+        {-8.68322625879911158542e-01, 1.31866330145601756696e-01, -7.54970354689117217895e-01},
+        {-9.31594413526467213238e-01, -4.12002398736754260611e-01, 8.83036880224505743575e-02},
+        {1.69495126409788587907e-01, -7.27890046394307987931e-01, -7.54970354689117217895e-01},
+        {-3.92454470370584895811e-01, -8.58640551681206232182e-01, 8.83036880224505743575e-02},
+        {-5.08573349576573296993e-01, 1.31866330145601756696e-01, -7.54970354689117217895e-01},
+        {-7.44706875759229114387e-01, -4.12002398736754260611e-01, 8.83036880224505743575e-02}};
+    return P[q][d];
+  }
+  OHP_HD static double w(int q) {
+    constexpr double W[8] = {2.95838850870823288908e-01, 1.28216324787812918640e-01,
+                             1.69256051636192478282e-01, 7.33554393718379577072e-02,
+                             2.95838850870823288908e-01, 1.28216324787812918640e-01,
+                             1.69256051636192478282e-01, 7.33554393718379577072e-02};
+    return W[q];
+  }
+};
+
+/* Affine cell geometry on the biunit reference simplex: J[d][f] = (x_{f+1}[d]-x_0[d])/2,
+ * real-space P1 gradients G[b][d] = sum_e Dref[b][e] invJ[e][d], Dref row 0 = -1/2,
+ * row b>0 = +1/2 at e = b-1. */
+template <int DIM> struct CellGeom {
+  double v0[DIM], J[DIM * DIM], detJ, G[DIM + 1][DIM];
+};
+
+template <int DIM> OHP_HD void cell_geometry(const double (&X)[DIM + 1][DIM], CellGeom<DIM> &g) {
+  double I[DIM * DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) {
+    g.v0[d] = X[0][d];
+#pragma unroll
+    for (int f = 0; f < DIM; ++f) g.J[d * DIM + f] = 0.5 * (X[f + 1][d] - X[0][d]);
+  }
+  const double *J = g.J;
+  if constexpr (DIM == 2) {
+    g.detJ = J[0] * J[3] - J[1] * J[2];
+    const double id = 1.0 / g.detJ;
+    I[0] = id * J[3]; I[1] = -id * J[1]; I[2] = -id * J[2]; I[3] = id * J[0];
+  } else {
+    const double c0 = J[4] * J[8] - J[5] * J[7];
+    const double c1 = J[5] * J[6] - J[3] * J[8];
+    const double c2 = J[3] * J[7] - J[4] * J[6];
+    g.detJ = J[0] * c0 + J[1] * c1 + J[2] * c2;
+    const double id = 1.0 / g.detJ;
+    I[0] = id * c0;
+    I[1] = id * (J[2] * J[7] - J[1] * J[8]);
+    I[2] = id * (J[1] * J[5] - J[2] * J[4]);
+    I[3] = id * c1;
+    I[4] = id * (J[0] * J[8] - J[2] * J[6]);
+    I[5] = id * (J[2] * J[3] - J[0] * J[5]);
+    I[6] = id * c2;
+    I[7] = id * (J[1] * J[6] - J[0] * J[7]);
+    I[8] = id * (J[0] * J[4] - J[1] * J[3]);
+  }
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) {
+    double s = 0.0;
+#pragma unroll
+    for (int e = 0; e < DIM; ++e) s += I[e * DIM + d];
+    g.G[0][d] = -0.5 * s;
+#pragma unroll
+    for (int b = 1; b <= DIM; ++b) g.G[b][d] = 0.5 * I[(b - 1) * DIM + d];
+  }
+}
+
+template <int DIM> OHP_HD void p1_basis(int q, double (&phi)[DIM + 1]) {
+  double s = 0.0;
+#pragma unroll
+  for (int e = 0; e < DIM; ++e) {
+    phi[e + 1] = 0.5 * (1.0 + Quadrature<DIM>::xi(q, e));
+    s += Quadrature<DIM>::xi(q, e);
+  }
+  phi[0] = -0.5 * (s + DIM - 2.0);
+}
+
+/* closure of one cell: vertex ids, coordinates and (optionally) local solution values with
+ * the essential boundary values inserted from the problem's BC function at the vertex
+ * (registered with DMAddBoundary at ex12.cpp:1237-1239) */
+template <int DIM, class P, bool WITH_U>
+__device__ __forceinline__ void load_cell(const ohp_assembly_view &vw, int c, int (&cv)[DIM + 1],
+                                          double (&X)[DIM + 1][DIM], double (&ue)[DIM + 1]) {
+  constexpr int NC = DIM + 1;
+#pragma unroll
+  for (int j = 0; j < NC; ++j) cv[j] = __ldg(vw.cells_dev + (size_t)c * NC + j);
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) X[j][d] = __ldg(vw.coords_dev + (size_t)cv[j] * DIM + d);
+  }
+  if (WITH_U) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const int l = __ldg(vw.lidx_dev + cv[j]);
+      if (l >= 0) ue[j] = __ldg(vw.u_dev + l);
+      else { double val = 0.0; P::bc(DIM, 0.0, X[j], 1, &val, nullptr); ue[j] = val; }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Residual: F[r] = sum over cells c in star(v_r), ascending, of Fe_c[b]                 */
+/* ------------------------------------------------------------------------------------ */
+template <int DIM, class P>
+__global__ void __launch_bounds__(256) k_residual_rows(const ohp_assembly_view vw) {
+  constexpr int NC = DIM + 1;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= vw.n_rows) return;
+  const int v = __ldg(vw.row_vertex_dev + r);
+  const int k0 = __ldg(vw.v2c_ptr_dev + v), k1 = __ldg(vw.v2c_ptr_dev + v + 1);
+  const int uOff[2] = {0, 1}, uOff_x[2] = {0, DIM};
+  double acc = 0.0;
+  for (int k = k0; k < k1; ++k) {
+    const int e = __ldg(vw.v2c_dev + k);
+    const int c = e >> 2, b = e & 3;
+    int cv[NC];
+    double X[NC][DIM], ue[NC];
+    load_cell<DIM, P, true>(vw, c, cv, X, ue);
+    CellGeom<DIM> g;
+    cell_geometry<DIM>(X, g);
+    double ux[DIM], Gb[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < NC; ++j) s += g.G[j][d] * ue[j];
+      ux[d] = s;
+      double gb = g.G[0][d];
+#pragma unroll
+      for (int j = 1; j < NC; ++j) gb = (b == j) ? g.G[j][d] : gb;
+      Gb[d] = gb;
+    }
+    double fe = 0.0;
+#pragma unroll
+    for (int q = 0; q < Quadrature<DIM>::NQ; ++q) {
+      double phi[NC], xq[DIM], uq = 0.0;
+      p1_basis<DIM>(q, phi);
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) {
+        double s = g.v0[d];
+#pragma unroll
+        for (int f = 0; f < DIM; ++f) s += g.J[d * DIM + f] * (Quadrature<DIM>::xi(q, f) + 1.0);
+        xq[d] = s;
+      }
+      double phib = phi[0];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) { uq += phi[j] * ue[j]; phib = (b == j) ? phi[j] : phib; }
+      double f0[1] = {0.0}, f1[DIM];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) f1[d] = 0.0;
+      P::f0(DIM, 1, 0, uOff, uOff_x, &uq, nullptr, ux, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, xq, 0, nullptr, f0);
+      P::f1(DIM, 1, 0, uOff, uOff_x, &uq, nullptr, ux, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, xq, 0, nullptr, f1);
+      const double w = g.detJ * Quadrature<DIM>::w(q);
+      double s = phib * (f0[0] * w);
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) s += Gb[d] * (f1[d] * w);
+      fe += s;
+    }
+    acc += fe;
+  }
+  vw.out_dev[r] = acc;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Jacobian: one thread per row; row b of every star cell's element matrix,               */
+/*   Ke[b][j] = detJ * G_b^T (sum_q w_q g3_q) G_j   (P1: gradients constant per cell),   */
+/* added to the row's slots in shared memory, flushed coalesced.                         */
+/* ------------------------------------------------------------------------------------ */
+template <int DIM, class P>
+__global__ void __launch_bounds__(256) k_jacobian_rows(const ohp_assembly_view vw, int smem_doubles) {
+  constexpr int NC = DIM + 1;
+  extern __shared__ double s_vals[];
+  const int r0 = blockIdx.x * blockDim.x;
+  const int r1 = min(r0 + (int)blockDim.x, vw.n_rows);
+  const int s0 = __ldg(vw.rowptr_dev + r0), s1 = __ldg(vw.rowptr_dev + r1);
+  const bool in_smem = (s1 - s0) <= smem_doubles;
+  double *acc_base = in_smem ? s_vals : (vw.out_dev + s0);
+  for (int i = threadIdx.x; i < s1 - s0; i += blockDim.x) acc_base[i] = 0.0;
+  __syncthreads();
+  const int r = r0 + threadIdx.x;
+  if (r < r1) {
+    const int v = __ldg(vw.row_vertex_dev + r);
+    const int k0 = __ldg(vw.v2c_ptr_dev + v), k1 = __ldg(vw.v2c_ptr_dev + v + 1);
+    double *row = acc_base + (__ldg(vw.rowptr_dev + r) - s0);
+    const int uOff[2] = {0, 1}, uOff_x[2] = {0, DIM};
+    for (int k = k0; k < k1; ++k) {
+      const int e = __ldg(vw.v2c_dev + k);
+      const int c = e >> 2, b = e & 3;
+      int cv[NC];
+      double X[NC][DIM], ue[NC];
+      load_cell<DIM, P, P::kJacobianUsesU>(vw, c, cv, X, ue);
+      CellGeom<DIM> g;
+      cell_geometry<DIM>(X, g);
+      double ux[DIM], Gb[DIM];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) {
+        double s = 0.0;
+        if (P::kJacobianUsesU) {
+#pragma unroll
+          for (int j = 0; j < NC; ++j) s += g.G[j][d] * ue[j];
+        }
+        ux[d] = s;
+        double gb = g.G[0][d];
+#pragma unroll
+        for (int j = 1; j < NC; ++j) gb = (b == j) ? g.G[j][d] : gb;
+        Gb[d] = gb;
+      }
+      double S[DIM * DIM];
+#pragma unroll
+      for (int i = 0; i < DIM * DIM; ++i) S[i] = 0.0;
+#pragma unroll
+      for (int q = 0; q < Quadrature<DIM>::NQ; ++q) {
+        double xq[DIM], uq = 0.0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+          double s = g.v0[d];
+#pragma unroll
+          for (int f = 0; f < DIM; ++f) s += g.J[d * DIM + f] * (Quadrature<DIM>::xi(q, f) + 1.0);
+          xq[d] = s;
+        }
+        if (P::kJacobianUsesU) {
+          double phi[NC];
+          p1_basis<DIM>(q, phi);
+#pragma unroll
+          for (int j = 0; j < NC; ++j) uq += phi[j] * ue[j];
+        }
+        double g3[DIM * DIM];
+#pragma unroll
+        for (int i = 0; i < DIM * DIM; ++i) g3[i] = 0.0; /* the integrator zeroes g3: g3_uu writes only the diagonal (ex12.cpp:215) */
+        P::g3(DIM, 1, 0, uOff, uOff_x, &uq, nullptr, ux, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, 0.0, xq, 0, nullptr, g3);
+        const double w = Quadrature<DIM>::w(q);
+#pragma unroll
+        for (int i = 0; i < DIM * DIM; ++i) S[i] += w * g3[i];
+      }
+      /* t[e] = detJ * sum_d Gb[d] S[d][e] */
+      double t[DIM];
+#pragma unroll
+      for (int e2 = 0; e2 < DIM; ++e2) {
+        double s = 0.0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) s += Gb[d] * S[d * DIM + e2];
+        t[e2] = g.detJ * s;
+      }
+      const uint8_t *sl = vw.slot_dev + (size_t)k * NC;
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        const int slot = __ldg(sl + j);
+        if (slot != 255) {
+          double s = 0.0;
+#pragma unroll
+          for (int e2 = 0; e2 < DIM; ++e2) s += t[e2] * g.G[j][e2];
+          row[slot] += s;
+        }
+      }
+    }
+  }
+  if (in_smem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < s1 - s0; i += blockDim.x) vw.out_dev[s0 + i] = s_vals[i];
+  }
+}
+
+/* DMProjectFunction of the exact solution onto P1 = point evaluation at the vertices */
+template <int DIM, class P> __global__ void k_project_exact(const ohp_assembly_view vw) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= vw.n_rows) return;
+  const int v = __ldg(vw.row_vertex_dev + r);
+  double x[DIM], val = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) x[d] = __ldg(vw.coords_dev + (size_t)v * DIM + d);
+  P::exact(DIM, 0.0, x, 1, &val, nullptr);
+  vw.out_dev[r] = val;
+}
+
+constexpr int kJacobianSmemDoubles = 6144; /* 48 KB per 256-row block */
+
+template <int DIM, class P> int launch_residual(const ohp_assembly_view *vw) {
+  if (vw->n_rows <= 0) return 0;
+  const int bs = 128;
+  k_residual_rows<DIM, P><<<(vw->n_rows + bs - 1) / bs, bs, 0, (cudaStream_t)vw->stream>>>(*vw);
+  return cudaGetLastError() == cudaSuccess ? 0 : OHP_ERR_LIB;
+}
+template <int DIM, class P> int launch_jacobian(const ohp_assembly_view *vw) {
+  if (vw->n_rows <= 0) return 0;
+  const int bs = 256;
+  k_jacobian_rows<DIM, P><<<(vw->n_rows + bs - 1) / bs, bs, kJacobianSmemDoubles * sizeof(double),
+                            (cudaStream_t)vw->stream>>>(*vw, kJacobianSmemDoubles);
+  return cudaGetLastError() == cudaSuccess ? 0 : OHP_ERR_LIB;
+}
+template <int DIM, class P> int launch_project_exact(const ohp_assembly_view *vw) {
+  if (vw->n_rows <= 0) return 0;
+  const int bs = 256;
+  k_project_exact<DIM, P><<<(vw->n_rows + bs - 1) / bs, bs, 0, (cudaStream_t)vw->stream>>>(*vw);
+  return cudaGetLastError() == cudaSuccess ? 0 : OHP_ERR_LIB;
+}
+
+/* dimension dispatch used by both the built-in problems and user registrations */
+template <class P> int launch_residual_any(const ohp_assembly_view *vw) {
+  return vw->dim == 2 ? launch_residual<2, P>(vw) : vw->dim == 3 ? launch_residual<3, P>(vw) : OHP_ERR_SUP;
+}
+template <class P> int launch_jacobian_any(const ohp_assembly_view *vw) {
+  return vw->dim == 2 ? launch_jacobian<2, P>(vw) : vw->dim == 3 ? launch_jacobian<3, P>(vw) : OHP_ERR_SUP;
+}
+template <class P> int launch_project_exact_any(const ohp_assembly_view *vw) {
+  return vw->dim == 2 ? launch_project_exact<2, P>(vw) : vw->dim == 3 ? launch_project_exact<3, P>(vw) : OHP_ERR_SUP;
+}
+
+}  // namespace ohp
+#endif

@@ -1,0 +1,662 @@
+/*
+ * ohp_core.cu -- context, DM construction and the device-side section / CSR build.
+ *
+ * Replaces, on the GPU, what ex12 delegates to PETSc between mesh creation and the solve
+ * (file:line are reference call sites; the algorithms behind them are PETSc-internal):
+ *   DMPlexInterpolate + support-size-1 boundary marking      ex12.cpp:958-1033
+ *   PetscSection (1 dof/vertex, "marker" vertices constrained) ex12.cpp:1309-1321,1237-1239
+ *   DMCreateGlobalVector numbering                            ex12.cpp:1505
+ *   DMCreateMatrix preallocation (CSR with explicit zeros)    ex12.cpp:1508
+ * The Omega_h primitives the reference adapter uses for the same kind of work
+ * (each_eq_to / offset_scan / parallel_for, ex12.cpp:587-588,616,629-647) map to the
+ * mask + scan + compaction kernels below.
+ */
+#include <string.h>
+
+#include <algorithm>
+
+#include "ohp_internal.h"
+
+/* ------------------------------------------------------------------------------------ */
+/* errors                                                                                */
+/* ------------------------------------------------------------------------------------ */
+static thread_local char g_err[1024] = "";
+
+void ohp_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char *ohp_last_error(void) { return g_err; }
+extern "C" int ohp_version(void) { return OHP_VERSION; }
+
+/* ------------------------------------------------------------------------------------ */
+/* context                                                                               */
+/* ------------------------------------------------------------------------------------ */
+extern "C" int ohp_init(int device, ohp_context *out) {
+  if (!out) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_init: null output");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    OHP_FAIL(OHP_ERR_GPU, "ohp_init: no CUDA device (%s); this library has no CPU path",
+             e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (device < 0 || device >= ndev) OHP_FAIL(OHP_ERR_ARG_OUTOFRANGE, "ohp_init: device %d of %d", device, ndev);
+  OHP_CUDA(cudaSetDevice(device));
+  ohp_context c = new ohp_context_s();
+  memset(c, 0, sizeof(*c));
+  c->device = device;
+  c->rank = 0;
+  c->nranks = 1;
+  cudaDeviceProp prop;
+  OHP_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->num_sms = prop.multiProcessorCount;
+  OHP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  OHP_CUDA(cudaMalloc(&c->d_partials, sizeof(double) * kMaxPartials * 2));
+  OHP_CUDA(cudaMalloc(&c->d_ticket, sizeof(unsigned) * 8));
+  OHP_CUDA(cudaMemset(c->d_ticket, 0, sizeof(unsigned) * 8));
+  OHP_CUDA(cudaMalloc(&c->d_scalars, sizeof(double) * 16));
+  OHP_CUDA(cudaMallocHost(&c->h_scalars, sizeof(double) * 16));
+  OHP_CUDA(cudaMalloc(&c->d_cg, sizeof(ohp_cg_state)));
+  OHP_CUDA(cudaMallocHost(&c->h_cg, sizeof(ohp_cg_state)));
+  OHP_CUDA(cudaMalloc(&c->d_flag, sizeof(int)));
+  OHP_CUDA(cudaMemset(c->d_flag, 0, sizeof(int)));
+  *out = c;
+  return 0;
+}
+
+extern "C" int ohp_finalize(ohp_context c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(c->d_partials); cudaFree(c->d_ticket); cudaFree(c->d_scalars);
+  cudaFreeHost(c->h_scalars); cudaFree(c->d_cg); cudaFreeHost(c->h_cg); cudaFree(c->d_flag);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+extern "C" int ohp_device_name(ohp_context c, char *buf, int buflen) {
+  cudaDeviceProp prop;
+  OHP_CUDA(cudaGetDeviceProperties(&prop, c->device));
+  snprintf(buf, buflen, "%s (sm_%d%d, %d SMs)", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
+  return 0;
+}
+extern "C" int ohp_sync(ohp_context c) { OHP_CUDA(cudaStreamSynchronize(c->stream)); return 0; }
+extern "C" int ohp_stream(ohp_context c, void **s) { *s = (void *)c->stream; return 0; }
+extern "C" int ohp_launch_count(ohp_context c, int64_t *n) { *n = c->launches; return 0; }
+
+/* ------------------------------------------------------------------------------------ */
+/* exclusive scan (n inputs -> n+1 outputs, out[n] = total), the shape of Omega_h's      */
+/* offset_scan (ex12.cpp:588,647,717).  Three phases, warp-shuffle block scans.          */
+/* ------------------------------------------------------------------------------------ */
+constexpr int SCAN_T = 512, SCAN_IPT = 8, SCAN_TILE = SCAN_T * SCAN_IPT;
+
+__device__ __forceinline__ int warp_incl_scan(int v) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) >= o) v += t;
+  }
+  return v;
+}
+
+/* exclusive scan of one value per thread across the block; returns the block total via *total */
+__device__ __forceinline__ int block_excl_scan(int v, int *total) {
+  __shared__ int wsum[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int inc = warp_incl_scan(v);
+  if (lane == 31) wsum[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int s = lane < nw ? wsum[lane] : 0;
+    s = warp_incl_scan(s);
+    wsum[lane] = s;
+  }
+  __syncthreads();
+  const int base = wid ? wsum[wid - 1] : 0;
+  *total = wsum[nw - 1];
+  return base + inc - v;
+}
+
+__global__ void __launch_bounds__(SCAN_T) k_scan_tile_sums(const int32_t *in, int64_t n, int32_t *sums) {
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+  int s = 0;
+  for (int i = threadIdx.x; i < SCAN_TILE; i += SCAN_T) {
+    const int64_t g = base + i;
+    if (g < n) s += in[g];
+  }
+  __shared__ int red[SCAN_T / 32];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < SCAN_T / 32; ++w) t += red[w];
+    sums[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(SCAN_T) k_scan_apply(const int32_t *in, int32_t *out, int64_t n,
+                                                       const int32_t *tile_off) {
+  __shared__ int tile[SCAN_TILE];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+  for (int i = threadIdx.x; i < SCAN_TILE; i += SCAN_T) {
+    const int64_t g = base + i;
+    tile[i] = g < n ? in[g] : 0;
+  }
+  __syncthreads();
+  int loc[SCAN_IPT], s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_IPT; ++k) { loc[k] = s; s += tile[threadIdx.x * SCAN_IPT + k]; }
+  int total;
+  const int off = block_excl_scan(s, &total) + (tile_off ? tile_off[blockIdx.x] : 0);
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < SCAN_IPT; ++k) tile[threadIdx.x * SCAN_IPT + k] = loc[k] + off;
+  __syncthreads();
+  for (int i = threadIdx.x; i < SCAN_TILE; i += SCAN_T) {
+    const int64_t g = base + i;
+    if (g < n) out[g] = tile[i];
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0)
+    out[n] = total + (tile_off ? tile_off[blockIdx.x] : 0);
+}
+
+static int scan_rec(ohp_context ctx, const int32_t *in, int32_t *out, int64_t n) {
+  const int64_t nt = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (nt <= 1) {
+    k_scan_apply<<<1, SCAN_T, 0, ctx->stream>>>(in, out, n, nullptr);
+    OHP_CHECK_LAUNCH(ctx);
+    return 0;
+  }
+  int32_t *sums = nullptr;
+  OHP_CUDA(cudaMalloc(&sums, sizeof(int32_t) * (nt + 1)));
+  k_scan_tile_sums<<<(unsigned)nt, SCAN_T, 0, ctx->stream>>>(in, n, sums);
+  OHP_CHECK_LAUNCH(ctx);
+  int rc = scan_rec(ctx, sums, sums, nt);
+  if (!rc) {
+    k_scan_apply<<<(unsigned)nt, SCAN_T, 0, ctx->stream>>>(in, out, n, sums);
+    ctx->launches++;
+    if (cudaGetLastError() != cudaSuccess) rc = OHP_ERR_LIB;
+  }
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(sums);
+  return rc;
+}
+
+int ohp_scan_exclusive_i32(ohp_context ctx, const int32_t *in, int32_t *out, int64_t n, int64_t *total) {
+  if (n == 0) {
+    OHP_CUDA(cudaMemsetAsync(out, 0, sizeof(int32_t), ctx->stream));
+    if (total) *total = 0;
+    return 0;
+  }
+  OHP_TRY(scan_rec(ctx, in, out, n));
+  if (total) {
+    int32_t t = 0;
+    OHP_CUDA(cudaMemcpyAsync(&t, out + n, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    OHP_CUDA(cudaStreamSynchronize(ctx->stream));
+    *total = t;
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* DM creation                                                                           */
+/* ------------------------------------------------------------------------------------ */
+extern "C" int ohp_mesh_create(ohp_context ctx, int dim, int32_t nC, int32_t nV, const int32_t *cells,
+                               const double *coords, ohp_mesh *out) {
+  if (!ctx || !out) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_mesh_create: null argument");
+  if (dim != 2 && dim != 3) OHP_FAIL(OHP_ERR_SUP, "ohp_mesh_create: dim %d (simplices in 2-D/3-D only)", dim);
+  if (nC < 0 || nV < 0) OHP_FAIL(OHP_ERR_ARG_SIZ, "ohp_mesh_create: negative size");
+  if ((int64_t)nC * (dim + 1) >= (int64_t)1 << 29) OHP_FAIL(OHP_ERR_ARG_SIZ, "ohp_mesh_create: too many cells for 32-bit incidence ids");
+  if ((nC && !cells) || (nV && !coords)) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_mesh_create: null arrays");
+  const int nc = dim + 1;
+  for (int64_t i = 0; i < (int64_t)nC * nc; ++i)
+    if (cells[i] < 0 || cells[i] >= nV)
+      OHP_FAIL(OHP_ERR_ARG_OUTOFRANGE, "ohp_mesh_create: cell %lld references vertex %d outside [0,%d)",
+               (long long)(i / nc), cells[i], nV);
+  OHP_CUDA(cudaSetDevice(ctx->device));
+  ohp_mesh m = new ohp_mesh_s();
+  m->ctx = ctx; m->dim = dim; m->nc = nc; m->nC = nC; m->nV = nV;
+  m->cells = nullptr; m->coords = nullptr; m->owned = nullptr; m->setup_done = false;
+  m->v2c_ptr = m->v2c = nullptr; m->bnd = nullptr; m->lidx = m->row_vertex = nullptr; m->ldof_gid = nullptr;
+  m->rowptr = m->colidx = nullptr; m->slot = nullptr; m->tile_row = nullptr; m->halo = nullptr;
+  m->n_owned = m->n_ghost = m->n_bnd = 0; m->n_global = m->row_start = m->nnz = 0; m->max_row = 0; m->n_tiles = 0;
+  OHP_CUDA(cudaMalloc(&m->cells, sizeof(int32_t) * std::max<int64_t>(1, (int64_t)nC * nc)));
+  OHP_CUDA(cudaMalloc(&m->coords, sizeof(double) * std::max<int64_t>(1, (int64_t)nV * dim)));
+  OHP_CUDA(cudaMemcpyAsync(m->cells, cells, sizeof(int32_t) * (int64_t)nC * nc, cudaMemcpyHostToDevice, ctx->stream));
+  OHP_CUDA(cudaMemcpyAsync(m->coords, coords, sizeof(double) * (int64_t)nV * dim, cudaMemcpyHostToDevice, ctx->stream));
+  OHP_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = m;
+  return 0;
+}
+
+extern "C" int ohp_mesh_destroy(ohp_mesh m) {
+  if (!m) return 0;
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  cudaFree(m->cells); cudaFree(m->coords); cudaFree(m->owned); cudaFree(m->v2c_ptr); cudaFree(m->v2c);
+  cudaFree(m->bnd); cudaFree(m->lidx); cudaFree(m->row_vertex); cudaFree(m->ldof_gid); cudaFree(m->rowptr);
+  cudaFree(m->colidx); cudaFree(m->slot); cudaFree(m->tile_row);
+  ohp_halo_free(m->halo);
+  delete m;
+  return 0;
+}
+
+extern "C" int ohp_mesh_set_ghosts(ohp_mesh m, int32_t n, const int32_t *gv, const int32_t *orank,
+                                   const int32_t *overt) {
+  if (!m) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_mesh_set_ghosts: null mesh");
+  if (m->setup_done) OHP_FAIL(OHP_ERR_ORDER, "ohp_mesh_set_ghosts: called after ohp_mesh_setup");
+  if (n > 0 && m->ctx->nranks == 1) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_mesh_set_ghosts: %d leaves but no communicator attached", n);
+  for (int i = 0; i < n; ++i) {
+    if (gv[i] < 0 || gv[i] >= m->nV) OHP_FAIL(OHP_ERR_ARG_OUTOFRANGE, "ohp_mesh_set_ghosts: leaf %d vertex %d", i, gv[i]);
+    if (orank[i] < 0 || orank[i] >= m->ctx->nranks || orank[i] == m->ctx->rank)
+      OHP_FAIL(OHP_ERR_ARG_OUTOFRANGE, "ohp_mesh_set_ghosts: leaf %d owner rank %d", i, orank[i]);
+  }
+  m->ghost_vertex.assign(gv, gv + n);
+  m->ghost_owner_rank.assign(orank, orank + n);
+  m->ghost_owner_vertex.assign(overt, overt + n);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* setup kernels                                                                         */
+/* ------------------------------------------------------------------------------------ */
+__global__ void k_count_incidence(const int32_t *cells, int64_t n, int32_t *deg) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(deg + cells[i], 1);
+}
+
+__global__ void k_fill_v2c(const int32_t *cells, int nc, int64_t n, const int32_t *ptr, int32_t *cursor,
+                           int32_t *v2c) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int v = cells[i];
+  const int c = (int)(i / nc), b = (int)(i - (int64_t)c * nc);
+  const int pos = atomicAdd(cursor + v, 1);
+  v2c[ptr[v] + pos] = c * 4 + b;
+}
+
+/* the atomic fill order is arbitrary: sort every star ascending so that downstream
+ * summation order (and therefore every assembled value) is deterministic */
+__global__ void k_sort_v2c(const int32_t *ptr, int32_t *v2c, int nV) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nV) return;
+  const int a = ptr[v], b = ptr[v + 1];
+  for (int i = a + 1; i < b; ++i) {
+    const int x = v2c[i];
+    int j = i - 1;
+    while (j >= a && v2c[j] > x) { v2c[j + 1] = v2c[j]; --j; }
+    v2c[j + 1] = x;
+  }
+}
+
+/* facet (cell minus one vertex) is on the boundary iff exactly one cell contains it
+ * (DMPlexGetSupportSize == 1, ex12.cpp:986-997); its vertices get "marker" = 1
+ * (ex12.cpp:1001-1010,1023-1026).  The support is counted inside star(facet vertex 0). */
+template <int NC>
+__global__ void k_mark_boundary(const int32_t *cells, int nC, const int32_t *ptr, const int32_t *v2c, uint8_t *bnd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nC) return;
+  int cv[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) cv[j] = cells[(size_t)c * NC + j];
+#pragma unroll
+  for (int skip = 0; skip < NC; ++skip) {
+    int fv[NC - 1], nf = 0;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) if (j != skip) fv[nf++] = cv[j];
+    int support = 0;
+    for (int k = ptr[fv[0]]; k < ptr[fv[0] + 1]; ++k) {
+      const int oc = v2c[k] >> 2;
+      int ov[NC];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) ov[j] = cells[(size_t)oc * NC + j];
+      bool all = true;
+#pragma unroll
+      for (int a = 1; a < NC - 1; ++a) {
+        bool found = false;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) found |= (ov[j] == fv[a]);
+        all &= found;
+      }
+      support += all ? 1 : 0;
+    }
+    if (support == 1) {
+#pragma unroll
+      for (int a = 0; a < NC - 1; ++a) bnd[fv[a]] = 1; /* same-value write race, as ex12.cpp:636-644 */
+    }
+  }
+}
+
+__global__ void k_free_mask(const uint8_t *bnd, const uint8_t *owned, int nV, int32_t *mask, int32_t *bmask) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nV) return;
+  mask[v] = (owned[v] && !bnd[v]) ? 1 : 0;
+  bmask[v] = bnd[v] ? 1 : 0;
+}
+
+__global__ void k_assign_rows(const int32_t *mask, const int32_t *scan, int nV, int32_t *lidx, int32_t *row_vertex) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nV) return;
+  if (mask[v]) { lidx[v] = scan[v]; row_vertex[scan[v]] = v; }
+  else lidx[v] = -1;
+}
+
+/* One warp per row: gather the local dofs of every vertex of every star cell, bitonic-sort them
+ * in shared memory, then count (fill == 0) or write (fill == 1) the unique ones. */
+constexpr int PAT_CAP = 512, PAT_WARPS = 8;
+template <int NC>
+__global__ void __launch_bounds__(PAT_WARPS * 32)
+k_row_pattern(const int32_t *cells, const int32_t *ptr, const int32_t *v2c, const int32_t *lidx,
+              const int32_t *row_vertex, int n_rows, int fill, int32_t *rowlen, const int32_t *rowptr,
+              int32_t *colidx, int *err) {
+  __shared__ int32_t s_keys[PAT_WARPS][PAT_CAP];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int r = blockIdx.x * PAT_WARPS + wid;
+  if (r >= n_rows) return;
+  int32_t *a = s_keys[wid];
+  const int v = row_vertex[r];
+  const int k0 = ptr[v], deg = ptr[v + 1] - k0;
+  const int ncand = deg * NC;
+  if (ncand > PAT_CAP) { if (lane == 0) atomicExch(err, 1); return; }
+  int P = 32;
+  while (P < ncand) P <<= 1;
+  for (int i = lane; i < P; i += 32) {
+    int key = 0x7fffffff;
+    if (i < ncand) {
+      const int c = v2c[k0 + i / NC] >> 2;
+      const int g = lidx[cells[(size_t)c * NC + (i % NC)]];
+      if (g >= 0) key = g;
+    }
+    a[i] = key;
+  }
+  __syncwarp();
+  for (int k = 2; k <= P; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < P; i += 32) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const int x = a[i], y = a[ixj];
+          const bool up = ((i & k) == 0);
+          if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+        }
+      }
+      __syncwarp();
+    }
+  int count = 0;
+  const int base_out = fill ? rowptr[r] : 0;
+  for (int base = 0; base < P; base += 32) {
+    const int i = base + lane;
+    const int x = a[i];
+    const int prev = i > 0 ? a[i - 1] : -1;
+    const bool isnew = (x != 0x7fffffff) && (x != prev);
+    const unsigned m = __ballot_sync(0xffffffffu, isnew);
+    if (fill && isnew) colidx[base_out + count + __popc(m & ((1u << lane) - 1u))] = x;
+    count += __popc(m);
+  }
+  if (!fill && lane == 0) rowlen[r] = count;
+}
+
+/* element -> row scatter map, stored from the row's side: for every incidence (v, c) of a row
+ * vertex and every vertex j of c, the position of column lidx[c_j] inside row(v), or 255 */
+template <int NC>
+__global__ void k_slot_map(const int32_t *cells, const int32_t *ptr, const int32_t *v2c, const int32_t *lidx,
+                           const int32_t *row_vertex, int n_rows, const int32_t *rowptr,
+                           const int32_t *colidx, uint8_t *slot, int *err) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const int v = row_vertex[r];
+  const int a = rowptr[r], len = rowptr[r + 1] - a;
+  if (len > 254) { atomicExch(err, 2); return; }
+  for (int k = ptr[v]; k < ptr[v + 1]; ++k) {
+    const int c = v2c[k] >> 2;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const int g = lidx[cells[(size_t)c * NC + j]];
+      int s = 255;
+      if (g >= 0) {
+        int lo = 0, hi = len - 1;
+        while (lo <= hi) {
+          const int mid = (lo + hi) >> 1;
+          const int x = colidx[a + mid];
+          if (x < g) lo = mid + 1; else if (x > g) hi = mid - 1; else { s = mid; break; }
+        }
+        if (s == 255) atomicExch(err, 3);
+      }
+      slot[(size_t)k * NC + j] = (uint8_t)s;
+    }
+  }
+}
+
+__global__ void k_max_rowlen(const int32_t *rowptr, int n_rows, int32_t *out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  int len = r < n_rows ? rowptr[r + 1] - rowptr[r] : 0;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+  if ((threadIdx.x & 31) == 0 && len > 0) atomicMax(out, len);
+}
+
+/* first row whose rowptr is >= t * tile: rows [tile_row[t], tile_row[t+1]) form SpMV tile t */
+__global__ void k_tile_rows(const int32_t *rowptr, int n_rows, int tile, int n_tiles, int32_t *tile_row) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > n_tiles) return;
+  if (t == n_tiles) { tile_row[t] = n_rows; return; }
+  const int64_t target = (int64_t)t * tile;
+  int lo = 0, hi = n_rows;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (rowptr[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  tile_row[t] = lo;
+}
+
+__global__ void k_fill_u8(uint8_t *p, int n, uint8_t val) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = val;
+}
+__global__ void k_clear_owned(uint8_t *owned, const int32_t *gv, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) owned[gv[i]] = 0;
+}
+__global__ void k_u8_to_i32(const uint8_t *in, int32_t *out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+__global__ void k_i32_to_u8_ghost(const int32_t *in, const uint8_t *owned, uint8_t *out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && !owned[i]) out[i] = (uint8_t)(in[i] != 0);
+}
+__global__ void k_owned_gid(int64_t *gid, int n, int64_t start) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) gid[i] = start + i;
+}
+
+static inline unsigned nblk(int64_t n, int bs) { return (unsigned)std::max<int64_t>(1, (n + bs - 1) / bs); }
+
+static int check_flag(ohp_context ctx, const char *what) {
+  int flag = 0;
+  OHP_CUDA(cudaMemcpyAsync(&flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  OHP_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (flag) {
+    cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream);
+    OHP_FAIL(OHP_ERR_SUP, "%s: device-side limit exceeded (code %d: 1 = vertex star too large for the pattern sort, "
+             "2 = row longer than 254, 3 = inconsistent pattern)", what, flag);
+  }
+  return 0;
+}
+
+extern "C" int ohp_mesh_setup(ohp_mesh m) {
+  if (!m) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_mesh_setup: null mesh");
+  if (m->setup_done) return 0;
+  ohp_context ctx = m->ctx;
+  OHP_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int nc = m->nc, nV = m->nV, nC = m->nC;
+  const int64_t ninc = (int64_t)nC * nc;
+  const int BS = 256;
+
+  /* ownership: every vertex that is not an SF leaf */
+  OHP_CUDA(cudaMalloc(&m->owned, std::max(1, nV)));
+  k_fill_u8<<<nblk(nV, BS), BS, 0, st>>>(m->owned, nV, 1); OHP_CHECK_LAUNCH(ctx);
+  const int nleaf = (int)m->ghost_vertex.size();
+  if (nleaf) {
+    int32_t *d_gv;
+    OHP_CUDA(cudaMalloc(&d_gv, sizeof(int32_t) * nleaf));
+    OHP_CUDA(cudaMemcpyAsync(d_gv, m->ghost_vertex.data(), sizeof(int32_t) * nleaf, cudaMemcpyHostToDevice, st));
+    k_clear_owned<<<nblk(nleaf, BS), BS, 0, st>>>(m->owned, d_gv, nleaf); OHP_CHECK_LAUNCH(ctx);
+    OHP_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_gv);
+  }
+
+  /* vertex -> cell stars */
+  int32_t *deg;
+  OHP_CUDA(cudaMalloc(&deg, sizeof(int32_t) * (nV + 1)));
+  OHP_CUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nV + 1), st));
+  OHP_CUDA(cudaMalloc(&m->v2c_ptr, sizeof(int32_t) * (nV + 1)));
+  OHP_CUDA(cudaMalloc(&m->v2c, sizeof(int32_t) * std::max<int64_t>(1, ninc)));
+  if (ninc) { k_count_incidence<<<nblk(ninc, BS), BS, 0, st>>>(m->cells, ninc, deg); OHP_CHECK_LAUNCH(ctx); }
+  OHP_TRY(ohp_scan_exclusive_i32(ctx, deg, m->v2c_ptr, nV, nullptr));
+  OHP_CUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nV + 1), st));
+  if (ninc) { k_fill_v2c<<<nblk(ninc, BS), BS, 0, st>>>(m->cells, nc, ninc, m->v2c_ptr, deg, m->v2c); OHP_CHECK_LAUNCH(ctx); }
+  k_sort_v2c<<<nblk(nV, BS), BS, 0, st>>>(m->v2c_ptr, m->v2c, nV); OHP_CHECK_LAUNCH(ctx);
+
+  /* boundary label */
+  OHP_CUDA(cudaMalloc(&m->bnd, std::max(1, nV)));
+  OHP_CUDA(cudaMemsetAsync(m->bnd, 0, std::max(1, nV), st));
+  if (nC) {
+    if (nc == 3) k_mark_boundary<3><<<nblk(nC, BS), BS, 0, st>>>(m->cells, nC, m->v2c_ptr, m->v2c, m->bnd);
+    else k_mark_boundary<4><<<nblk(nC, BS), BS, 0, st>>>(m->cells, nC, m->v2c_ptr, m->v2c, m->bnd);
+    OHP_CHECK_LAUNCH(ctx);
+  }
+  int32_t *tmp_a, *tmp_b;
+  OHP_CUDA(cudaMalloc(&tmp_a, sizeof(int32_t) * (nV + 1)));
+  OHP_CUDA(cudaMalloc(&tmp_b, sizeof(int32_t) * (nV + 1)));
+  if (ctx->nranks > 1) {
+    /* a ghost vertex's star is incomplete here: take its label from the owner (hazard H2) */
+    k_u8_to_i32<<<nblk(nV, BS), BS, 0, st>>>(m->bnd, tmp_a, nV); OHP_CHECK_LAUNCH(ctx);
+    OHP_TRY(ohp_vertex_halo_i32(m, tmp_a));
+    k_i32_to_u8_ghost<<<nblk(nV, BS), BS, 0, st>>>(tmp_a, m->owned, m->bnd, nV); OHP_CHECK_LAUNCH(ctx);
+  }
+
+  /* section: owned unconstrained vertices, ascending local point order */
+  k_free_mask<<<nblk(nV, BS), BS, 0, st>>>(m->bnd, m->owned, nV, tmp_a, tmp_b); OHP_CHECK_LAUNCH(ctx);
+  int64_t n_owned = 0, n_bnd = 0;
+  OHP_TRY(ohp_scan_exclusive_i32(ctx, tmp_b, deg, nV, &n_bnd));
+  OHP_TRY(ohp_scan_exclusive_i32(ctx, tmp_a, deg, nV, &n_owned));
+  m->n_owned = (int32_t)n_owned; m->n_bnd = (int32_t)n_bnd;
+  OHP_CUDA(cudaMalloc(&m->lidx, sizeof(int32_t) * std::max(1, nV)));
+  OHP_CUDA(cudaMalloc(&m->row_vertex, sizeof(int32_t) * std::max(1, m->n_owned)));
+  k_assign_rows<<<nblk(nV, BS), BS, 0, st>>>(tmp_a, deg, nV, m->lidx, m->row_vertex); OHP_CHECK_LAUNCH(ctx);
+  OHP_CUDA(cudaStreamSynchronize(st));
+  cudaFree(tmp_a); cudaFree(tmp_b); cudaFree(deg);
+
+  /* global numbering: ranks concatenated in rank order; ghost dofs + halo plan */
+  m->row_start = 0; m->n_global = m->n_owned; m->n_ghost = 0;
+  if (ctx->nranks > 1) OHP_TRY(ohp_halo_build(m)); /* sets row_start, n_global, n_ghost, ghost lidx, ldof_gid */
+  else {
+    OHP_CUDA(cudaMalloc(&m->ldof_gid, sizeof(int64_t) * std::max(1, m->n_owned)));
+    k_owned_gid<<<nblk(m->n_owned, BS), BS, 0, st>>>(m->ldof_gid, m->n_owned, 0); OHP_CHECK_LAUNCH(ctx);
+  }
+
+  /* CSR pattern: count, scan, fill */
+  const int N = m->n_owned;
+  int32_t *rowlen;
+  OHP_CUDA(cudaMalloc(&rowlen, sizeof(int32_t) * (N + 1)));
+  OHP_CUDA(cudaMalloc(&m->rowptr, sizeof(int32_t) * (N + 1)));
+  if (N) {
+    if (nc == 3) k_row_pattern<3><<<nblk(N, PAT_WARPS), PAT_WARPS * 32, 0, st>>>(m->cells, m->v2c_ptr, m->v2c, m->lidx, m->row_vertex, N, 0, rowlen, nullptr, nullptr, ctx->d_flag);
+    else k_row_pattern<4><<<nblk(N, PAT_WARPS), PAT_WARPS * 32, 0, st>>>(m->cells, m->v2c_ptr, m->v2c, m->lidx, m->row_vertex, N, 0, rowlen, nullptr, nullptr, ctx->d_flag);
+    OHP_CHECK_LAUNCH(ctx);
+  }
+  OHP_TRY(check_flag(ctx, "ohp_mesh_setup (pattern count)"));
+  OHP_TRY(ohp_scan_exclusive_i32(ctx, rowlen, m->rowptr, N, &m->nnz));
+  cudaFree(rowlen);
+  OHP_CUDA(cudaMalloc(&m->colidx, sizeof(int32_t) * std::max<int64_t>(1, m->nnz)));
+  OHP_CUDA(cudaMalloc(&m->slot, std::max<int64_t>(1, ninc * nc)));
+  OHP_CUDA(cudaMemsetAsync(m->slot, 0xff, std::max<int64_t>(1, ninc * nc), st));
+  if (N) {
+    if (nc == 3) k_row_pattern<3><<<nblk(N, PAT_WARPS), PAT_WARPS * 32, 0, st>>>(m->cells, m->v2c_ptr, m->v2c, m->lidx, m->row_vertex, N, 1, nullptr, m->rowptr, m->colidx, ctx->d_flag);
+    else k_row_pattern<4><<<nblk(N, PAT_WARPS), PAT_WARPS * 32, 0, st>>>(m->cells, m->v2c_ptr, m->v2c, m->lidx, m->row_vertex, N, 1, nullptr, m->rowptr, m->colidx, ctx->d_flag);
+    OHP_CHECK_LAUNCH(ctx);
+    if (nc == 3) k_slot_map<3><<<nblk(N, 128), 128, 0, st>>>(m->cells, m->v2c_ptr, m->v2c, m->lidx, m->row_vertex, N, m->rowptr, m->colidx, m->slot, ctx->d_flag);
+    else k_slot_map<4><<<nblk(N, 128), 128, 0, st>>>(m->cells, m->v2c_ptr, m->v2c, m->lidx, m->row_vertex, N, m->rowptr, m->colidx, m->slot, ctx->d_flag);
+    OHP_CHECK_LAUNCH(ctx);
+  }
+  OHP_TRY(check_flag(ctx, "ohp_mesh_setup (pattern fill)"));
+
+  /* longest row + SpMV tiles */
+  int32_t *d_max;
+  OHP_CUDA(cudaMalloc(&d_max, sizeof(int32_t)));
+  OHP_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int32_t), st));
+  if (N) { k_max_rowlen<<<nblk(N, BS), BS, 0, st>>>(m->rowptr, N, d_max); OHP_CHECK_LAUNCH(ctx); }
+  OHP_CUDA(cudaMemcpyAsync(&m->max_row, d_max, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  OHP_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_max);
+  m->n_tiles = (int32_t)((m->nnz + kSpmvTile - 1) / kSpmvTile);
+  if (m->n_tiles == 0 && N > 0) m->n_tiles = 1;
+  OHP_CUDA(cudaMalloc(&m->tile_row, sizeof(int32_t) * (m->n_tiles + 1)));
+  k_tile_rows<<<nblk(m->n_tiles + 1, BS), BS, 0, st>>>(m->rowptr, N, kSpmvTile, m->n_tiles, m->tile_row); OHP_CHECK_LAUNCH(ctx);
+  OHP_CUDA(cudaStreamSynchronize(st));
+  m->setup_done = true;
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* getters                                                                               */
+/* ------------------------------------------------------------------------------------ */
+#define NEED_SETUP(m, name)                                                     \
+  do {                                                                          \
+    if (!(m)) OHP_FAIL(OHP_ERR_ARG_WRONG, name ": null mesh");                  \
+    if (!(m)->setup_done) OHP_FAIL(OHP_ERR_ORDER, name ": ohp_mesh_setup has not been called"); \
+    OHP_CUDA(cudaSetDevice((m)->ctx->device));                                  \
+  } while (0)
+
+extern "C" int ohp_mesh_get_info(ohp_mesh m, ohp_mesh_info *info) {
+  NEED_SETUP(m, "ohp_mesh_get_info");
+  info->dim = m->dim; info->n_cells = m->nC; info->n_verts = m->nV; info->n_boundary_verts = m->n_bnd;
+  info->n_owned = m->n_owned; info->n_ghost = m->n_ghost; info->n_global = m->n_global;
+  info->row_start = m->row_start; info->nnz = m->nnz; info->max_row = m->max_row;
+  return 0;
+}
+
+extern "C" int ohp_mesh_get_boundary(ohp_mesh m, uint8_t *bnd) {
+  NEED_SETUP(m, "ohp_mesh_get_boundary");
+  OHP_CUDA(cudaMemcpyAsync(bnd, m->bnd, m->nV, cudaMemcpyDeviceToHost, m->ctx->stream));
+  OHP_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  return 0;
+}
+
+extern "C" int ohp_mesh_get_numbering(ohp_mesh m, int64_t *gidx) {
+  NEED_SETUP(m, "ohp_mesh_get_numbering");
+  std::vector<int32_t> lidx(m->nV);
+  std::vector<int64_t> gid(m->n_owned + m->n_ghost);
+  OHP_CUDA(cudaMemcpyAsync(lidx.data(), m->lidx, sizeof(int32_t) * m->nV, cudaMemcpyDeviceToHost, m->ctx->stream));
+  OHP_CUDA(cudaMemcpyAsync(gid.data(), m->ldof_gid, sizeof(int64_t) * gid.size(), cudaMemcpyDeviceToHost, m->ctx->stream));
+  OHP_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  for (int v = 0; v < m->nV; ++v) gidx[v] = lidx[v] >= 0 ? gid[lidx[v]] : -1;
+  return 0;
+}
+
+extern "C" int ohp_mesh_get_csr(ohp_mesh m, int32_t *rowptr, int64_t *colidx) {
+  NEED_SETUP(m, "ohp_mesh_get_csr");
+  std::vector<int32_t> col(m->nnz);
+  std::vector<int64_t> gid(m->n_owned + m->n_ghost);
+  OHP_CUDA(cudaMemcpyAsync(rowptr, m->rowptr, sizeof(int32_t) * (m->n_owned + 1), cudaMemcpyDeviceToHost, m->ctx->stream));
+  OHP_CUDA(cudaMemcpyAsync(col.data(), m->colidx, sizeof(int32_t) * m->nnz, cudaMemcpyDeviceToHost, m->ctx->stream));
+  OHP_CUDA(cudaMemcpyAsync(gid.data(), m->ldof_gid, sizeof(int64_t) * gid.size(), cudaMemcpyDeviceToHost, m->ctx->stream));
+  OHP_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  for (int64_t k = 0; k < m->nnz; ++k) colidx[k] = gid[col[k]];
+  return 0;
+}
+
+int ohp_assembly_view_make(ohp_mesh m, const double *u, double *out, ohp_assembly_view *vw) {
+  vw->dim = m->dim; vw->n_cells = m->nC; vw->n_verts = m->nV; vw->n_rows = m->n_owned;
+  vw->cells_dev = m->cells; vw->coords_dev = m->coords; vw->lidx_dev = m->lidx;
+  vw->row_vertex_dev = m->row_vertex; vw->v2c_ptr_dev = m->v2c_ptr; vw->v2c_dev = m->v2c;
+  vw->slot_dev = m->slot; vw->rowptr_dev = m->rowptr; vw->u_dev = u; vw->out_dev = out;
+  vw->stream = (void *)m->ctx->stream;
+  return 0;
+}

@@ -1,0 +1,143 @@
+/* Internal declarations of libohp.so (not part of the C-ABI). */
+#ifndef OHP_INTERNAL_H
+#define OHP_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <vector>
+
+#include "ohp.h"
+
+void ohp_set_error(const char *fmt, ...);
+
+#define OHP_FAIL(code, ...)      \
+  do {                           \
+    ohp_set_error(__VA_ARGS__);  \
+    return (code);               \
+  } while (0)
+
+#define OHP_CUDA(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      OHP_FAIL(OHP_ERR_LIB, "%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr,             \
+               cudaGetErrorString(e__));                                                      \
+  } while (0)
+
+#define OHP_TRY(expr)                 \
+  do {                                \
+    int rc__ = (expr);                \
+    if (rc__) return rc__;            \
+  } while (0)
+
+#define OHP_CHECK_LAUNCH(ctx)                                                                 \
+  do {                                                                                        \
+    (ctx)->launches++;                                                                        \
+    cudaError_t e__ = cudaGetLastError();                                                     \
+    if (e__ != cudaSuccess)                                                                   \
+      OHP_FAIL(OHP_ERR_LIB, "%s:%d kernel launch failed: %s", __FILE__, __LINE__,             \
+               cudaGetErrorString(e__));                                                      \
+  } while (0)
+
+/* device-side scalar block of the CG recurrence (lives in HBM, polled by the host) */
+struct ohp_cg_state {
+  double beta, betaold, dpi, alpha, dp, rnorm0, ttol;
+  double rtol, abstol, dtol;
+  int its, reason, maxit, done;
+};
+
+struct ohp_halo;  /* ohp_comm.cu */
+
+struct ohp_context_s {
+  int device;
+  int num_sms;
+  cudaStream_t stream;
+  int64_t launches;
+  /* reduction scratch */
+  double *d_partials;   /* kMaxPartials * 2 */
+  unsigned *d_ticket;   /* last-block ticket counters */
+  double *d_scalars;    /* results of reductions */
+  double *h_scalars;    /* pinned */
+  ohp_cg_state *d_cg;
+  ohp_cg_state *h_cg;   /* pinned */
+  int *d_flag;          /* device error flag for setup kernels */
+  /* communicator (NULL = serial) */
+  void *nccl_lib;
+  void *comm;
+  int rank, nranks;
+};
+
+constexpr int kMaxPartials = 1 << 16;
+constexpr int kSpmvTile = 4096;     /* nnz per CSR-stream tile */
+constexpr int kSpmvThreads = 256;
+
+struct ohp_mesh_s {
+  ohp_context ctx;
+  int dim, nc;
+  int32_t nC, nV;
+  int32_t *cells;   /* device */
+  double *coords;   /* device */
+  /* point SF (host copies) */
+  std::vector<int32_t> ghost_vertex, ghost_owner_rank, ghost_owner_vertex;
+  uint8_t *owned;   /* device, per vertex */
+  bool setup_done;
+  /* topology */
+  int32_t *v2c_ptr, *v2c;
+  uint8_t *bnd;
+  /* section */
+  int32_t *lidx;        /* per vertex local dof (-1 constrained) */
+  int32_t *row_vertex;  /* per owned row */
+  int64_t *ldof_gid;    /* per local dof (owned + ghost): global id */
+  int32_t n_owned, n_ghost, n_bnd;
+  int64_t n_global, row_start;
+  /* CSR */
+  int32_t *rowptr, *colidx;
+  uint8_t *slot;
+  int64_t nnz;
+  int32_t max_row;
+  /* SpMV tiling */
+  int32_t *tile_row; /* n_tiles+1: first row of each nnz tile */
+  int32_t n_tiles;
+  ohp_halo *halo;    /* dof-level halo plan (NULL when serial) */
+};
+
+struct ohp_vec_s {
+  ohp_mesh mesh;
+  double *d;    /* n_owned + n_ghost */
+  int32_t n;    /* n_owned */
+};
+
+struct ohp_mat_s {
+  ohp_mesh mesh;
+  double *vals;
+  /* CG work vectors, allocated on first solve */
+  double *r, *z, *p, *w, *dinv;
+  double *hist;
+  int32_t hist_cap;
+};
+
+/* ohp_core.cu */
+int ohp_scan_exclusive_i32(ohp_context ctx, const int32_t *in, int32_t *out, int64_t n, int64_t *total);
+int ohp_assembly_view_make(ohp_mesh mesh, const double *u, double *out, ohp_assembly_view *vw);
+
+/* ohp_comm.cu */
+int ohp_halo_build(ohp_mesh mesh);
+void ohp_halo_free(ohp_halo *h);
+/* fill the ghost tail x[n_owned ..] from the owners (on the context stream) */
+int ohp_halo_exchange(ohp_mesh mesh, double *x);
+int ohp_allreduce_sum(ohp_context ctx, double *d_vals, int n);
+int ohp_vertex_halo_i32(ohp_mesh mesh, int32_t *vertex_data_dev);
+int ohp_allgather_i64(ohp_context ctx, int64_t mine, std::vector<int64_t> &all);
+
+/* ohp_linalg.cu */
+int ohp_spmv_launch(ohp_mat A, const double *x, double *y);
+
+/* ohp_problems.cu */
+int ohp_problem_lookup(int id, ohp_assembly_launcher *res, ohp_assembly_launcher *jac,
+                       ohp_assembly_launcher *proj);
+int ohp_l2_error_builtin(ohp_mesh mesh, int problem, const double *u, double *err);
+
+#endif

@@ -1,0 +1,534 @@
+/*
+ * ohp_linalg.cu -- Vec / Mat kernels and the CG solve.
+ *
+ * Replaces [PETSc-internal] MatMult_SeqAIJ/MPIAIJ, VecDot/Norm/AXPY/AYPX/Set/Chop (used
+ * directly at ex12.cpp:1626-1675 and inside KSP) and KSPSolve_CG (selected by -ksp_type cg
+ * at ex12.cpp:1543; tolerances of the reference CTests at CMakeLists.txt:53).
+ *
+ * Everything is HBM-bandwidth bound, FP64, no tensor cores:
+ *   - SpMV is CSR-stream: a block streams one tile of vals/colidx fully coalesced, leaves the
+ *     products in shared memory, then each thread sums whole rows in column order (the same
+ *     order as a serial CSR loop).  (p, Ap) is fused into the same kernel.
+ *   - axpy-type updates are fused with the dot products they feed.
+ *   - reductions are two-stage and deterministic: per-block partials, summed in a fixed order by
+ *     the last block to arrive (ticket counter); the CG scalars (alpha, beta, norms, iteration
+ *     count, converged reason) live in HBM and are updated by that last block, so an
+ *     iteration needs no host round trip.  The host polls the `done` flag every
+ *     `check_every` iterations; kernels launched past convergence return immediately.
+ */
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "ohp_internal.h"
+
+static inline unsigned nblk(int64_t n, int bs) { return (unsigned)std::max<int64_t>(1, (n + bs - 1) / bs); }
+
+/* ------------------------------------------------------------------------------------ */
+/* block reduction + last-block ticket                                                   */
+/* ------------------------------------------------------------------------------------ */
+template <int NV> __device__ __forceinline__ void block_sum(double (&v)[NV], double *s_red /* NV*32 */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if (lane == 0) s_red[k * 32 + wid] = v[k];
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double t = lane < nw ? s_red[k * 32 + lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      v[k] = t;
+    }
+  }
+  __syncthreads();
+}
+
+/* returns true in every thread of the last block to arrive, with the grid totals in v
+ * (valid in thread 0).  Summation order is fixed => bitwise reproducible. */
+template <int NV>
+__device__ __forceinline__ bool grid_sum(double (&v)[NV], double *partials, unsigned *ticket) {
+  __shared__ double s_red[NV * 32];
+  __shared__ bool s_last;
+  block_sum<NV>(v, s_red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) partials[(size_t)blockIdx.x * NV + k] = v[k];
+    __threadfence();
+    const unsigned t = atomicInc(ticket, gridDim.x - 1); /* wraps back to 0: self-resetting */
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = 0.0;
+  for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] += __ldcg(partials + (size_t)b * NV + k);
+  }
+  block_sum<NV>(v, s_red);
+  return true;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* CG scalar recurrences (KSPSolve_CG + KSPConvergedDefault), run by one thread          */
+/* ------------------------------------------------------------------------------------ */
+__device__ __forceinline__ void cg_converged(ohp_cg_state *st, double dp) {
+  if (dp != dp) st->reason = -9;                                  /* KSP_DIVERGED_NANORINF */
+  else if (dp <= st->ttol) st->reason = (dp < st->abstol) ? 3 : 2; /* ATOL : RTOL */
+  else if (st->its > 0 && dp >= st->dtol * st->rnorm0) st->reason = -4;
+}
+__device__ __forceinline__ void cg_loop_head(ohp_cg_state *st) {
+  /* `while (!reason && i < maxit) { if (beta == 0) -> CONVERGED_ATOL ...` */
+  if (!st->reason && st->its >= st->maxit) st->reason = -3;
+  if (!st->reason && st->beta == 0.0) st->reason = 3;
+  if (st->reason) st->done = 1;
+}
+__device__ void cg_fin_init(ohp_cg_state *st, double zz, double zr, double *hist) {
+  const double dp = sqrt(zz);
+  st->dp = dp; st->rnorm0 = dp; st->ttol = fmax(st->rtol * dp, st->abstol);
+  st->beta = zr; st->betaold = 1.0; st->its = 0; st->reason = 0; st->done = 0;
+  if (hist) hist[0] = dp;
+  cg_converged(st, dp);
+  cg_loop_head(st);
+}
+__device__ void cg_fin_spmv(ohp_cg_state *st, double dpi) {
+  st->dpi = dpi;
+  st->betaold = st->beta;
+  if (!(dpi > 0.0)) { st->reason = (dpi != dpi) ? -9 : -8; st->its += 1; st->done = 1; return; }
+  st->alpha = st->beta / dpi;
+}
+__device__ void cg_fin_update(ohp_cg_state *st, double zz, double zr, double *hist, int hist_cap) {
+  const double dp = sqrt(zz);
+  st->dp = dp;
+  st->its += 1;
+  if (hist && st->its < hist_cap) hist[st->its] = dp;
+  cg_converged(st, dp);
+  if (!st->reason) st->beta = zr;
+  cg_loop_head(st);
+}
+
+__global__ void k_cg_fin(ohp_cg_state *st, const double *sums, int which, double *hist, int hist_cap) {
+  if (which != 0 && st->done) return;
+  if (which == 0) cg_fin_init(st, sums[0], sums[1], hist);
+  else if (which == 1) cg_fin_spmv(st, sums[0]);
+  else cg_fin_update(st, sums[0], sums[1], hist, hist_cap);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* SpMV (CSR-stream) with optional fused (x, y) dot                                      */
+/* ------------------------------------------------------------------------------------ */
+template <bool CG>
+__global__ void __launch_bounds__(kSpmvThreads)
+k_spmv_stream(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+              const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+              const int32_t *__restrict__ tile_row, int n_tiles, ohp_cg_state *st, double *partials,
+              unsigned *ticket, double *sums, int fin_inline) {
+  extern __shared__ double s_prod[];
+  if (CG && st->done) return;
+  double dot[1] = {0.0};
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int r0 = __ldg(tile_row + t), r1 = __ldg(tile_row + t + 1);
+    if (r0 == r1) continue;
+    const int k0 = __ldg(rowptr + r0), k1 = __ldg(rowptr + r1);
+    for (int k = k0 + threadIdx.x; k < k1; k += kSpmvThreads)
+      s_prod[k - k0] = __ldcs(vals + k) * x[__ldcs(colidx + k)];
+    __syncthreads();
+    for (int r = r0 + threadIdx.x; r < r1; r += kSpmvThreads) {
+      const int a = __ldg(rowptr + r) - k0, b = __ldg(rowptr + r + 1) - k0;
+      double s = 0.0;
+      for (int i = a; i < b; ++i) s += s_prod[i];
+      y[r] = s;
+      if (CG) dot[0] += s * x[r];
+    }
+    __syncthreads();
+  }
+  if (CG) {
+    if (grid_sum<1>(dot, partials, ticket) && threadIdx.x == 0) {
+      sums[0] = dot[0];
+      if (fin_inline) cg_fin_spmv(st, dot[0]);
+    }
+  }
+}
+
+static int spmv_smem_bytes(ohp_mesh m) { return (int)sizeof(double) * (kSpmvTile + std::max(1, m->max_row)); }
+
+static int spmv_configure(ohp_mesh m) {
+  const int bytes = spmv_smem_bytes(m);
+  if (bytes > 200 * 1024) OHP_FAIL(OHP_ERR_SUP, "SpMV: longest row %d exceeds the shared-memory tile", m->max_row);
+  static int configured_bytes = 0;
+  if (bytes > configured_bytes) {
+    OHP_CUDA(cudaFuncSetAttribute(k_spmv_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    OHP_CUDA(cudaFuncSetAttribute(k_spmv_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    configured_bytes = bytes;
+  }
+  return 0;
+}
+
+int ohp_spmv_launch(ohp_mat A, const double *x, double *y) {
+  ohp_mesh m = A->mesh;
+  ohp_context ctx = m->ctx;
+  if (m->n_owned == 0) return 0;
+  OHP_TRY(spmv_configure(m));
+  const int grid = std::min(m->n_tiles, kMaxPartials);
+  k_spmv_stream<false><<<grid, kSpmvThreads, spmv_smem_bytes(m), ctx->stream>>>(
+      m->rowptr, m->colidx, A->vals, x, y, m->tile_row, m->n_tiles, nullptr, nullptr, nullptr, nullptr, 0);
+  OHP_CHECK_LAUNCH(ctx);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Vec                                                                                   */
+/* ------------------------------------------------------------------------------------ */
+__global__ void k_set(double *x, int n, double a) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] = a;
+}
+__global__ void k_axpy(double *y, const double *x, int n, double a) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] += a * x[i];
+}
+__global__ void k_aypx(double *y, const double *x, int n, double a) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] = x[i] + a * y[i];
+}
+__global__ void k_chop(double *x, int n, double tol) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (fabs(x[i]) < tol) x[i] = 0.0;
+}
+__global__ void __launch_bounds__(256) k_dot(const double *x, const double *y, int n, double *partials,
+                                             unsigned *ticket, double *out) {
+  double s[1] = {0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s[0] += x[i] * y[i];
+  if (grid_sum<1>(s, partials, ticket) && threadIdx.x == 0) out[0] = s[0];
+}
+
+static int vec_grid(ohp_context ctx, int n) {
+  return (int)std::min<int64_t>(nblk(n, 256), (int64_t)ctx->num_sms * 8);
+}
+
+extern "C" int ohp_vec_create(ohp_mesh m, ohp_vec *out) {
+  if (!m || !m->setup_done) OHP_FAIL(OHP_ERR_ORDER, "ohp_vec_create: mesh not set up");
+  OHP_CUDA(cudaSetDevice(m->ctx->device));
+  ohp_vec v = new ohp_vec_s();
+  v->mesh = m; v->n = m->n_owned;
+  const size_t len = (size_t)std::max(1, m->n_owned + m->n_ghost);
+  OHP_CUDA(cudaMalloc(&v->d, sizeof(double) * len));
+  OHP_CUDA(cudaMemsetAsync(v->d, 0, sizeof(double) * len, m->ctx->stream));
+  *out = v;
+  return 0;
+}
+extern "C" int ohp_vec_duplicate(ohp_vec v, ohp_vec *w) { return ohp_vec_create(v->mesh, w); }
+extern "C" int ohp_vec_destroy(ohp_vec v) {
+  if (!v) return 0;
+  cudaSetDevice(v->mesh->ctx->device);
+  cudaStreamSynchronize(v->mesh->ctx->stream);
+  cudaFree(v->d);
+  delete v;
+  return 0;
+}
+extern "C" int ohp_vec_size(ohp_vec v, int32_t *n) { *n = v->n; return 0; }
+extern "C" void *ohp_vec_device_ptr(ohp_vec v) { return v ? (void *)v->d : nullptr; }
+
+extern "C" int ohp_vec_set(ohp_vec v, double a) {
+  ohp_context ctx = v->mesh->ctx;
+  OHP_CUDA(cudaSetDevice(ctx->device));
+  k_set<<<vec_grid(ctx, v->n), 256, 0, ctx->stream>>>(v->d, v->n, a);
+  OHP_CHECK_LAUNCH(ctx);
+  return 0;
+}
+extern "C" int ohp_vec_copy(ohp_vec src, ohp_vec dst) {
+  if (src->n != dst->n) OHP_FAIL(OHP_ERR_ARG_SIZ, "ohp_vec_copy: sizes %d vs %d", src->n, dst->n);
+  OHP_CUDA(cudaSetDevice(src->mesh->ctx->device));
+  OHP_CUDA(cudaMemcpyAsync(dst->d, src->d, sizeof(double) * src->n, cudaMemcpyDeviceToDevice, src->mesh->ctx->stream));
+  return 0;
+}
+extern "C" int ohp_vec_from_host(ohp_vec v, const double *h) {
+  OHP_CUDA(cudaSetDevice(v->mesh->ctx->device));
+  OHP_CUDA(cudaMemcpyAsync(v->d, h, sizeof(double) * v->n, cudaMemcpyHostToDevice, v->mesh->ctx->stream));
+  OHP_CUDA(cudaStreamSynchronize(v->mesh->ctx->stream));
+  return 0;
+}
+extern "C" int ohp_vec_to_host(ohp_vec v, double *h) {
+  OHP_CUDA(cudaSetDevice(v->mesh->ctx->device));
+  OHP_CUDA(cudaMemcpyAsync(h, v->d, sizeof(double) * v->n, cudaMemcpyDeviceToHost, v->mesh->ctx->stream));
+  OHP_CUDA(cudaStreamSynchronize(v->mesh->ctx->stream));
+  return 0;
+}
+extern "C" int ohp_vec_axpy(ohp_vec y, double a, ohp_vec x) {
+  if (x->n != y->n) OHP_FAIL(OHP_ERR_ARG_SIZ, "ohp_vec_axpy: sizes %d vs %d", x->n, y->n);
+  ohp_context ctx = y->mesh->ctx;
+  OHP_CUDA(cudaSetDevice(ctx->device));
+  k_axpy<<<vec_grid(ctx, y->n), 256, 0, ctx->stream>>>(y->d, x->d, y->n, a);
+  OHP_CHECK_LAUNCH(ctx);
+  return 0;
+}
+extern "C" int ohp_vec_aypx(ohp_vec y, double a, ohp_vec x) {
+  if (x->n != y->n) OHP_FAIL(OHP_ERR_ARG_SIZ, "ohp_vec_aypx: sizes %d vs %d", x->n, y->n);
+  ohp_context ctx = y->mesh->ctx;
+  OHP_CUDA(cudaSetDevice(ctx->device));
+  k_aypx<<<vec_grid(ctx, y->n), 256, 0, ctx->stream>>>(y->d, x->d, y->n, a);
+  OHP_CHECK_LAUNCH(ctx);
+  return 0;
+}
+extern "C" int ohp_vec_chop(ohp_vec v, double tol) {
+  ohp_context ctx = v->mesh->ctx;
+  OHP_CUDA(cudaSetDevice(ctx->device));
+  k_chop<<<vec_grid(ctx, v->n), 256, 0, ctx->stream>>>(v->d, v->n, tol);
+  OHP_CHECK_LAUNCH(ctx);
+  return 0;
+}
+extern "C" int ohp_vec_dot(ohp_vec x, ohp_vec y, double *result) {
+  if (x->n != y->n) OHP_FAIL(OHP_ERR_ARG_SIZ, "ohp_vec_dot: sizes %d vs %d", x->n, y->n);
+  ohp_context ctx = x->mesh->ctx;
+  OHP_CUDA(cudaSetDevice(ctx->device));
+  k_dot<<<vec_grid(ctx, x->n), 256, 0, ctx->stream>>>(x->d, y->d, x->n, ctx->d_partials, ctx->d_ticket, ctx->d_scalars);
+  OHP_CHECK_LAUNCH(ctx);
+  if (ctx->nranks > 1) OHP_TRY(ohp_allreduce_sum(ctx, ctx->d_scalars, 1));
+  OHP_CUDA(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  OHP_CUDA(cudaStreamSynchronize(ctx->stream));
+  *result = ctx->h_scalars[0];
+  return 0;
+}
+extern "C" int ohp_vec_norm2(ohp_vec x, double *result) {
+  double d = 0.0;
+  OHP_TRY(ohp_vec_dot(x, x, &d));
+  *result = sqrt(d);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Mat                                                                                   */
+/* ------------------------------------------------------------------------------------ */
+extern "C" int ohp_mat_create(ohp_mesh m, ohp_mat *out) {
+  if (!m || !m->setup_done) OHP_FAIL(OHP_ERR_ORDER, "ohp_mat_create: mesh not set up");
+  OHP_CUDA(cudaSetDevice(m->ctx->device));
+  ohp_mat A = new ohp_mat_s();
+  A->mesh = m; A->r = A->z = A->p = A->w = A->dinv = A->hist = nullptr; A->hist_cap = 0;
+  OHP_CUDA(cudaMalloc(&A->vals, sizeof(double) * std::max<int64_t>(1, m->nnz)));
+  OHP_CUDA(cudaMemsetAsync(A->vals, 0, sizeof(double) * std::max<int64_t>(1, m->nnz), m->ctx->stream));
+  *out = A;
+  return 0;
+}
+extern "C" int ohp_mat_destroy(ohp_mat A) {
+  if (!A) return 0;
+  cudaSetDevice(A->mesh->ctx->device);
+  cudaStreamSynchronize(A->mesh->ctx->stream);
+  cudaFree(A->vals); cudaFree(A->r); cudaFree(A->z); cudaFree(A->p); cudaFree(A->w); cudaFree(A->dinv); cudaFree(A->hist);
+  delete A;
+  return 0;
+}
+extern "C" int ohp_mat_zero(ohp_mat A) {
+  OHP_CUDA(cudaSetDevice(A->mesh->ctx->device));
+  OHP_CUDA(cudaMemsetAsync(A->vals, 0, sizeof(double) * A->mesh->nnz, A->mesh->ctx->stream));
+  return 0;
+}
+extern "C" int ohp_mat_get_values(ohp_mat A, double *vals) {
+  OHP_CUDA(cudaSetDevice(A->mesh->ctx->device));
+  OHP_CUDA(cudaMemcpyAsync(vals, A->vals, sizeof(double) * A->mesh->nnz, cudaMemcpyDeviceToHost, A->mesh->ctx->stream));
+  OHP_CUDA(cudaStreamSynchronize(A->mesh->ctx->stream));
+  return 0;
+}
+extern "C" int ohp_mat_mult(ohp_mat A, ohp_vec x, ohp_vec y) {
+  if (x->n != A->mesh->n_owned || y->n != A->mesh->n_owned) OHP_FAIL(OHP_ERR_ARG_SIZ, "ohp_mat_mult: size mismatch");
+  if (x == y) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_mat_mult: x and y must differ");
+  OHP_CUDA(cudaSetDevice(A->mesh->ctx->device));
+  if (A->mesh->ctx->nranks > 1) OHP_TRY(ohp_halo_exchange(A->mesh, x->d));
+  return ohp_spmv_launch(A, x->d, y->d);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* CG                                                                                    */
+/* ------------------------------------------------------------------------------------ */
+template <bool JACOBI>
+__global__ void __launch_bounds__(256)
+k_cg_init(const double *__restrict__ b, double *__restrict__ x, double *__restrict__ r, double *__restrict__ z,
+          const double *__restrict__ dinv, int n, ohp_cg_state *st, double *partials, unsigned *ticket,
+          double *sums, double *hist, int fin_inline) {
+  double s[2] = {0.0, 0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double bi = b[i];
+    x[i] = 0.0;
+    r[i] = bi;
+    double zi = bi;
+    if (JACOBI) { zi = dinv[i] * bi; z[i] = zi; }
+    s[0] += zi * zi;
+    s[1] += zi * bi;
+  }
+  if (grid_sum<2>(s, partials, ticket) && threadIdx.x == 0) {
+    sums[0] = s[0]; sums[1] = s[1];
+    if (fin_inline) cg_fin_init(st, s[0], s[1], hist);
+  }
+}
+
+/* p = z + (beta/betaold) p  (first iteration: p = z) */
+__global__ void __launch_bounds__(256)
+k_cg_pupdate(double *__restrict__ p, const double *__restrict__ z, int n, const ohp_cg_state *st) {
+  if (st->done) return;
+  const bool first = (st->its == 0);
+  const double bb = first ? 0.0 : st->beta / st->betaold;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    p[i] = first ? z[i] : z[i] + bb * p[i];
+}
+
+/* x += a p; r -= a w; z = M^-1 r; (z,z), (z,r) */
+template <bool JACOBI>
+__global__ void __launch_bounds__(256)
+k_cg_update(double *__restrict__ x, double *__restrict__ r, double *__restrict__ z, const double *__restrict__ p,
+            const double *__restrict__ w, const double *__restrict__ dinv, int n, ohp_cg_state *st,
+            double *partials, unsigned *ticket, double *sums, double *hist, int hist_cap, int fin_inline) {
+  if (st->done) return;
+  const double a = st->alpha;
+  double s[2] = {0.0, 0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    x[i] += a * p[i];
+    const double ri = r[i] - a * w[i];
+    r[i] = ri;
+    double zi = ri;
+    if (JACOBI) { zi = dinv[i] * ri; z[i] = zi; }
+    s[0] += zi * zi;
+    s[1] += zi * ri;
+  }
+  if (grid_sum<2>(s, partials, ticket) && threadIdx.x == 0) {
+    sums[0] = s[0]; sums[1] = s[1];
+    if (fin_inline) cg_fin_update(st, s[0], s[1], hist, hist_cap);
+  }
+}
+
+__global__ void k_extract_dinv(const int32_t *rowptr, const int32_t *colidx, const double *vals, int n, double *dinv) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  double d = 0.0;
+  for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) if (colidx[k] == r) d = vals[k];
+  dinv[r] = (d != 0.0) ? 1.0 / d : 1.0;
+}
+
+extern "C" int ohp_ksp_default_options(ohp_ksp_options *o) {
+  o->rtol = 1e-5; o->abstol = 1e-50; o->dtol = 1e5; o->max_it = 10000; o->pc = OHP_PC_NONE;
+  o->check_every = 0; o->history_cap = 0; o->history = nullptr; o->profile = 0;
+  return 0;
+}
+
+extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o, ohp_ksp_result *res) {
+  if (!A || !b || !x || !o || !res) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_ksp_cg: null argument");
+  ohp_mesh m = A->mesh;
+  ohp_context ctx = m->ctx;
+  const int n = m->n_owned;
+  if (b->n != n || x->n != n) OHP_FAIL(OHP_ERR_ARG_SIZ, "ohp_ksp_cg: vector sizes do not match the matrix");
+  if (b == x) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_ksp_cg: b and x must differ");
+  if (o->pc != OHP_PC_NONE && o->pc != OHP_PC_JACOBI) OHP_FAIL(OHP_ERR_SUP, "ohp_ksp_cg: pc %d", o->pc);
+  OHP_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t len = (size_t)std::max(1, n + m->n_ghost);
+  if (!A->r) {
+    OHP_CUDA(cudaMalloc(&A->r, sizeof(double) * len));
+    OHP_CUDA(cudaMalloc(&A->p, sizeof(double) * len));
+    OHP_CUDA(cudaMalloc(&A->w, sizeof(double) * len));
+    OHP_CUDA(cudaMemsetAsync(A->p, 0, sizeof(double) * len, st));
+  }
+  const bool jac = (o->pc == OHP_PC_JACOBI);
+  if (jac) {
+    if (!A->z) { OHP_CUDA(cudaMalloc(&A->z, sizeof(double) * len)); OHP_CUDA(cudaMalloc(&A->dinv, sizeof(double) * len)); }
+    k_extract_dinv<<<nblk(n, 256), 256, 0, st>>>(m->rowptr, m->colidx, A->vals, n, A->dinv);
+    OHP_CHECK_LAUNCH(ctx);
+  }
+  double *z = jac ? A->z : A->r;
+  double *hist = nullptr;
+  int hist_cap = 0;
+  if (o->history && o->history_cap > 0) {
+    if (A->hist_cap < o->history_cap) {
+      cudaFree(A->hist);
+      OHP_CUDA(cudaMalloc(&A->hist, sizeof(double) * o->history_cap));
+      A->hist_cap = o->history_cap;
+    }
+    hist = A->hist; hist_cap = o->history_cap;
+    OHP_CUDA(cudaMemsetAsync(hist, 0, sizeof(double) * hist_cap, st));
+  }
+  /* scalar block */
+  ohp_cg_state init;
+  memset(&init, 0, sizeof(init));
+  init.rtol = o->rtol; init.abstol = o->abstol; init.dtol = o->dtol; init.maxit = o->max_it;
+  *ctx->h_cg = init;
+  OHP_CUDA(cudaMemcpyAsync(ctx->d_cg, ctx->h_cg, sizeof(init), cudaMemcpyHostToDevice, st));
+  const int serial = (ctx->nranks == 1);
+  const int vgrid = vec_grid(ctx, n);
+  double *sums = ctx->d_scalars;
+  if (n > 0) OHP_TRY(spmv_configure(m));
+  const int sgrid = std::max(1, std::min(m->n_tiles, kMaxPartials));
+  const int smem = spmv_smem_bytes(m);
+
+  if (jac) k_cg_init<true><<<vgrid, 256, 0, st>>>(b->d, x->d, A->r, z, A->dinv, n, ctx->d_cg, ctx->d_partials, ctx->d_ticket, sums, hist, serial);
+  else k_cg_init<false><<<vgrid, 256, 0, st>>>(b->d, x->d, A->r, z, A->dinv, n, ctx->d_cg, ctx->d_partials, ctx->d_ticket, sums, hist, serial);
+  OHP_CHECK_LAUNCH(ctx);
+  if (!serial) {
+    OHP_TRY(ohp_allreduce_sum(ctx, sums, 2));
+    k_cg_fin<<<1, 1, 0, st>>>(ctx->d_cg, sums, 0, hist, hist_cap); OHP_CHECK_LAUNCH(ctx);
+  }
+  const int check_every = o->check_every > 0 ? o->check_every : 50;
+  int launched = 0;
+  /* optional per-launch timing of the dominant kernel, skipping the first (cold) chunk */
+  std::vector<cudaEvent_t> prof;
+  const int nprof = std::max(0, o->profile);
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+  OHP_CUDA(cudaEventCreate(&ev_t0));
+  OHP_CUDA(cudaEventCreate(&ev_t1));
+  OHP_CUDA(cudaEventRecord(ev_t0, st));
+  for (;;) {
+    OHP_CUDA(cudaMemcpyAsync(ctx->h_cg, ctx->d_cg, sizeof(ohp_cg_state), cudaMemcpyDeviceToHost, st));
+    OHP_CUDA(cudaStreamSynchronize(st));
+    if (ctx->h_cg->done) break;
+    if (launched > o->max_it + check_every) OHP_FAIL(OHP_ERR_LIB, "ohp_ksp_cg: device-side iteration control did not terminate");
+    for (int it = 0; it < check_every; ++it) {
+      k_cg_pupdate<<<vgrid, 256, 0, st>>>(A->p, z, n, ctx->d_cg); OHP_CHECK_LAUNCH(ctx);
+      if (!serial) OHP_TRY(ohp_halo_exchange(m, A->p));
+      const bool timed = (int)prof.size() < 2 * nprof && (launched > 0 || o->max_it <= check_every);
+      if (timed) { cudaEvent_t e; OHP_CUDA(cudaEventCreate(&e)); OHP_CUDA(cudaEventRecord(e, st)); prof.push_back(e); }
+      k_spmv_stream<true><<<sgrid, kSpmvThreads, smem, st>>>(m->rowptr, m->colidx, A->vals, A->p, A->w, m->tile_row,
+                                                          m->n_tiles, ctx->d_cg, ctx->d_partials, ctx->d_ticket + 1, sums, serial);
+      OHP_CHECK_LAUNCH(ctx);
+      if (timed) { cudaEvent_t e; OHP_CUDA(cudaEventCreate(&e)); OHP_CUDA(cudaEventRecord(e, st)); prof.push_back(e); }
+      if (!serial) {
+        OHP_TRY(ohp_allreduce_sum(ctx, sums, 1));
+        k_cg_fin<<<1, 1, 0, st>>>(ctx->d_cg, sums, 1, hist, hist_cap); OHP_CHECK_LAUNCH(ctx);
+      }
+      if (jac) k_cg_update<true><<<vgrid, 256, 0, st>>>(x->d, A->r, z, A->p, A->w, A->dinv, n, ctx->d_cg, ctx->d_partials, ctx->d_ticket, sums, hist, hist_cap, serial);
+      else k_cg_update<false><<<vgrid, 256, 0, st>>>(x->d, A->r, z, A->p, A->w, A->dinv, n, ctx->d_cg, ctx->d_partials, ctx->d_ticket, sums, hist, hist_cap, serial);
+      OHP_CHECK_LAUNCH(ctx);
+      if (!serial) {
+        OHP_TRY(ohp_allreduce_sum(ctx, sums, 2));
+        k_cg_fin<<<1, 1, 0, st>>>(ctx->d_cg, sums, 2, hist, hist_cap); OHP_CHECK_LAUNCH(ctx);
+      }
+    }
+    launched += check_every;
+  }
+  res->its = ctx->h_cg->its; res->reason = ctx->h_cg->reason; res->rnorm = ctx->h_cg->dp; res->rnorm0 = ctx->h_cg->rnorm0;
+  OHP_CUDA(cudaEventRecord(ev_t1, st));
+  OHP_CUDA(cudaEventSynchronize(ev_t1));
+  res->total_ms = 0.f;
+  cudaEventElapsedTime(&res->total_ms, ev_t0, ev_t1);
+  cudaEventDestroy(ev_t0); cudaEventDestroy(ev_t1);
+  res->spmv_ms = 0.f; res->spmv_samples = 0;
+  {
+    /* only launches that ran before convergence did real work: iteration k is sample k - first_timed */
+    double acc = 0.0;
+    int used = 0;
+    const int first_timed_it = (o->max_it <= check_every) ? 0 : check_every;
+    for (size_t i = 0; i + 1 < prof.size(); i += 2) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, prof[i], prof[i + 1]);
+      if (first_timed_it + (int)(i / 2) < res->its) { acc += ms; used++; }
+    }
+    for (cudaEvent_t e : prof) cudaEventDestroy(e);
+    if (used) { res->spmv_ms = (float)(acc / used); res->spmv_samples = used; }
+  }
+  if (hist) {
+    const int ncopy = std::min(hist_cap, res->its + 1);
+    OHP_CUDA(cudaMemcpyAsync(o->history, hist, sizeof(double) * ncopy, cudaMemcpyDeviceToHost, st));
+    OHP_CUDA(cudaStreamSynchronize(st));
+  }
+  return 0;
+}

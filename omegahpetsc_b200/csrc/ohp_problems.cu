@@ -1,0 +1,328 @@
+/*
+ * ohp_problems.cu -- the PetscDS side of the path: ex12's callback sets compiled into the
+ * assembly kernels, the problem registry, the FEM evaluators and the Newton driver.
+ *
+ * Reference: SetupProblem (ex12.cpp:1162-1243) registers (f0,f1) with PetscDSSetResidual and
+ * g3 with PetscDSSetJacobian, the exact solution with PetscDSSetExactSolution and the
+ * Dirichlet function with DMAddBoundary; DMPlexSetSNESLocalFEM (ex12.cpp:1540) installs the
+ * evaluators; SNESSolve (ex12.cpp:1609) runs newtonls + bt over KSP.
+ */
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "ohp_fem.cuh"
+#include "ohp_internal.h"
+
+namespace {
+
+/* exact / Dirichlet data: quadratic_u_2d (ex12.cpp:113-117), quadratic_u_3d (ex12.cpp:408-412) */
+struct QuadraticBC {
+  OHP_HD static int bc(int dim, double time, const double x[], int Nc, double *u, void *ctx) {
+    if (dim == 3) *u = 2.0 * (x[0] * x[0] + x[1] * x[1] + x[2] * x[2]) / 3.0;
+    else *u = x[0] * x[0] + x[1] * x[1];
+    return 0;
+  }
+  OHP_HD static int exact(int dim, double time, const double x[], int Nc, double *u, void *ctx) {
+    return bc(dim, time, x, Nc, u, ctx);
+  }
+};
+
+/* COEFF_NONE: f0_u (ex12.cpp:147-153), f1_u (:198-205), g3_uu (:209-216) */
+struct ProblemCoeffNone : QuadraticBC {
+  static constexpr bool kJacobianUsesU = false;
+  OHP_HD static void f0(OHP_PF_ARGS, double f0[]) { f0[0] = 4.0; }
+  OHP_HD static void f1(OHP_PF_ARGS, double f1[]) {
+    for (int d = 0; d < dim; ++d) f1[d] = u_x[d];
+  }
+  OHP_HD static void g3(OHP_PJ_ARGS, double g3[]) {
+    for (int d = 0; d < dim; ++d) g3[d * dim + d] = 1.0;
+  }
+};
+
+/* COEFF_ANALYTIC: f0_analytic_u (ex12.cpp:283-289), f1_analytic_u (:292-299), g3_analytic_uu (:313-320) */
+struct ProblemAnalytic : QuadraticBC {
+  static constexpr bool kJacobianUsesU = false;
+  OHP_HD static void f0(OHP_PF_ARGS, double f0[]) { f0[0] = 6.0 * (x[0] + x[1]); }
+  OHP_HD static void f1(OHP_PF_ARGS, double f1[]) {
+    for (int d = 0; d < dim; ++d) f1[d] = (x[0] + x[1]) * u_x[d];
+  }
+  OHP_HD static void g3(OHP_PJ_ARGS, double g3[]) {
+    for (int d = 0; d < dim; ++d) g3[d * dim + d] = x[0] + x[1];
+  }
+};
+
+/* COEFF_NONLINEAR (p-Laplacian, p = 4): f0/f1/g3_analytic_nonlinear_u (ex12.cpp:341-347,350-359,369-383) */
+struct ProblemNonlinear : QuadraticBC {
+  static constexpr bool kJacobianUsesU = true;
+  OHP_HD static void f0(OHP_PF_ARGS, double f0[]) { f0[0] = 16.0 * (x[0] * x[0] + x[1] * x[1]); }
+  OHP_HD static void f1(OHP_PF_ARGS, double f1[]) {
+    double nu = 0.0;
+    for (int d = 0; d < dim; ++d) nu += u_x[d] * u_x[d];
+    for (int d = 0; d < dim; ++d) f1[d] = 0.5 * nu * u_x[d];
+  }
+  OHP_HD static void g3(OHP_PJ_ARGS, double g3[]) {
+    double nu = 0.0;
+    for (int d = 0; d < dim; ++d) nu += u_x[d] * u_x[d];
+    for (int d = 0; d < dim; ++d) {
+      g3[d * dim + d] = 0.5 * nu;
+      for (int e = 0; e < dim; ++e) g3[d * dim + e] += u_x[d] * u_x[e];
+    }
+  }
+};
+
+struct ProblemEntry {
+  ohp_assembly_launcher residual, jacobian, project;
+};
+
+std::mutex g_reg_mutex;
+std::vector<ProblemEntry> &registry() {
+  static std::vector<ProblemEntry> r = {
+      {ohp::launch_residual_any<ProblemCoeffNone>, ohp::launch_jacobian_any<ProblemCoeffNone>, ohp::launch_project_exact_any<ProblemCoeffNone>},
+      {ohp::launch_residual_any<ProblemAnalytic>, ohp::launch_jacobian_any<ProblemAnalytic>, ohp::launch_project_exact_any<ProblemAnalytic>},
+      {ohp::launch_residual_any<ProblemNonlinear>, ohp::launch_jacobian_any<ProblemNonlinear>, ohp::launch_project_exact_any<ProblemNonlinear>},
+  };
+  return r;
+}
+
+/* DMComputeL2Diff [PETSc-internal, reached from ex12.cpp:1611,1637]: sqrt(sum_c sum_q w_q detJ (u_h - u_exact)^2),
+ * evaluated with the same quadrature; deterministic two-stage sum */
+template <int DIM>
+__global__ void __launch_bounds__(256) k_l2_diff(const ohp_assembly_view vw, double *partials) {
+  constexpr int NC = DIM + 1;
+  double acc = 0.0;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < vw.n_cells; c += gridDim.x * blockDim.x) {
+    int cv[NC];
+    double X[NC][DIM], ue[NC];
+    ohp::load_cell<DIM, QuadraticBC, true>(vw, c, cv, X, ue);
+    ohp::CellGeom<DIM> g;
+    ohp::cell_geometry<DIM>(X, g);
+    for (int q = 0; q < ohp::Quadrature<DIM>::NQ; ++q) {
+      double phi[NC], xq[DIM], uq = 0.0, ex = 0.0;
+      ohp::p1_basis<DIM>(q, phi);
+      for (int d = 0; d < DIM; ++d) {
+        double s = g.v0[d];
+        for (int f = 0; f < DIM; ++f) s += g.J[d * DIM + f] * (ohp::Quadrature<DIM>::xi(q, f) + 1.0);
+        xq[d] = s;
+      }
+      for (int j = 0; j < NC; ++j) uq += phi[j] * ue[j];
+      QuadraticBC::exact(DIM, 0.0, xq, 1, &ex, nullptr);
+      acc += ohp::Quadrature<DIM>::w(q) * fabs(g.detJ) * (uq - ex) * (uq - ex);
+    }
+  }
+  __shared__ double red[8];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    partials[blockIdx.x] = t;
+  }
+}
+
+}  // namespace
+
+int ohp_problem_lookup(int id, ohp_assembly_launcher *res, ohp_assembly_launcher *jac, ohp_assembly_launcher *proj) {
+  std::lock_guard<std::mutex> lock(g_reg_mutex);
+  auto &r = registry();
+  if (id < 0 || id >= (int)r.size()) OHP_FAIL(OHP_ERR_ARG_OUTOFRANGE, "unknown problem id %d", id);
+  if (res) *res = r[id].residual;
+  if (jac) *jac = r[id].jacobian;
+  if (proj) *proj = r[id].project;
+  return 0;
+}
+
+extern "C" int ohp_problem_register(ohp_assembly_launcher residual, ohp_assembly_launcher jacobian,
+                                    ohp_assembly_launcher project_exact, int *problem_id) {
+  if (!residual || !jacobian || !problem_id) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_problem_register: null launcher");
+  std::lock_guard<std::mutex> lock(g_reg_mutex);
+  registry().push_back({residual, jacobian, project_exact});
+  *problem_id = (int)registry().size() - 1;
+  return 0;
+}
+
+#define NEED(m, name)                                                                              \
+  do {                                                                                             \
+    if (!(m) || !(m)->setup_done) OHP_FAIL(OHP_ERR_ORDER, name ": mesh not set up");               \
+    OHP_CUDA(cudaSetDevice((m)->ctx->device));                                                     \
+  } while (0)
+
+extern "C" int ohp_residual(ohp_mesh m, int problem, ohp_vec u, ohp_vec F) {
+  NEED(m, "ohp_residual");
+  if (u->n != m->n_owned || F->n != m->n_owned) OHP_FAIL(OHP_ERR_ARG_SIZ, "ohp_residual: vector size mismatch");
+  ohp_assembly_launcher fn;
+  OHP_TRY(ohp_problem_lookup(problem, &fn, nullptr, nullptr));
+  if (m->ctx->nranks > 1) OHP_TRY(ohp_halo_exchange(m, u->d)); /* DMGlobalToLocal */
+  ohp_assembly_view vw;
+  ohp_assembly_view_make(m, u->d, F->d, &vw);
+  int rc = fn(&vw);
+  m->ctx->launches++;
+  if (rc) OHP_FAIL(rc, "ohp_residual: kernel launch failed (%s)", cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
+
+extern "C" int ohp_jacobian(ohp_mesh m, int problem, ohp_vec u, ohp_mat J) {
+  NEED(m, "ohp_jacobian");
+  if (u->n != m->n_owned || J->mesh != m) OHP_FAIL(OHP_ERR_ARG_SIZ, "ohp_jacobian: size mismatch");
+  ohp_assembly_launcher fn;
+  OHP_TRY(ohp_problem_lookup(problem, nullptr, &fn, nullptr));
+  if (m->ctx->nranks > 1) OHP_TRY(ohp_halo_exchange(m, u->d));
+  ohp_assembly_view vw;
+  ohp_assembly_view_make(m, u->d, J->vals, &vw);
+  int rc = fn(&vw);
+  m->ctx->launches++;
+  if (rc) OHP_FAIL(rc, "ohp_jacobian: kernel launch failed (%s)", cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
+
+extern "C" int ohp_project(ohp_mesh m, int problem, int which, ohp_vec u) {
+  NEED(m, "ohp_project");
+  if (which == 0) return ohp_vec_set(u, 0.0); /* zero(), ex12.cpp:76-80 */
+  ohp_assembly_launcher fn;
+  OHP_TRY(ohp_problem_lookup(problem, nullptr, nullptr, &fn));
+  if (!fn) OHP_FAIL(OHP_ERR_SUP, "ohp_project: problem %d has no exact solution registered", problem);
+  ohp_assembly_view vw;
+  ohp_assembly_view_make(m, nullptr, u->d, &vw);
+  int rc = fn(&vw);
+  m->ctx->launches++;
+  if (rc) OHP_FAIL(rc, "ohp_project: kernel launch failed");
+  return 0;
+}
+
+extern "C" int ohp_l2_error(ohp_mesh m, int problem, ohp_vec u, double *err) {
+  NEED(m, "ohp_l2_error");
+  (void)problem; /* all built-in problems share the quadratic exact solution (ex12.cpp:1222,1230) */
+  if (m->ctx->nranks > 1) OHP_FAIL(OHP_ERR_SUP, "ohp_l2_error: serial only (owned-cell mask not wired)");
+  ohp_context ctx = m->ctx;
+  ohp_assembly_view vw;
+  ohp_assembly_view_make(m, u->d, nullptr, &vw);
+  const int grid = std::min(std::max(1, (m->nC + 255) / 256), 1024);
+  if (m->dim == 2) k_l2_diff<2><<<grid, 256, 0, ctx->stream>>>(vw, ctx->d_partials);
+  else k_l2_diff<3><<<grid, 256, 0, ctx->stream>>>(vw, ctx->d_partials);
+  OHP_CHECK_LAUNCH(ctx);
+  std::vector<double> part(grid);
+  OHP_CUDA(cudaMemcpyAsync(part.data(), ctx->d_partials, sizeof(double) * grid, cudaMemcpyDeviceToHost, ctx->stream));
+  OHP_CUDA(cudaStreamSynchronize(ctx->stream));
+  double s = 0.0;
+  for (double p : part) s += p;
+  *err = sqrt(s);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* SNES newtonls + bt                                                                    */
+/* ------------------------------------------------------------------------------------ */
+extern "C" int ohp_snes_default_options(ohp_snes_options *o) {
+  o->rtol = 1e-8; o->abstol = 1e-50; o->stol = 1e-8; o->max_it = 50;
+  return ohp_ksp_default_options(&o->ksp);
+}
+
+namespace {
+struct PhaseTimer {
+  cudaStream_t st;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[3];
+  explicit PhaseTimer(cudaStream_t s) : st(s) {}
+  int begin(int phase) {
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return 1;
+    cudaEventRecord(a, st);
+    ev[phase].push_back({a, b});
+    return 0;
+  }
+  void end(int phase) { cudaEventRecord(ev[phase].back().second, st); }
+  float total(int phase) {
+    float t = 0.f;
+    for (auto &p : ev[phase]) {
+      float ms = 0.f;
+      cudaEventSynchronize(p.second);
+      cudaEventElapsedTime(&ms, p.first, p.second);
+      t += ms;
+    }
+    return t;
+  }
+  ~PhaseTimer() {
+    for (auto &v : ev)
+      for (auto &p : v) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  }
+};
+}  // namespace
+
+extern "C" int ohp_snes_solve(ohp_mesh m, int problem, ohp_mat J, ohp_vec u, const ohp_snes_options *o,
+                              ohp_snes_result *res) {
+  NEED(m, "ohp_snes_solve");
+  if (!J || !u || !o || !res) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_snes_solve: null argument");
+  ohp_context ctx = m->ctx;
+  ohp_vec F = nullptr, y = nullptr, w = nullptr, Fw = nullptr;
+  OHP_TRY(ohp_vec_create(m, &F));
+  OHP_TRY(ohp_vec_create(m, &y));
+  OHP_TRY(ohp_vec_create(m, &w));
+  OHP_TRY(ohp_vec_create(m, &Fw));
+  PhaseTimer tm(ctx->stream);
+  memset(res, 0, sizeof(*res));
+  int rc = 0, its = 0, kits = 0, reason = 0;
+  double fnorm = 0.0, fnorm0 = 0.0;
+#define SN_TRY(e) do { rc = (e); if (rc) goto done; } while (0)
+  tm.begin(0);
+  SN_TRY(ohp_residual(m, problem, u, F));
+  tm.end(0);
+  res->n_residual++;
+  SN_TRY(ohp_vec_norm2(F, &fnorm));
+  fnorm0 = fnorm;
+  if (fnorm < o->abstol) reason = 2;
+  while (!reason && its < o->max_it) {
+    tm.begin(1);
+    SN_TRY(ohp_jacobian(m, problem, u, J));
+    tm.end(1);
+    res->n_jacobian++;
+    ohp_ksp_result kr;
+    tm.begin(2);
+    SN_TRY(ohp_ksp_cg(J, F, y, &o->ksp, &kr));
+    tm.end(2);
+    kits += kr.its;
+    res->spmv_ms = kr.spmv_ms; res->spmv_samples = kr.spmv_samples;
+    if (kr.reason < 0) { reason = -3; break; }
+    /* bt line search: accept lambda when 0.5 g^2 <= 0.5 f^2 + lambda * 1e-4 * initslope */
+    SN_TRY(ohp_mat_mult(J, y, w));
+    double initslope = 0.0;
+    SN_TRY(ohp_vec_dot(F, w, &initslope));
+    initslope = -initslope;
+    if (initslope > 0.0) initslope = -initslope;
+    if (initslope == 0.0) initslope = -1.0;
+    double lambda = 1.0, gnorm = 0.0;
+    for (int bt = 0; bt < 40; ++bt) {
+      SN_TRY(ohp_vec_copy(u, w));
+      SN_TRY(ohp_vec_axpy(w, -lambda, y));
+      tm.begin(0);
+      SN_TRY(ohp_residual(m, problem, w, Fw));
+      tm.end(0);
+      res->n_residual++;
+      SN_TRY(ohp_vec_norm2(Fw, &gnorm));
+      if (0.5 * gnorm * gnorm <= 0.5 * fnorm * fnorm + lambda * 1e-4 * initslope) break;
+      lambda *= 0.5;
+    }
+    double ynorm = 0.0, xnorm = 0.0;
+    SN_TRY(ohp_vec_norm2(y, &ynorm));
+    ynorm *= lambda;
+    SN_TRY(ohp_vec_copy(w, u));
+    SN_TRY(ohp_vec_copy(Fw, F));
+    fnorm = gnorm;
+    ++its;
+    SN_TRY(ohp_vec_norm2(u, &xnorm));
+    if (fnorm < o->abstol) reason = 2;
+    else if (fnorm <= o->rtol * fnorm0) reason = 3;
+    else if (ynorm < o->stol * xnorm) reason = 4;
+  }
+  if (!reason) reason = -5;
+  SN_TRY(ohp_sync(ctx));
+  res->its = its; res->ksp_its = kits; res->reason = reason; res->fnorm0 = fnorm0; res->fnorm = fnorm;
+  res->ms_residual = tm.total(0); res->ms_jacobian = tm.total(1); res->ms_ksp = tm.total(2);
+done:
+#undef SN_TRY
+  ohp_vec_destroy(F); ohp_vec_destroy(y); ohp_vec_destroy(w); ohp_vec_destroy(Fw);
+  return rc;
+}

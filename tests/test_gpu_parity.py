@@ -1,0 +1,353 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C-ABI, against the oracle on the
+same inputs.  Contract (BASELINE.json north_star): numbering and sparsity pattern BIT-EXACT;
+assembled values within 1e-12 relative (relative to the largest magnitude of the row / vector:
+exact-zero couplings of right-angled cells make an entrywise ratio meaningless); solution within
+the solver tolerance."""
+import numpy as np
+import pytest
+
+import omegahpetsc_b200 as ohp
+from conftest import load_osh_oracle, synthetic_meshes
+
+pytestmark = pytest.mark.gpu
+
+VAL_RTOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = ohp.Context(0)
+    yield c
+    c.close()
+
+
+def all_meshes():
+    out = dict(synthetic_meshes())
+    for name, file in (("T23", "23elm.osh"), ("T24k", "24k.osh")):
+        c, x, _ = load_osh_oracle(file)
+        out[name] = (c, x)
+    return out
+
+
+MESHES = None
+
+
+def get_mesh(name):
+    global MESHES
+    if MESHES is None:
+        MESHES = all_meshes()
+    return MESHES[name]
+
+
+NAMES = ["one_tri", "fan4", "T23", "box2d_8x8", "box2d_33x17", "box2d_100x70", "sheared_21x13", "T24k",
+         "box3d_5x4x3", "box3d_12x11x10", "warped3d_6x5x7"]
+
+
+def oracle_setup(oracle, cells, coords):
+    bnd = oracle.mark_boundary(cells, coords.shape[0])
+    gidx, N = oracle.numbering(bnd)
+    rowptr, colidx = oracle.pattern(cells, gidx, N)
+    return bnd, gidx, N, rowptr, colidx
+
+
+def test_field(coords, gidx):
+    x = coords[gidx >= 0]
+    return np.sin(3.0 * x[:, 0]) * np.cos(2.0 * x[:, 1]) + (0.3 * x[:, 2] if x.shape[1] == 3 else 0.0)
+
+
+def rowwise_close(vals, ref, rowptr, rtol):
+    if vals.size == 0:
+        return True
+    rowmax = np.maximum.reduceat(np.abs(ref), rowptr[:-1][np.diff(rowptr) > 0])
+    scale = np.repeat(rowmax, np.diff(rowptr)[np.diff(rowptr) > 0])
+    return bool((np.abs(vals - ref) <= rtol * scale).all())
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_numbering_and_pattern_bit_exact(ctx, oracle_mod, name):
+    cells, coords = get_mesh(name)
+    bnd, gidx, N, rowptr, colidx = oracle_setup(oracle_mod, cells, coords)
+    m = ohp.Mesh(ctx, cells, coords).setup()
+    info = m.info()
+    assert (info.n_cells, info.n_verts, info.n_boundary_verts, info.n_owned, info.n_global, info.nnz) == (
+        cells.shape[0], coords.shape[0], int(bnd.sum()), N, N, colidx.size)
+    assert np.array_equal(m.boundary(), bnd)
+    assert np.array_equal(m.numbering(), gidx.astype(np.int64))
+    rp, ci = m.csr()
+    assert np.array_equal(rp, rowptr)
+    assert np.array_equal(ci, colidx.astype(np.int64))
+    assert info.max_row == (int(np.diff(rowptr).max()) if N else 0)
+    m.destroy()
+
+
+def test_golden_hashes_T24k(ctx, expected):
+    import hashlib
+    m = ohp.Mesh.from_osh(ctx, __import__("conftest").golden_mesh_path("24k.osh")).setup()
+    e = expected["T24k"]
+    rp, ci = m.csr()
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    assert sha(m.boundary()) == e["sha_bnd"] and sha(m.numbering()) == e["sha_gidx"]
+    assert sha(rp) == e["sha_rowptr"] and sha(ci) == e["sha_colidx"]
+    u, F = m.create_global_vector(), m.create_global_vector()
+    m.residual(0, u.set(0.0), F)
+    assert F.norm() == pytest.approx(e["F0_norm"], rel=1e-13)
+    m.destroy()
+
+
+@pytest.mark.parametrize("problem", [0, 1, 2])
+@pytest.mark.parametrize("name", NAMES)
+def test_residual_and_jacobian_values(ctx, oracle_mod, name, problem):
+    cells, coords = get_mesh(name)
+    if problem != 0 and coords.shape[1] == 3 and name != "box3d_5x4x3":
+        pytest.skip("variable-coefficient callbacks are 2-D formulas; one 3-D case is enough")
+    bnd, gidx, N, rowptr, colidx = oracle_setup(oracle_mod, cells, coords)
+    m = ohp.Mesh(ctx, cells, coords).setup()
+    u, F, J = m.create_global_vector(), m.create_global_vector(), m.create_matrix()
+    for uh in (np.zeros(N), test_field(coords, gidx)):
+        u.from_host(uh)
+        Fd = m.residual(problem, u, F).to_host()
+        Fo = oracle_mod.residual(problem, cells, coords, gidx, N, uh)
+        assert np.abs(Fd - Fo).max(initial=0.0) <= VAL_RTOL * max(np.abs(Fo).max(initial=0.0), 1e-300)
+        vd = m.jacobian(problem, u, J).values()
+        vo = oracle_mod.jacobian(problem, cells, coords, gidx, N, uh, rowptr, colidx)
+        assert rowwise_close(vd, vo, rowptr, VAL_RTOL)
+        if problem == 0 and name.startswith("box2d"):
+            assert np.array_equal(vd == 0.0, vo == 0.0), "explicit zeros must stay exact zeros"
+    # bitwise reproducible: colour-free, atomic-free assembly
+    v1 = m.jacobian(problem, u, J).values().copy()
+    v2 = m.jacobian(problem, u, J).values()
+    F1 = m.residual(problem, u, F).to_host().copy()
+    F2 = m.residual(problem, u, F).to_host()
+    assert np.array_equal(v1, v2) and np.array_equal(F1, F2)
+    for o in (u, F):
+        o.destroy()
+    J.destroy()
+    m.destroy()
+
+
+@pytest.mark.parametrize("name", ["T23", "box2d_100x70", "T24k", "box3d_12x11x10", "warped3d_6x5x7"])
+def test_spmv_and_vec_ops(ctx, oracle_mod, name):
+    cells, coords = get_mesh(name)
+    bnd, gidx, N, rowptr, colidx = oracle_setup(oracle_mod, cells, coords)
+    m = ohp.Mesh(ctx, cells, coords).setup()
+    J = m.create_matrix()
+    u, x, y = (m.create_global_vector() for _ in range(3))
+    m.jacobian(0, u, J)
+    vals = J.values()
+    rng = np.random.default_rng(11)
+    xh, yh = rng.standard_normal(N), rng.standard_normal(N)
+    x.from_host(xh)
+    yd = J.mult(x, y).to_host()
+    yo = oracle_mod.spmv(rowptr, colidx, vals, xh)
+    assert np.abs(yd - yo).max() <= 1e-13 * np.abs(yo).max()
+    y.from_host(yh)
+    assert x.dot(y) == pytest.approx(float(xh @ yh), rel=1e-12, abs=1e-12)
+    assert x.norm() == pytest.approx(float(np.linalg.norm(xh)), rel=1e-13)
+    assert np.allclose(y.axpy(-0.75, x).to_host(), yh - 0.75 * xh, rtol=0, atol=1e-15 * 4)
+    y.from_host(yh)
+    assert np.allclose(y.aypx(0.5, x).to_host(), xh + 0.5 * yh, rtol=0, atol=1e-15 * 4)
+    y.from_host(yh)
+    ch = y.chop(0.5).to_host()
+    assert np.array_equal(ch, np.where(np.abs(yh) < 0.5, 0.0, yh))
+    assert np.array_equal(y.copy_from(x).to_host(), xh)
+    assert x.dot(x) == x.dot(x), "deterministic reduction"
+    for o in (u, x, y):
+        o.destroy()
+    J.destroy()
+    m.destroy()
+
+
+@pytest.mark.parametrize("pc", [0, 1])
+@pytest.mark.parametrize("name", ["T23", "box2d_33x17", "sheared_21x13", "T24k", "box3d_12x11x10"])
+def test_cg_matches_oracle(ctx, oracle_mod, name, pc):
+    cells, coords = get_mesh(name)
+    bnd, gidx, N, rowptr, colidx = oracle_setup(oracle_mod, cells, coords)
+    m = ohp.Mesh(ctx, cells, coords).setup()
+    J = m.create_matrix()
+    u, b, x = (m.create_global_vector() for _ in range(3))
+    m.jacobian(0, u, J)
+    m.residual(0, u, b)
+    out = ohp.ksp_cg(J, b, x, ohp.ksp_options(rtol=1e-9, max_it=20000, pc=pc), history=True)
+    ref = oracle_mod.cg(rowptr, colidx, J.values(), b.to_host(), rtol=1e-9, maxit=20000, pc=pc, history=True)
+    assert out["reason"] == ref["reason"] == 2
+    assert abs(out["its"] - ref["its"]) <= max(2, ref["its"] // 100)
+    k = min(out["its"], ref["its"], 50)
+    assert np.allclose(out["hist"][:k], ref["hist"][:k], rtol=1e-8)
+    xs = x.to_host()
+    assert np.abs(xs - ref["x"]).max() <= 1e-7 * np.abs(ref["x"]).max()
+    # true residual meets the tolerance
+    r = b.to_host() - oracle_mod.spmv(rowptr, colidx, J.values(), xs)
+    assert np.linalg.norm(r) <= 2e-9 * np.linalg.norm(b.to_host()) * (1 if pc == 0 else 50)
+    for o in (u, b, x):
+        o.destroy()
+    J.destroy()
+    m.destroy()
+
+
+def test_cg_limits(ctx, oracle_mod):
+    cells, coords = get_mesh("T24k")
+    m = ohp.Mesh(ctx, cells, coords).setup()
+    J = m.create_matrix()
+    u, b, x = (m.create_global_vector() for _ in range(3))
+    m.jacobian(0, u, J)
+    m.residual(0, u, b)
+    out = ohp.ksp_cg(J, b, x, ohp.ksp_options(rtol=1e-9, max_it=37, check_every=7))
+    assert (out["its"], out["reason"]) == (37, -3)
+    out = ohp.ksp_cg(J, b.set(0.0), x, ohp.ksp_options(rtol=1e-9))
+    assert (out["its"], out["reason"]) == (0, 3)
+    m.destroy()
+
+
+@pytest.mark.parametrize("name", ["T23", "box2d_33x17", "T24k", "box3d_12x11x10"])
+def test_newton_matches_oracle(ctx, oracle_mod, expected, name):
+    cells, coords = get_mesh(name)
+    bnd, gidx, N, rowptr, colidx = oracle_setup(oracle_mod, cells, coords)
+    m = ohp.Mesh(ctx, cells, coords).setup()
+    J, u = m.create_matrix(), m.create_global_vector()
+    m.project(0, 0, u)
+    res = m.snes_solve(0, J, u, ksp=ohp.ksp_options(rtol=1e-9, max_it=100000))
+    ref = oracle_mod.newton(0, cells, coords, gidx, N, rowptr, colidx, ksp_rtol=1e-9, ksp_maxit=100000)
+    assert (res["its"], res["reason"]) == (ref["snes_its"], ref["reason"]) == (1, 3)
+    assert (res["n_residual"], res["n_jacobian"]) == (2, 1)
+    assert abs(res["ksp_its"] - ref["ksp_its"]) <= max(2, ref["ksp_its"] // 100)
+    assert res["fnorm0"] == pytest.approx(ref["norms"][0], rel=1e-12)
+    uh = u.to_host()
+    assert np.abs(uh - ref["u"]).max() <= 1e-7 * np.abs(ref["u"]).max()
+    if name in expected:
+        assert np.linalg.norm(uh) == pytest.approx(expected[name]["u_norm"], rel=1e-7)
+    exact = m.project(0, 1, m.create_global_vector()).to_host()
+    full_exact = (coords ** 2).sum(axis=1) * (1.0 if coords.shape[1] == 2 else 2.0 / 3.0)
+    assert np.array_equal(exact, full_exact[gidx >= 0])
+    m.destroy()
+
+
+def test_nonlinear_newton(ctx, oracle_mod):
+    cells, coords = get_mesh("box2d_33x17")
+    bnd, gidx, N, rowptr, colidx = oracle_setup(oracle_mod, cells, coords)
+    u0 = 0.7 * (coords ** 2).sum(axis=1)[gidx >= 0]
+    m = ohp.Mesh(ctx, cells, coords).setup()
+    J, u = m.create_matrix(), m.create_global_vector()
+    u.from_host(u0)
+    res = m.snes_solve(2, J, u, ksp=ohp.ksp_options(rtol=1e-10, max_it=5000))
+    ref = oracle_mod.newton(2, cells, coords, gidx, N, rowptr, colidx, u0=u0, ksp_rtol=1e-10, ksp_maxit=5000)
+    assert res["reason"] == ref["reason"] and res["its"] == ref["snes_its"] > 1
+    assert np.abs(u.to_host() - ref["u"]).max() <= 1e-6 * np.abs(ref["u"]).max()
+    m.destroy()
+
+
+def test_error_paths(ctx):
+    with pytest.raises(ohp.OhpError):
+        ohp.Mesh(ctx, np.array([[0, 1, 7]], np.int32), np.zeros((3, 2)))
+    m = ohp.Mesh(ctx, *get_mesh("fan4"))
+    with pytest.raises(ohp.OhpError) as e:
+        m.create_global_vector()
+    assert e.value.code == 58
+    m.setup()
+    u = m.create_global_vector()
+    with pytest.raises(ohp.OhpError):
+        m.residual(99, u, u)
+    with pytest.raises(ohp.OhpError):
+        ohp.Context(1234)
+    m.destroy()
+
+
+def test_picpart_extract_matches_reference_semantics(ctx, expected):
+    """getPicPartCore* (ex12.cpp:584-730) on the 4-part XGC fixture: counts from the survey
+    probe, arrays against a numpy restatement."""
+    from conftest import golden_mesh_path
+    for r in range(4):
+        o = ohp.Osh(golden_mesh_path("24k_4p_%d.osh" % r))
+        ev, X = o.elem_verts(), o.coords()
+        eo, vo, gid = o.tag(2, "ownership"), o.tag(0, "ownership"), o.tag(0, "gids")
+        got = ctx.picpart_extract(2, r, ev, X, eo, vo, gid)
+        e = expected["T24k_4p"][str(r)]
+        assert (got["n_core_elems"], got["n_core_verts"], got["n_owned_verts"], got["n_ghost_verts"]) == (
+            e["owned_elems"], e["core_verts"], e["owned_verts"], e["ghosts"])
+        keep = eo == r
+        core = np.zeros(X.shape[0], bool)
+        core[ev[keep].reshape(-1)] = True
+        p2c = np.where(core, np.cumsum(core) - 1, -1)
+        assert np.array_equal(got["part2core"], p2c)
+        assert np.array_equal(got["core_elem_verts"], p2c[ev[keep]])
+        assert np.array_equal(got["core_coords"], X[core])
+        g = core & (vo != r)
+        assert np.array_equal(got["ghost_core_idx"], p2c[g]) and np.array_equal(got["ghost_gid"], gid[g])
+        assert np.array_equal(got["ghost_owner"], vo[g]) and np.array_equal(got["core_gid"], gid[core])
+        assert (got["ghost_owner"] == r - 1).all()
+        o.close()
+
+
+# ----------------------------------------------------------------------------------------------
+# size-independent properties at (and near) BASELINE.json's full sizes
+# ----------------------------------------------------------------------------------------------
+def test_large_box_properties(ctx, oracle_mod):
+    """1024^2 box (N ~ 1M): pattern equals the oracle's (hash), A u + F(0) = F(u)
+    (ex12.cpp:1651-1661), symmetry via x'Ay = y'Ax, explicit zeros, nodal exactness after the solve."""
+    n = 1024
+    cells, coords = oracle_mod.box2d(n, n)
+    m = ohp.Mesh(ctx, cells, coords).setup()
+    info = m.info()
+    N = (n - 1) ** 2
+    assert (info.n_owned, info.n_boundary_verts, info.nnz) == (N, 4 * n, N + 2 * (2 * (n - 1) * (n - 2) + (n - 2) ** 2))
+    bnd = oracle_mod.mark_boundary(cells, coords.shape[0], omp=True)
+    gidx, _ = oracle_mod.numbering(bnd)
+    rowptr, colidx = oracle_mod.pattern(cells, gidx, N, omp=True)
+    rp, ci = m.csr()
+    assert np.array_equal(rp, rowptr) and np.array_equal(ci, colidx)
+    J = m.create_matrix()
+    u, F0, Fu, Au, y = (m.create_global_vector() for _ in range(5))
+    rng = np.random.default_rng(5)
+    uh, yh = rng.standard_normal(N), rng.standard_normal(N)
+    m.residual(0, u.set(0.0), F0)
+    m.jacobian(0, u, J)
+    u.from_host(uh)
+    y.from_host(yh)
+    m.residual(0, u, Fu)
+    J.mult(u, Au)
+    lin = Au.to_host() + F0.to_host() - Fu.to_host()
+    assert np.abs(lin).max() <= 1e-11 * np.abs(Fu.to_host()).max()
+    yAu = y.dot(Au)
+    J.mult(y, Au)
+    assert u.dot(Au) == pytest.approx(yAu, rel=1e-11)
+    vals = J.values()
+    assert (vals == 0.0).sum() == 2 * (n - 2) ** 2, "hypotenuse couplings: exact zeros kept in the pattern"
+    res = m.snes_solve(0, J, u.set(0.0), ksp=ohp.ksp_options(rtol=1e-12, max_it=100000))
+    assert res["reason"] == 3 and res["its"] == 1
+    exact = (coords ** 2).sum(axis=1)[gidx >= 0]
+    assert np.abs(u.to_host() - exact).max() < 1e-8
+    m.destroy()
+
+
+def test_full_size_16M_triangles(ctx):
+    """BASELINE config 4 (2896 x 2896 box, 16 773 632 triangles): counts in closed form, linearity of
+    the assembled operator, symmetry, and CG residual reduction over a fixed number of iterations."""
+    n = 2896
+    import oracle  # input generator only
+    cells, coords = oracle.box2d(n, n)
+    m = ohp.Mesh(ctx, cells, coords).setup()
+    info = m.info()
+    N = (n - 1) ** 2
+    assert info.n_cells == 16773632 and info.n_verts == 8392609
+    assert (info.n_owned, info.n_boundary_verts, info.nnz, info.max_row) == (N, 4 * n, 58644017, 7)
+    del cells
+    J = m.create_matrix()
+    u, F0, Fu, Au, y = (m.create_global_vector() for _ in range(5))
+    rng = np.random.default_rng(9)
+    m.residual(0, u.set(0.0), F0)
+    m.jacobian(0, u, J)
+    u.from_host(rng.standard_normal(N))
+    y.from_host(rng.standard_normal(N))
+    m.residual(0, u, Fu)
+    J.mult(u, Au)
+    Au.axpy(1.0, F0).axpy(-1.0, Fu)
+    assert Au.norm() <= 1e-11 * Fu.norm()
+    J.mult(u, Au)
+    yAu = y.dot(Au)
+    J.mult(y, Au)
+    assert u.dot(Au) == pytest.approx(yAu, rel=1e-10)
+    out = ohp.ksp_cg(J, F0, u, ohp.ksp_options(rtol=1e-9, max_it=300), history=True)
+    assert out["reason"] == -3 and out["its"] == 300
+    J.mult(u, Au)
+    Au.aypx(-1.0, F0)  # r = b - A x
+    assert Au.norm() == pytest.approx(out["rnorm"], rel=1e-6)
+    m.destroy()
