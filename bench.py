@@ -320,7 +320,7 @@ def run_ours(args):
     roof = None
     if spmv_ms:
         ach = ab["spmv"] / (spmv_ms * 1e-3) / 1e9
-        roof = {"kernel": "k_spmv_stream<true> (CSR SpMV + fused (p,Ap))", "bound": "hbm", "achieved": ach, "peak": peak,
+        roof = {"kernel": "k_spmv_tma<true> (persistent TMA-pipelined CSR SpMV + fused (p,Ap))", "bound": "hbm", "achieved": ach, "peak": peak,
                 "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                 "bytes_per_launch": ab["spmv"], "ms_per_launch": spmv_ms, "launches_timed": int(res["spmv_samples"])}
         tr = os.path.join(ROOT, "profiles", "traffic.json")

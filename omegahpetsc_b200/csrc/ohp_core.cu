@@ -223,7 +223,7 @@ extern "C" int ohp_mesh_create(ohp_context ctx, int dim, int32_t nC, int32_t nV,
   m->cells = nullptr; m->coords = nullptr; m->owned = nullptr; m->setup_done = false;
   m->v2c_ptr = m->v2c = nullptr; m->bnd = nullptr; m->lidx = m->row_vertex = nullptr; m->ldof_gid = nullptr;
   m->rowptr = m->colidx = nullptr; m->slot = nullptr; m->tile_row = nullptr; m->halo = nullptr;
-  m->n_owned = m->n_ghost = m->n_bnd = 0; m->n_global = m->row_start = m->nnz = 0; m->max_row = 0; m->n_tiles = 0;
+  m->n_owned = m->n_ghost = m->n_bnd = 0; m->n_global = m->row_start = m->nnz = 0; m->max_row = 0; m->n_tiles = 0; m->max_tile_rows = 0;
   OHP_CUDA(cudaMalloc(&m->cells, sizeof(int32_t) * std::max<int64_t>(1, (int64_t)nC * nc)));
   OHP_CUDA(cudaMalloc(&m->coords, sizeof(double) * std::max<int64_t>(1, (int64_t)nV * dim)));
   OHP_CUDA(cudaMemcpyAsync(m->cells, cells, sizeof(int32_t) * (int64_t)nC * nc, cudaMemcpyHostToDevice, ctx->stream));
@@ -574,7 +574,8 @@ extern "C" int ohp_mesh_setup(ohp_mesh m) {
   OHP_TRY(check_flag(ctx, "ohp_mesh_setup (pattern count)"));
   OHP_TRY(ohp_scan_exclusive_i32(ctx, rowlen, m->rowptr, N, &m->nnz));
   cudaFree(rowlen);
-  OHP_CUDA(cudaMalloc(&m->colidx, sizeof(int32_t) * std::max<int64_t>(1, m->nnz)));
+  OHP_CUDA(cudaMalloc(&m->colidx, sizeof(int32_t) * ohp_padded_nnz(m->nnz)));
+  OHP_CUDA(cudaMemsetAsync(m->colidx, 0, sizeof(int32_t) * ohp_padded_nnz(m->nnz), st));
   OHP_CUDA(cudaMalloc(&m->slot, std::max<int64_t>(1, ninc * nc)));
   OHP_CUDA(cudaMemsetAsync(m->slot, 0xff, std::max<int64_t>(1, ninc * nc), st));
   if (N) {
@@ -599,7 +600,13 @@ extern "C" int ohp_mesh_setup(ohp_mesh m) {
   if (m->n_tiles == 0 && N > 0) m->n_tiles = 1;
   OHP_CUDA(cudaMalloc(&m->tile_row, sizeof(int32_t) * (m->n_tiles + 1)));
   k_tile_rows<<<nblk(m->n_tiles + 1, BS), BS, 0, st>>>(m->rowptr, N, kSpmvTile, m->n_tiles, m->tile_row); OHP_CHECK_LAUNCH(ctx);
-  OHP_CUDA(cudaStreamSynchronize(st));
+  {
+    std::vector<int32_t> tr(m->n_tiles + 1);
+    OHP_CUDA(cudaMemcpyAsync(tr.data(), m->tile_row, sizeof(int32_t) * (m->n_tiles + 1), cudaMemcpyDeviceToHost, st));
+    OHP_CUDA(cudaStreamSynchronize(st));
+    m->max_tile_rows = 0;
+    for (int t = 0; t < m->n_tiles; ++t) m->max_tile_rows = std::max(m->max_tile_rows, tr[t + 1] - tr[t]);
+  }
   m->setup_done = true;
   return 0;
 }

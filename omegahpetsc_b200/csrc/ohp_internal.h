@@ -47,6 +47,7 @@ struct ohp_cg_state {
   double beta, betaold, dpi, alpha, dp, rnorm0, ttol;
   double rtol, abstol, dtol;
   int its, reason, maxit, done;
+  int x_pending, pad; /* 1: x += alpha p of the last completed iteration has not been applied yet */
 };
 
 struct ohp_halo;  /* ohp_comm.cu */
@@ -71,8 +72,12 @@ struct ohp_context_s {
 };
 
 constexpr int kMaxPartials = 1 << 16;
-constexpr int kSpmvTile = 4096;     /* nnz per CSR-stream tile */
-constexpr int kSpmvThreads = 256;
+constexpr int kSpmvTile = 4096;     /* nnz per SpMV tile (both kernels) */
+constexpr int kSpmvThreads = 256;   /* block size of the fallback CSR-stream kernel */
+constexpr int kSpmvRowCap = 2048;   /* rows starting in one tile that the TMA-pipelined kernel stages */
+/* vals / colidx are allocated to a whole number of tiles (zero-filled tail) so that every tile is
+ * one fixed-size, 16-byte aligned bulk copy */
+static inline int64_t ohp_padded_nnz(int64_t nnz) { return ((nnz + kSpmvTile - 1) / kSpmvTile) * kSpmvTile + kSpmvTile; }
 
 struct ohp_mesh_s {
   ohp_context ctx;
@@ -101,6 +106,7 @@ struct ohp_mesh_s {
   /* SpMV tiling */
   int32_t *tile_row; /* n_tiles+1: first row of each nnz tile */
   int32_t n_tiles;
+  int32_t max_tile_rows; /* most rows starting inside one tile */
   ohp_halo *halo;    /* dof-level halo plan (NULL when serial) */
 };
 

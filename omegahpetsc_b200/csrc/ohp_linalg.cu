@@ -17,6 +17,7 @@
  *     `check_every` iterations; kernels launched past convergence return immediately.
  */
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -94,7 +95,7 @@ __device__ __forceinline__ void cg_loop_head(ohp_cg_state *st) {
 __device__ void cg_fin_init(ohp_cg_state *st, double zz, double zr, double *hist) {
   const double dp = sqrt(zz);
   st->dp = dp; st->rnorm0 = dp; st->ttol = fmax(st->rtol * dp, st->abstol);
-  st->beta = zr; st->betaold = 1.0; st->its = 0; st->reason = 0; st->done = 0;
+  st->beta = zr; st->betaold = 1.0; st->its = 0; st->reason = 0; st->done = 0; st->x_pending = 0;
   if (hist) hist[0] = dp;
   cg_converged(st, dp);
   cg_loop_head(st);
@@ -102,8 +103,9 @@ __device__ void cg_fin_init(ohp_cg_state *st, double zz, double zr, double *hist
 __device__ void cg_fin_spmv(ohp_cg_state *st, double dpi) {
   st->dpi = dpi;
   st->betaold = st->beta;
-  if (!(dpi > 0.0)) { st->reason = (dpi != dpi) ? -9 : -8; st->its += 1; st->done = 1; return; }
+  if (!(dpi > 0.0)) { st->reason = (dpi != dpi) ? -9 : -8; st->its += 1; st->done = 1; st->x_pending = 0; return; }
   st->alpha = st->beta / dpi;
+  st->x_pending = 1; /* applied by the next k_cg_pupdate, or by k_cg_final_x when the iteration stops */
 }
 __device__ void cg_fin_update(ohp_cg_state *st, double zz, double zr, double *hist, int hist_cap) {
   const double dp = sqrt(zz);
@@ -158,6 +160,152 @@ k_spmv_stream(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ co
   }
 }
 
+/* ------------------------------------------------------------------------------------ */
+/* SpMV, sm_100a path: persistent, warp-specialised, TMA-pipelined.                      */
+/*                                                                                       */
+/* One CTA per SM owns a contiguous run of fixed-size nnz tiles.  A producer warp streams  */
+/* each tile's vals (8 B) and colidx (4 B) into a ring of shared-memory stages with 1-D   */
+/* bulk async copies (cp.async.bulk -> mbarrier complete_tx) and stages the tile's rowptr  */
+/* slice with cp.async; consumer warps wait on the stage's `full` mbarrier, sum whole rows */
+/* (one thread per row, columns in ascending order: the serial CSR order) gathering x     */
+/* through the read-only path, and release the stage through its `empty` mbarrier.  No     */
+/* __syncthreads in the steady state; bytes in flight per SM = STAGES x 24 KB, which is    */
+/* what hides HBM latency (the first CSR-stream kernel was latency-bound at 47 % of peak). */
+/* A row that straddles a tile boundary is carried in a register by the thread that       */
+/* started it (same thread finishes it in the next tile), so the order stays serial.      */
+/* ------------------------------------------------------------------------------------ */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+/* sum_{k in [a,b)} vs[k] * x[cs[k]], ascending k; loads batched 8 at a time for memory-level parallelism */
+__device__ __forceinline__ double row_dot(const double *__restrict__ vs, const int32_t *__restrict__ cs,
+                                          int a, int b, const double *__restrict__ x, double s) {
+  for (int k = a; k < b; k += 8) {
+    double xv[8], vv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool ok = (k + j) < b;
+      const int c = ok ? cs[k + j] : 0;
+      vv[j] = ok ? vs[k + j] : 0.0;
+      xv[j] = ok ? __ldg(x + c) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if ((k + j) < b) s += vv[j] * xv[j];
+  }
+  return s;
+}
+
+constexpr int kTmaRpStride = kSpmvRowCap + 4;           /* rowptr slice + (first row, end row) of the tile */
+constexpr int tma_smem_bytes(int stages) { return stages * (kSpmvTile * 12 + kTmaRpStride * 4) + 2 * stages * 8; }
+
+template <bool CG, int kTmaStages, int kTmaConsumers>
+__global__ void __launch_bounds__(kTmaConsumers + 32, 1)
+k_spmv_tma(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, const double *__restrict__ vals,
+           const double *__restrict__ x, double *__restrict__ y, const int32_t *__restrict__ tile_row, int n_tiles,
+           ohp_cg_state *st, double *partials, unsigned *ticket, double *sums, int fin_inline) {
+  constexpr int T = kSpmvTile, S = kTmaStages, NC = kTmaConsumers;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  if (CG && st->done) return;
+  double *vals_s = reinterpret_cast<double *>(smem_raw);
+  int32_t *cols_s = reinterpret_cast<int32_t *>(vals_s + S * T);
+  int32_t *rp_s = cols_s + S * T;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(rp_s + S * kTmaRpStride);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 33); mbar_init(empty0 + 8 * s, NC / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int t0 = (int)(((int64_t)n_tiles * blockIdx.x) / gridDim.x);
+  const int t1 = (int)(((int64_t)n_tiles * (blockIdx.x + 1)) / gridDim.x);
+  double dot[1] = {0.0};
+  if (warp == NC / 32) {
+    /* ---------------- producer warp ---------------- */
+    for (int t = t0; t < t1; ++t) {
+      const int i = t - t0, s = i % S;
+      mbar_wait(empty0 + 8 * s, ((i / S) & 1) ^ 1);
+      const int rs = __ldg(tile_row + t), re = __ldg(tile_row + t + 1);
+      if (lane == 0) {
+        mbar_expect_tx(full0 + 8 * s, T * 12);
+        tma_load_1d(smem_u32(vals_s + s * T), vals + (size_t)t * T, T * 8, full0 + 8 * s);
+        tma_load_1d(smem_u32(cols_s + s * T), colidx + (size_t)t * T, T * 4, full0 + 8 * s);
+      }
+      int32_t *rp = rp_s + s * kTmaRpStride;
+      for (int j = lane; j <= re - rs; j += 32) cp_async4(smem_u32(rp + j), rowptr + rs + j);
+      if (lane < 2) cp_async4(smem_u32(rp + kSpmvRowCap + 2 + lane), tile_row + t + lane);
+      cp_async_mbar_arrive_noinc(full0 + 8 * s);
+    }
+  } else {
+    /* ---------------- consumer warps ---------------- */
+    double carry = 0.0;
+    int pend = -1;
+    for (int t = t0; t < t1; ++t) {
+      const int i = t - t0, s = i % S;
+      mbar_wait(full0 + 8 * s, (i / S) & 1);
+      const int32_t *rp = rp_s + s * kTmaRpStride;
+      const double *vs = vals_s + s * T;
+      const int32_t *cs = cols_s + s * T;
+      const int rs = rp[kSpmvRowCap + 2], re = rp[kSpmvRowCap + 3];
+      const int base = t * T, lim = base + T;
+      if (pend >= 0) { /* finish (or continue) the row this thread carried over the tile boundary */
+        const int end = rp[0];
+        carry = row_dot(vs, cs, 0, min(end, lim) - base, x, carry);
+        if (end <= lim) { y[pend] = carry; if (CG) dot[0] += carry * __ldg(x + pend); pend = -1; }
+      }
+      for (int r = rs + tid; r < re; r += NC) {
+        const int a = rp[r - rs], b = rp[r - rs + 1];
+        const double sum = row_dot(vs, cs, a - base, min(b, lim) - base, x, 0.0);
+        if (b > lim) { carry = sum; pend = r; }
+        else { y[r] = sum; if (CG) dot[0] += sum * __ldg(x + r); }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + 8 * s);
+    }
+    if (pend >= 0) { /* the row runs past this CTA's last tile: finish it straight from HBM */
+      const int end = __ldg(rowptr + pend + 1);
+      for (int k = t1 * T; k < end; ++k) carry += vals[k] * __ldg(x + colidx[k]);
+      y[pend] = carry;
+      if (CG) dot[0] += carry * __ldg(x + pend);
+    }
+  }
+  if (CG) {
+    if (grid_sum<1>(dot, partials, ticket) && threadIdx.x == 0) {
+      sums[0] = dot[0];
+      if (fin_inline) cg_fin_spmv(st, dot[0]);
+    }
+  }
+}
+
+static bool spmv_use_tma(ohp_mesh m) { return m->max_tile_rows <= kSpmvRowCap - 1 && m->n_tiles > 0; }
+
 static int spmv_smem_bytes(ohp_mesh m) { return (int)sizeof(double) * (kSpmvTile + std::max(1, m->max_row)); }
 
 static int spmv_configure(ohp_mesh m) {
@@ -172,16 +320,53 @@ static int spmv_configure(ohp_mesh m) {
   return 0;
 }
 
-int ohp_spmv_launch(ohp_mat A, const double *x, double *y) {
+template <int S, int NC>
+static int spmv_tma_launch(ohp_mat A, const double *x, double *y, ohp_cg_state *st, double *sums, int fin_inline) {
   ohp_mesh m = A->mesh;
   ohp_context ctx = m->ctx;
-  if (m->n_owned == 0) return 0;
-  OHP_TRY(spmv_configure(m));
-  const int grid = std::min(m->n_tiles, kMaxPartials);
-  k_spmv_stream<false><<<grid, kSpmvThreads, spmv_smem_bytes(m), ctx->stream>>>(
+  static bool configured = false;
+  if (!configured) {
+    OHP_CUDA(cudaFuncSetAttribute(k_spmv_tma<true, S, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_smem_bytes(S)));
+    OHP_CUDA(cudaFuncSetAttribute(k_spmv_tma<false, S, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_smem_bytes(S)));
+    configured = true;
+  }
+  const int grid = std::max(1, std::min(m->n_tiles, ctx->num_sms));
+  if (st) k_spmv_tma<true, S, NC><<<grid, NC + 32, tma_smem_bytes(S), ctx->stream>>>(
+      m->rowptr, m->colidx, A->vals, x, y, m->tile_row, m->n_tiles, st, ctx->d_partials, ctx->d_ticket + 1, sums, fin_inline);
+  else k_spmv_tma<false, S, NC><<<grid, NC + 32, tma_smem_bytes(S), ctx->stream>>>(
       m->rowptr, m->colidx, A->vals, x, y, m->tile_row, m->n_tiles, nullptr, nullptr, nullptr, nullptr, 0);
   OHP_CHECK_LAUNCH(ctx);
   return 0;
+}
+
+/* y = A x on the context stream; with `st` the (x, y) dot and the CG scalar update are fused in */
+static int spmv_enqueue(ohp_mat A, const double *x, double *y, ohp_cg_state *st, double *sums, int fin_inline) {
+  ohp_mesh m = A->mesh;
+  ohp_context ctx = m->ctx;
+  static const char *force = getenv("OHP_SPMV"); /* "stream" forces the fallback kernel; "0".."5" pick a TMA config (A/B runs) */
+  const bool tma = spmv_use_tma(m) && !(force && force[0] == 's');
+  if (tma) {
+    const int cfg = (force && force[0] >= '0' && force[0] <= '9') ? force[0] - '0' : 0;
+    switch (cfg) {
+      case 1: return spmv_tma_launch<3, 384>(A, x, y, st, sums, fin_inline);
+      case 2: return spmv_tma_launch<3, 768>(A, x, y, st, sums, fin_inline);
+      case 3: return spmv_tma_launch<2, 640>(A, x, y, st, sums, fin_inline);
+      default: return spmv_tma_launch<3, 608>(A, x, y, st, sums, fin_inline);
+    }
+  }
+  OHP_TRY(spmv_configure(m));
+  const int grid = std::max(1, std::min(m->n_tiles, kMaxPartials));
+  if (st) k_spmv_stream<true><<<grid, kSpmvThreads, spmv_smem_bytes(m), ctx->stream>>>(
+      m->rowptr, m->colidx, A->vals, x, y, m->tile_row, m->n_tiles, st, ctx->d_partials, ctx->d_ticket + 1, sums, fin_inline);
+  else k_spmv_stream<false><<<grid, kSpmvThreads, spmv_smem_bytes(m), ctx->stream>>>(
+      m->rowptr, m->colidx, A->vals, x, y, m->tile_row, m->n_tiles, nullptr, nullptr, nullptr, nullptr, 0);
+  OHP_CHECK_LAUNCH(ctx);
+  return 0;
+}
+
+int ohp_spmv_launch(ohp_mat A, const double *x, double *y) {
+  if (A->mesh->n_owned == 0) return 0;
+  return spmv_enqueue(A, x, y, nullptr, nullptr, 0);
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -309,8 +494,8 @@ extern "C" int ohp_mat_create(ohp_mesh m, ohp_mat *out) {
   OHP_CUDA(cudaSetDevice(m->ctx->device));
   ohp_mat A = new ohp_mat_s();
   A->mesh = m; A->r = A->z = A->p = A->w = A->dinv = A->hist = nullptr; A->hist_cap = 0;
-  OHP_CUDA(cudaMalloc(&A->vals, sizeof(double) * std::max<int64_t>(1, m->nnz)));
-  OHP_CUDA(cudaMemsetAsync(A->vals, 0, sizeof(double) * std::max<int64_t>(1, m->nnz), m->ctx->stream));
+  OHP_CUDA(cudaMalloc(&A->vals, sizeof(double) * ohp_padded_nnz(m->nnz)));
+  OHP_CUDA(cudaMemsetAsync(A->vals, 0, sizeof(double) * ohp_padded_nnz(m->nnz), m->ctx->stream));
   *out = A;
   return 0;
 }
@@ -365,27 +550,44 @@ k_cg_init(const double *__restrict__ b, double *__restrict__ x, double *__restri
   }
 }
 
-/* p = z + (beta/betaold) p  (first iteration: p = z) */
+/* x += alpha_prev p (the x update of the PREVIOUS iteration, deferred so that p is read once);
+ * p = z + (beta/betaold) p  (first iteration: p = z) */
 __global__ void __launch_bounds__(256)
-k_cg_pupdate(double *__restrict__ p, const double *__restrict__ z, int n, const ohp_cg_state *st) {
+k_cg_pupdate(double *__restrict__ p, const double *__restrict__ z, double *__restrict__ x, int n,
+             const ohp_cg_state *st) {
   if (st->done) return;
   const bool first = (st->its == 0);
   const double bb = first ? 0.0 : st->beta / st->betaold;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    p[i] = first ? z[i] : z[i] + bb * p[i];
+  const double a = st->alpha;
+  if (first) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = z[i];
+  } else {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      const double pi = p[i];
+      x[i] += a * pi;
+      p[i] = z[i] + bb * pi;
+    }
+  }
 }
 
-/* x += a p; r -= a w; z = M^-1 r; (z,z), (z,r) */
+/* the x update still pending when the iteration stops */
+__global__ void __launch_bounds__(256)
+k_cg_final_x(double *__restrict__ x, const double *__restrict__ p, int n, ohp_cg_state *st) {
+  if (!st->x_pending) return;
+  const double a = st->alpha;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] += a * p[i];
+}
+
+/* r -= a w; z = M^-1 r; (z,z), (z,r) */
 template <bool JACOBI>
 __global__ void __launch_bounds__(256)
-k_cg_update(double *__restrict__ x, double *__restrict__ r, double *__restrict__ z, const double *__restrict__ p,
-            const double *__restrict__ w, const double *__restrict__ dinv, int n, ohp_cg_state *st,
+k_cg_update(double *__restrict__ r, double *__restrict__ z, const double *__restrict__ w,
+            const double *__restrict__ dinv, int n, ohp_cg_state *st,
             double *partials, unsigned *ticket, double *sums, double *hist, int hist_cap, int fin_inline) {
   if (st->done) return;
   const double a = st->alpha;
   double s[2] = {0.0, 0.0};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    x[i] += a * p[i];
     const double ri = r[i] - a * w[i];
     r[i] = ri;
     double zi = ri;
@@ -457,9 +659,6 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
   const int serial = (ctx->nranks == 1);
   const int vgrid = vec_grid(ctx, n);
   double *sums = ctx->d_scalars;
-  if (n > 0) OHP_TRY(spmv_configure(m));
-  const int sgrid = std::max(1, std::min(m->n_tiles, kMaxPartials));
-  const int smem = spmv_smem_bytes(m);
 
   if (jac) k_cg_init<true><<<vgrid, 256, 0, st>>>(b->d, x->d, A->r, z, A->dinv, n, ctx->d_cg, ctx->d_partials, ctx->d_ticket, sums, hist, serial);
   else k_cg_init<false><<<vgrid, 256, 0, st>>>(b->d, x->d, A->r, z, A->dinv, n, ctx->d_cg, ctx->d_partials, ctx->d_ticket, sums, hist, serial);
@@ -483,20 +682,18 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
     if (ctx->h_cg->done) break;
     if (launched > o->max_it + check_every) OHP_FAIL(OHP_ERR_LIB, "ohp_ksp_cg: device-side iteration control did not terminate");
     for (int it = 0; it < check_every; ++it) {
-      k_cg_pupdate<<<vgrid, 256, 0, st>>>(A->p, z, n, ctx->d_cg); OHP_CHECK_LAUNCH(ctx);
+      k_cg_pupdate<<<vgrid, 256, 0, st>>>(A->p, z, x->d, n, ctx->d_cg); OHP_CHECK_LAUNCH(ctx);
       if (!serial) OHP_TRY(ohp_halo_exchange(m, A->p));
       const bool timed = (int)prof.size() < 2 * nprof && (launched > 0 || o->max_it <= check_every);
       if (timed) { cudaEvent_t e; OHP_CUDA(cudaEventCreate(&e)); OHP_CUDA(cudaEventRecord(e, st)); prof.push_back(e); }
-      k_spmv_stream<true><<<sgrid, kSpmvThreads, smem, st>>>(m->rowptr, m->colidx, A->vals, A->p, A->w, m->tile_row,
-                                                          m->n_tiles, ctx->d_cg, ctx->d_partials, ctx->d_ticket + 1, sums, serial);
-      OHP_CHECK_LAUNCH(ctx);
+      OHP_TRY(spmv_enqueue(A, A->p, A->w, ctx->d_cg, sums, serial));
       if (timed) { cudaEvent_t e; OHP_CUDA(cudaEventCreate(&e)); OHP_CUDA(cudaEventRecord(e, st)); prof.push_back(e); }
       if (!serial) {
         OHP_TRY(ohp_allreduce_sum(ctx, sums, 1));
         k_cg_fin<<<1, 1, 0, st>>>(ctx->d_cg, sums, 1, hist, hist_cap); OHP_CHECK_LAUNCH(ctx);
       }
-      if (jac) k_cg_update<true><<<vgrid, 256, 0, st>>>(x->d, A->r, z, A->p, A->w, A->dinv, n, ctx->d_cg, ctx->d_partials, ctx->d_ticket, sums, hist, hist_cap, serial);
-      else k_cg_update<false><<<vgrid, 256, 0, st>>>(x->d, A->r, z, A->p, A->w, A->dinv, n, ctx->d_cg, ctx->d_partials, ctx->d_ticket, sums, hist, hist_cap, serial);
+      if (jac) k_cg_update<true><<<vgrid, 256, 0, st>>>(A->r, z, A->w, A->dinv, n, ctx->d_cg, ctx->d_partials, ctx->d_ticket, sums, hist, hist_cap, serial);
+      else k_cg_update<false><<<vgrid, 256, 0, st>>>(A->r, z, A->w, A->dinv, n, ctx->d_cg, ctx->d_partials, ctx->d_ticket, sums, hist, hist_cap, serial);
       OHP_CHECK_LAUNCH(ctx);
       if (!serial) {
         OHP_TRY(ohp_allreduce_sum(ctx, sums, 2));
@@ -505,6 +702,7 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
     }
     launched += check_every;
   }
+  k_cg_final_x<<<vgrid, 256, 0, st>>>(x->d, A->p, n, ctx->d_cg); OHP_CHECK_LAUNCH(ctx);
   res->its = ctx->h_cg->its; res->reason = ctx->h_cg->reason; res->rnorm = ctx->h_cg->dp; res->rnorm0 = ctx->h_cg->rnorm0;
   OHP_CUDA(cudaEventRecord(ev_t1, st));
   OHP_CUDA(cudaEventSynchronize(ev_t1));

@@ -170,7 +170,7 @@ def test_cg_matches_oracle(ctx, oracle_mod, name, pc):
     out = ohp.ksp_cg(J, b, x, ohp.ksp_options(rtol=1e-9, max_it=20000, pc=pc), history=True)
     ref = oracle_mod.cg(rowptr, colidx, J.values(), b.to_host(), rtol=1e-9, maxit=20000, pc=pc, history=True)
     assert out["reason"] == ref["reason"] == 2
-    assert abs(out["its"] - ref["its"]) <= max(2, ref["its"] // 100)
+    assert abs(out["its"] - ref["its"]) <= max(2, ref["its"] // 40)  # rounding-order sensitivity of CG
     # CG amplifies rounding differences (summation order, FMA contraction) exponentially on an
     # ill-conditioned operator: the monitored norms agree to many digits only for the first iterations
     k = min(out["its"], ref["its"], 8)
@@ -211,7 +211,7 @@ def test_newton_matches_oracle(ctx, oracle_mod, expected, name):
     ref = oracle_mod.newton(0, cells, coords, gidx, N, rowptr, colidx, ksp_rtol=1e-9, ksp_maxit=100000)
     assert (res["its"], res["reason"]) == (ref["snes_its"], ref["reason"]) == (1, 3)
     assert (res["n_residual"], res["n_jacobian"]) == (2, 1)
-    assert abs(res["ksp_its"] - ref["ksp_its"]) <= max(2, ref["ksp_its"] // 100)
+    assert abs(res["ksp_its"] - ref["ksp_its"]) <= max(2, ref["ksp_its"] // 40)
     assert res["fnorm0"] == pytest.approx(ref["norms"][0], rel=1e-12)
     uh = u.to_host()
     assert np.abs(uh - ref["u"]).max() <= 1e-7 * np.abs(ref["u"]).max()
@@ -306,6 +306,9 @@ def test_large_box_properties(ctx, oracle_mod):
     y.from_host(yh)
     m.residual(0, u, Fu)
     J.mult(u, Au)
+    # direct SpMV parity at a size where CTAs own many tiles and rows straddle tile boundaries
+    Ao = oracle_mod.spmv(rowptr, colidx, J.values(), uh, omp=True)
+    assert np.abs(Au.to_host() - Ao).max() <= 1e-13 * np.abs(Ao).max()
     lin = Au.to_host() + F0.to_host() - Fu.to_host()
     assert np.abs(lin).max() <= 1e-11 * np.abs(Fu.to_host()).max()
     yAu = y.dot(Au)
