@@ -211,7 +211,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import omegahpetsc_b200 as ohp
-    from omegahpetsc_b200 import meshgen
+    from omegahpetsc_b200 import partition
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -230,8 +230,8 @@ def run_ours(args):
     dim = coords.shape[1]
     n_cells_global, n_verts_global = cells.shape[0], coords.shape[0]
     if world > 1:
-        eo, vo = meshgen.chain_partition(cells, coords, world)
-        part = meshgen.local_part(cells, coords, eo, vo, rank)
+        eo, vo = partition.chain_partition(cells, coords, world)
+        part = partition.local_part(cells, coords, eo, vo, rank)
         lcells, lcoords = part["cells"], part["coords"]
     else:
         part, lcells, lcoords = None, cells, coords
@@ -239,7 +239,8 @@ def run_ours(args):
     def build_mesh():
         m = ohp.Mesh(ctx, lcells, lcoords)
         if part is not None:
-            attach_ghosts(m, part, vo, rank, world, dist)
+            m.set_ghosts(part["ghost_local"], part["ghost_owner"],
+                         partition.resolve_ghost_roots(part, vo, rank, world, dist.all_gather_object))
         return m.setup()
 
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
@@ -367,24 +368,6 @@ def run_ours(args):
                                                     "Newton step, D2H of the solution"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu}
     print(json.dumps(line))
-
-
-def attach_ghosts(m, part, vert_owner, rank, world, dist):
-    """PetscSFSetGraph (ex12.cpp:873-876): root index = the ghost's LOCAL vertex index on its owner.
-    Each rank publishes its global->local vertex map for the vertices it owns (host all-gather)."""
-    owned_g = part["gverts"][vert_owner[part["gverts"]] == rank]
-    owned_l = np.nonzero(vert_owner[part["gverts"]] == rank)[0]
-    tables = [None] * world
-    dist.all_gather_object(tables, (owned_g, owned_l))
-    owner_vertex = np.empty(part["ghost_local"].size, dtype=np.int32)
-    for r in range(world):
-        sel = part["ghost_owner"] == r
-        if sel.any():
-            g, l = tables[r]
-            pos = np.searchsorted(g, part["ghost_gvert"][sel])
-            assert np.array_equal(g[pos], part["ghost_gvert"][sel])
-            owner_vertex[sel] = l[pos]
-    m.set_ghosts(part["ghost_local"], part["ghost_owner"], owner_vertex)
 
 
 def main():

@@ -1,18 +1,361 @@
 /*
- * ohp_comm.cu -- communicator, halo plans and halo exchange (stub while the serial path is
- * brought up; see the multi-GPU section of DESIGN.md).
+ * ohp_comm.cu -- communicator, halo plans and halo exchange for the partitioned path.
+ *
+ * Replaces MPI as used through Omega_h::Comm/Dist (ex12.cpp:530-563,731-765) and PETSc's PetscSF
+ * (ex12.cpp:873-876,937-939): the point SF given to ohp_mesh_set_ghosts becomes
+ *   (1) a vertex-level plan (ghost vertex <- owner vertex) used during setup to fetch the owners'
+ *       boundary labels and dof numbers (PetscSFBcast of the section, PETSc-internal), and
+ *   (2) a dof-level plan for vectors: ghost dofs are numbered after the owned ones, grouped by
+ *       owner rank and ordered by the owner's dof number, so every receive lands directly in the
+ *       vector's ghost tail (DMGlobalToLocal / the MPIAIJ MatMult scatter, PETSc-internal);
+ * dot products are summed with an all-reduce (VecDot's MPI_Allreduce).
+ * One process per GPU; transport is NCCL over NVLink/NVSwitch, loaded with dlopen so that the
+ * library shares whatever libnccl the host process (e.g. torch) already mapped.
  */
+#include <dlfcn.h>
+#include <nccl.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+
 #include "ohp_internal.h"
 
-struct ohp_halo { int dummy; };
+namespace {
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
 
-extern "C" int ohp_comm_unique_id(void *) { OHP_FAIL(OHP_ERR_SUP, "ohp_comm_unique_id: not built yet"); }
-extern "C" int ohp_comm_init(ohp_context, int, int, const void *) { OHP_FAIL(OHP_ERR_SUP, "ohp_comm_init: not built yet"); }
-extern "C" int ohp_comm_rank_size(ohp_context ctx, int *rank, int *nranks) { *rank = ctx->rank; *nranks = ctx->nranks; return 0; }
+int nccl_load() {
+  if (g_nccl.lib) return 0;
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) OHP_FAIL(OHP_ERR_LIB, "cannot load libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                        \
+  do {                                                                          \
+    *(void **)(&g_nccl.field) = dlsym(h, name);                                 \
+    if (!g_nccl.field) OHP_FAIL(OHP_ERR_LIB, "libnccl: missing symbol %s", name); \
+  } while (0)
+  SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
+  SYM(AllReduce, "ncclAllReduce"); SYM(AllGather, "ncclAllGather"); SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv");
+  SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd"); SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+  g_nccl.lib = h;
+  return 0;
+}
+}  // namespace
 
-int ohp_halo_build(ohp_mesh) { OHP_FAIL(OHP_ERR_SUP, "halo: not built yet"); }
-void ohp_halo_free(ohp_halo *h) { delete h; }
-int ohp_halo_exchange(ohp_mesh, double *) { OHP_FAIL(OHP_ERR_SUP, "halo: not built yet"); }
-int ohp_allreduce_sum(ohp_context, double *, int) { OHP_FAIL(OHP_ERR_SUP, "allreduce: not built yet"); }
-int ohp_vertex_halo_i32(ohp_mesh, int32_t *) { OHP_FAIL(OHP_ERR_SUP, "halo: not built yet"); }
-int ohp_allgather_i64(ohp_context, int64_t, std::vector<int64_t> &) { OHP_FAIL(OHP_ERR_SUP, "allgather: not built yet"); }
+#define OHP_NCCL(expr)                                                                       \
+  do {                                                                                       \
+    ncclResult_t r__ = (expr);                                                               \
+    if (r__ != ncclSuccess)                                                                  \
+      OHP_FAIL(OHP_ERR_LIB, "%s:%d NCCL error %s: %s", __FILE__, __LINE__, #expr, g_nccl.GetErrorString(r__)); \
+  } while (0)
+
+static inline unsigned nblk(int64_t n, int bs) { return (unsigned)std::max<int64_t>(1, (n + bs - 1) / bs); }
+
+extern "C" int ohp_comm_unique_id(void *out) {
+  if (!out) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_comm_unique_id: null buffer");
+  OHP_TRY(nccl_load());
+  ncclUniqueId id;
+  OHP_NCCL(g_nccl.GetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(out, &id, sizeof(id));
+  return 0;
+}
+
+extern "C" int ohp_comm_init(ohp_context ctx, int nranks, int rank, const void *uid) {
+  if (!ctx || !uid) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_comm_init: null argument");
+  if (nranks < 1 || rank < 0 || rank >= nranks) OHP_FAIL(OHP_ERR_ARG_OUTOFRANGE, "ohp_comm_init: rank %d of %d", rank, nranks);
+  if (ctx->comm) OHP_FAIL(OHP_ERR_ORDER, "ohp_comm_init: communicator already attached");
+  OHP_TRY(nccl_load());
+  OHP_CUDA(cudaSetDevice(ctx->device));
+  ncclUniqueId id;
+  memcpy(&id, uid, sizeof(id));
+  ncclComm_t comm;
+  OHP_NCCL(g_nccl.CommInitRank(&comm, nranks, id, rank));
+  ctx->comm = comm; ctx->rank = rank; ctx->nranks = nranks;
+  return 0;
+}
+
+extern "C" int ohp_comm_rank_size(ohp_context ctx, int *rank, int *nranks) {
+  *rank = ctx->rank; *nranks = ctx->nranks;
+  return 0;
+}
+
+void ohp_comm_destroy(ohp_context ctx) {
+  if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->comm);
+  ctx->comm = nullptr;
+}
+
+int ohp_allreduce_sum(ohp_context ctx, double *d_vals, int n) {
+  if (ctx->nranks == 1) return 0;
+  OHP_NCCL(g_nccl.AllReduce(d_vals, d_vals, (size_t)n, ncclFloat64, ncclSum, (ncclComm_t)ctx->comm, ctx->stream));
+  return 0;
+}
+
+int ohp_allgather_i64(ohp_context ctx, int64_t mine, std::vector<int64_t> &all) {
+  all.assign(ctx->nranks, mine);
+  if (ctx->nranks == 1) return 0;
+  int64_t *d;
+  OHP_CUDA(cudaMalloc(&d, sizeof(int64_t) * (ctx->nranks + 1)));
+  OHP_CUDA(cudaMemcpyAsync(d + ctx->nranks, &mine, sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+  OHP_NCCL(g_nccl.AllGather(d + ctx->nranks, d, 1, ncclInt64, (ncclComm_t)ctx->comm, ctx->stream));
+  OHP_CUDA(cudaMemcpyAsync(all.data(), d, sizeof(int64_t) * ctx->nranks, cudaMemcpyDeviceToHost, ctx->stream));
+  OHP_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* sparse neighbour exchange of int32 lists (setup only): the role of Omega_h's           */
+/* Dist::exch (ex12.cpp:562,740,765).  send[q] goes to rank q; returns recv[q] from q.    */
+/* ------------------------------------------------------------------------------------ */
+static int exchange_lists(ohp_context ctx, const std::vector<std::vector<int32_t>> &send,
+                          std::vector<std::vector<int32_t>> &recv) {
+  const int P = ctx->nranks;
+  cudaStream_t st = ctx->stream;
+  std::vector<int64_t> counts(P), matrix((size_t)P * P);
+  int64_t *d_counts;
+  OHP_CUDA(cudaMalloc(&d_counts, sizeof(int64_t) * ((size_t)P * P + P)));
+  for (int q = 0; q < P; ++q) counts[q] = (int64_t)send[q].size();
+  OHP_CUDA(cudaMemcpyAsync(d_counts + (size_t)P * P, counts.data(), sizeof(int64_t) * P, cudaMemcpyHostToDevice, st));
+  OHP_NCCL(g_nccl.AllGather(d_counts + (size_t)P * P, d_counts, P, ncclInt64, (ncclComm_t)ctx->comm, st));
+  OHP_CUDA(cudaMemcpyAsync(matrix.data(), d_counts, sizeof(int64_t) * P * P, cudaMemcpyDeviceToHost, st));
+  OHP_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_counts);
+  int64_t ns = 0, nr = 0;
+  std::vector<int64_t> soff(P + 1, 0), roff(P + 1, 0);
+  for (int q = 0; q < P; ++q) { soff[q + 1] = soff[q] + matrix[(size_t)ctx->rank * P + q]; roff[q + 1] = roff[q] + matrix[(size_t)q * P + ctx->rank]; }
+  ns = soff[P]; nr = roff[P];
+  int32_t *d_s, *d_r;
+  OHP_CUDA(cudaMalloc(&d_s, sizeof(int32_t) * std::max<int64_t>(1, ns)));
+  OHP_CUDA(cudaMalloc(&d_r, sizeof(int32_t) * std::max<int64_t>(1, nr)));
+  std::vector<int32_t> flat((size_t)ns);
+  for (int q = 0; q < P; ++q) std::copy(send[q].begin(), send[q].end(), flat.begin() + soff[q]);
+  OHP_CUDA(cudaMemcpyAsync(d_s, flat.data(), sizeof(int32_t) * ns, cudaMemcpyHostToDevice, st));
+  OHP_NCCL(g_nccl.GroupStart());
+  for (int q = 0; q < P; ++q) {
+    if (q == ctx->rank) continue;
+    if (soff[q + 1] > soff[q]) OHP_NCCL(g_nccl.Send(d_s + soff[q], (size_t)(soff[q + 1] - soff[q]), ncclInt32, q, (ncclComm_t)ctx->comm, st));
+    if (roff[q + 1] > roff[q]) OHP_NCCL(g_nccl.Recv(d_r + roff[q], (size_t)(roff[q + 1] - roff[q]), ncclInt32, q, (ncclComm_t)ctx->comm, st));
+  }
+  OHP_NCCL(g_nccl.GroupEnd());
+  std::vector<int32_t> rflat((size_t)nr);
+  OHP_CUDA(cudaMemcpyAsync(rflat.data(), d_r, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, st));
+  OHP_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_s); cudaFree(d_r);
+  recv.assign(P, {});
+  for (int q = 0; q < P; ++q) recv[q].assign(rflat.begin() + roff[q], rflat.begin() + roff[q + 1]);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* halo plans                                                                            */
+/* ------------------------------------------------------------------------------------ */
+struct ohp_halo {
+  /* vertex level: neighbour q sends me the values of its vertices v_req[q]; I send v_serve[q] */
+  std::vector<int> nbr;                      /* ranks I exchange with (either direction) */
+  std::vector<int64_t> v_soff, v_roff;       /* per neighbour offsets into the flat lists */
+  int32_t *d_v_send_idx = nullptr;           /* my vertices other ranks ghost */
+  int32_t *d_v_recv_idx = nullptr;           /* my ghost vertices, grouped by owner */
+  int32_t *d_v_sbuf = nullptr, *d_v_rbuf = nullptr;
+  int64_t v_ns = 0, v_nr = 0;
+  /* dof level */
+  std::vector<int> d_nbr;
+  std::vector<int64_t> d_soff, d_roff;       /* send offsets into d_send_ldof; recv offsets into the ghost tail */
+  int32_t *d_send_ldof = nullptr;
+  double *d_sbuf = nullptr;
+  int64_t d_ns = 0, d_nr = 0;
+};
+
+void ohp_halo_free(ohp_halo *h) {
+  if (!h) return;
+  cudaFree(h->d_v_send_idx); cudaFree(h->d_v_recv_idx); cudaFree(h->d_v_sbuf); cudaFree(h->d_v_rbuf);
+  cudaFree(h->d_send_ldof); cudaFree(h->d_sbuf);
+  delete h;
+}
+
+static int vertex_plan_build(ohp_mesh m) {
+  ohp_context ctx = m->ctx;
+  const int P = ctx->nranks;
+  ohp_halo *h = new ohp_halo();
+  m->halo = h;
+  const int nleaf = (int)m->ghost_vertex.size();
+  /* my requests, grouped by owner rank, ordered by the owner's vertex index */
+  std::vector<int> order(nleaf);
+  std::iota(order.begin(), order.end(), 0);
+  std::sort(order.begin(), order.end(), [&](int a, int b) {
+    if (m->ghost_owner_rank[a] != m->ghost_owner_rank[b]) return m->ghost_owner_rank[a] < m->ghost_owner_rank[b];
+    if (m->ghost_owner_vertex[a] != m->ghost_owner_vertex[b]) return m->ghost_owner_vertex[a] < m->ghost_owner_vertex[b];
+    return m->ghost_vertex[a] < m->ghost_vertex[b];
+  });
+  std::vector<std::vector<int32_t>> req(P), serve;
+  std::vector<int32_t> recv_idx;
+  recv_idx.reserve(nleaf);
+  for (int i : order) { req[m->ghost_owner_rank[i]].push_back(m->ghost_owner_vertex[i]); recv_idx.push_back(m->ghost_vertex[i]); }
+  OHP_TRY(exchange_lists(ctx, req, serve));
+  std::vector<int32_t> send_idx;
+  h->v_soff.assign(1, 0); h->v_roff.assign(1, 0);
+  for (int q = 0; q < P; ++q) {
+    if (req[q].empty() && serve[q].empty()) continue;
+    for (int32_t v : serve[q]) {
+      if (v < 0 || v >= m->nV) OHP_FAIL(OHP_ERR_ARG_OUTOFRANGE, "point SF: rank %d asks for vertex %d of rank %d (has %d)", q, v, ctx->rank, m->nV);
+      send_idx.push_back(v);
+    }
+    h->nbr.push_back(q);
+    h->v_soff.push_back((int64_t)send_idx.size());
+    h->v_roff.push_back(h->v_roff.back() + (int64_t)req[q].size());
+  }
+  h->v_ns = (int64_t)send_idx.size(); h->v_nr = (int64_t)recv_idx.size();
+  OHP_CUDA(cudaMalloc(&h->d_v_send_idx, sizeof(int32_t) * std::max<int64_t>(1, h->v_ns)));
+  OHP_CUDA(cudaMalloc(&h->d_v_recv_idx, sizeof(int32_t) * std::max<int64_t>(1, h->v_nr)));
+  OHP_CUDA(cudaMalloc(&h->d_v_sbuf, sizeof(int32_t) * std::max<int64_t>(1, h->v_ns)));
+  OHP_CUDA(cudaMalloc(&h->d_v_rbuf, sizeof(int32_t) * std::max<int64_t>(1, h->v_nr)));
+  OHP_CUDA(cudaMemcpyAsync(h->d_v_send_idx, send_idx.data(), sizeof(int32_t) * h->v_ns, cudaMemcpyHostToDevice, ctx->stream));
+  OHP_CUDA(cudaMemcpyAsync(h->d_v_recv_idx, recv_idx.data(), sizeof(int32_t) * h->v_nr, cudaMemcpyHostToDevice, ctx->stream));
+  OHP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+__global__ void k_gather_i32(const int32_t *src, const int32_t *idx, int64_t n, int32_t *out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = src[idx[i]];
+}
+__global__ void k_scatter_i32(int32_t *dst, const int32_t *idx, int64_t n, const int32_t *in) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[idx[i]] = in[i];
+}
+__global__ void k_gather_f64(const double *__restrict__ src, const int32_t *__restrict__ idx, int64_t n, double *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = src[idx[i]];
+}
+
+/* ghost entries of a per-vertex int32 array <- the owners' entries */
+int ohp_vertex_halo_i32(ohp_mesh m, int32_t *data) {
+  ohp_context ctx = m->ctx;
+  if (ctx->nranks == 1) return 0;
+  if (!m->halo) OHP_TRY(vertex_plan_build(m));
+  ohp_halo *h = m->halo;
+  cudaStream_t st = ctx->stream;
+  if (h->v_ns) { k_gather_i32<<<nblk(h->v_ns, 256), 256, 0, st>>>(data, h->d_v_send_idx, h->v_ns, h->d_v_sbuf); OHP_CHECK_LAUNCH(ctx); }
+  OHP_NCCL(g_nccl.GroupStart());
+  for (size_t k = 0; k < h->nbr.size(); ++k) {
+    const int64_t ns = h->v_soff[k + 1] - h->v_soff[k], nr = h->v_roff[k + 1] - h->v_roff[k];
+    if (ns) OHP_NCCL(g_nccl.Send(h->d_v_sbuf + h->v_soff[k], (size_t)ns, ncclInt32, h->nbr[k], (ncclComm_t)ctx->comm, st));
+    if (nr) OHP_NCCL(g_nccl.Recv(h->d_v_rbuf + h->v_roff[k], (size_t)nr, ncclInt32, h->nbr[k], (ncclComm_t)ctx->comm, st));
+  }
+  OHP_NCCL(g_nccl.GroupEnd());
+  if (h->v_nr) { k_scatter_i32<<<nblk(h->v_nr, 256), 256, 0, st>>>(data, h->d_v_recv_idx, h->v_nr, h->d_v_rbuf); OHP_CHECK_LAUNCH(ctx); }
+  return 0;
+}
+
+__global__ void k_ldof_gid(int64_t *gid, int n_owned, int64_t start, const int64_t *ghost_gid, int n_ghost) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_owned) gid[i] = start + i;
+  else if (i < n_owned + n_ghost) gid[i] = ghost_gid[i - n_owned];
+}
+
+/* global numbering across ranks + ghost dofs + the dof-level plan (called from ohp_mesh_setup
+ * once lidx holds the owned rows) */
+int ohp_halo_build(ohp_mesh m) {
+  ohp_context ctx = m->ctx;
+  const int P = ctx->nranks;
+  cudaStream_t st = ctx->stream;
+  if (!m->halo) OHP_TRY(vertex_plan_build(m));
+  ohp_halo *h = m->halo;
+  /* rank offsets: exclusive scan of the owned counts (global section, ranks concatenated) */
+  std::vector<int64_t> all;
+  OHP_TRY(ohp_allgather_i64(ctx, m->n_owned, all));
+  std::vector<int64_t> start(P + 1, 0);
+  for (int q = 0; q < P; ++q) start[q + 1] = start[q] + all[q];
+  m->row_start = start[ctx->rank]; m->n_global = start[P];
+  /* owners' local dof numbers for my ghost vertices */
+  int32_t *d_tmp;
+  OHP_CUDA(cudaMalloc(&d_tmp, sizeof(int32_t) * std::max(1, m->nV)));
+  OHP_CUDA(cudaMemcpyAsync(d_tmp, m->lidx, sizeof(int32_t) * m->nV, cudaMemcpyDeviceToDevice, st));
+  OHP_TRY(ohp_vertex_halo_i32(m, d_tmp));
+  const int nleaf = (int)m->ghost_vertex.size();
+  std::vector<int32_t> owner_ldof_all(m->nV);
+  OHP_CUDA(cudaMemcpyAsync(owner_ldof_all.data(), d_tmp, sizeof(int32_t) * m->nV, cudaMemcpyDeviceToHost, st));
+  OHP_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_tmp);
+  /* unconstrained ghosts, ordered by (owner rank, owner dof): contiguous receive ranges */
+  struct G { int rank; int32_t ldof; int32_t vertex; };
+  std::vector<G> gh;
+  for (int i = 0; i < nleaf; ++i) {
+    const int32_t l = owner_ldof_all[m->ghost_vertex[i]];
+    if (l >= 0) gh.push_back({m->ghost_owner_rank[i], l, m->ghost_vertex[i]});
+  }
+  std::sort(gh.begin(), gh.end(), [](const G &a, const G &b) { return a.rank != b.rank ? a.rank < b.rank : a.ldof < b.ldof; });
+  m->n_ghost = (int32_t)gh.size();
+  std::vector<int32_t> lidx(m->nV);
+  OHP_CUDA(cudaMemcpyAsync(lidx.data(), m->lidx, sizeof(int32_t) * m->nV, cudaMemcpyDeviceToHost, st));
+  OHP_CUDA(cudaStreamSynchronize(st));
+  std::vector<int64_t> ghost_gid(gh.size());
+  std::vector<std::vector<int32_t>> req(P), serve;
+  for (size_t k = 0; k < gh.size(); ++k) {
+    lidx[gh[k].vertex] = m->n_owned + (int32_t)k;
+    ghost_gid[k] = start[gh[k].rank] + gh[k].ldof;
+    req[gh[k].rank].push_back(gh[k].ldof);
+  }
+  OHP_CUDA(cudaMemcpyAsync(m->lidx, lidx.data(), sizeof(int32_t) * m->nV, cudaMemcpyHostToDevice, st));
+  int64_t *d_ggid;
+  OHP_CUDA(cudaMalloc(&d_ggid, sizeof(int64_t) * std::max<size_t>(1, gh.size())));
+  OHP_CUDA(cudaMemcpyAsync(d_ggid, ghost_gid.data(), sizeof(int64_t) * gh.size(), cudaMemcpyHostToDevice, st));
+  OHP_CUDA(cudaMalloc(&m->ldof_gid, sizeof(int64_t) * std::max(1, m->n_owned + m->n_ghost)));
+  k_ldof_gid<<<nblk(m->n_owned + m->n_ghost, 256), 256, 0, st>>>(m->ldof_gid, m->n_owned, m->row_start, d_ggid, m->n_ghost);
+  OHP_CHECK_LAUNCH(ctx);
+  OHP_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_ggid);
+  /* who needs which of my dofs */
+  OHP_TRY(exchange_lists(ctx, req, serve));
+  std::vector<int32_t> send_ldof;
+  h->d_soff.assign(1, 0); h->d_roff.assign(1, 0);
+  for (int q = 0; q < P; ++q) {
+    if (req[q].empty() && serve[q].empty()) continue;
+    for (int32_t l : serve[q]) {
+      if (l < 0 || l >= m->n_owned) OHP_FAIL(OHP_ERR_ARG_OUTOFRANGE, "halo: rank %d asks for dof %d of rank %d", q, l, ctx->rank);
+      send_ldof.push_back(l);
+    }
+    h->d_nbr.push_back(q);
+    h->d_soff.push_back((int64_t)send_ldof.size());
+    h->d_roff.push_back(h->d_roff.back() + (int64_t)req[q].size());
+  }
+  h->d_ns = (int64_t)send_ldof.size(); h->d_nr = m->n_ghost;
+  OHP_CUDA(cudaMalloc(&h->d_send_ldof, sizeof(int32_t) * std::max<int64_t>(1, h->d_ns)));
+  OHP_CUDA(cudaMalloc(&h->d_sbuf, sizeof(double) * std::max<int64_t>(1, h->d_ns)));
+  OHP_CUDA(cudaMemcpyAsync(h->d_send_ldof, send_ldof.data(), sizeof(int32_t) * h->d_ns, cudaMemcpyHostToDevice, st));
+  OHP_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+/* DMGlobalToLocal / MatMult scatter: x[n_owned + k] <- owner's value of ghost dof k */
+int ohp_halo_exchange(ohp_mesh m, double *x) {
+  ohp_context ctx = m->ctx;
+  if (ctx->nranks == 1) return 0;
+  ohp_halo *h = m->halo;
+  if (!h) OHP_FAIL(OHP_ERR_ORDER, "ohp_halo_exchange: no halo plan");
+  cudaStream_t st = ctx->stream;
+  if (h->d_ns) { k_gather_f64<<<nblk(h->d_ns, 256), 256, 0, st>>>(x, h->d_send_ldof, h->d_ns, h->d_sbuf); OHP_CHECK_LAUNCH(ctx); }
+  if (h->d_nbr.empty()) return 0;
+  OHP_NCCL(g_nccl.GroupStart());
+  for (size_t k = 0; k < h->d_nbr.size(); ++k) {
+    const int64_t ns = h->d_soff[k + 1] - h->d_soff[k], nr = h->d_roff[k + 1] - h->d_roff[k];
+    if (ns) OHP_NCCL(g_nccl.Send(h->d_sbuf + h->d_soff[k], (size_t)ns, ncclFloat64, h->d_nbr[k], (ncclComm_t)ctx->comm, st));
+    if (nr) OHP_NCCL(g_nccl.Recv(x + m->n_owned + h->d_roff[k], (size_t)nr, ncclFloat64, h->d_nbr[k], (ncclComm_t)ctx->comm, st));
+  }
+  OHP_NCCL(g_nccl.GroupEnd());
+  return 0;
+}

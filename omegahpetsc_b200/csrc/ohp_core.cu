@@ -69,6 +69,7 @@ extern "C" int ohp_finalize(ohp_context c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  ohp_comm_destroy(c);
   cudaFree(c->d_partials); cudaFree(c->d_ticket); cudaFree(c->d_scalars);
   cudaFreeHost(c->h_scalars); cudaFree(c->d_cg); cudaFreeHost(c->h_cg); cudaFree(c->d_flag);
   cudaStreamDestroy(c->stream);

@@ -2,8 +2,7 @@
 nx*ny quads, each cut on the same diagonal, vertices row-major; the unit cube split into
 nx*ny*nz hexes x 6 Kuhn tetrahedra.  These stand in for Omega_h::build_box (ex12.cpp:805), whose
 Hilbert reordering is Omega_h-internal; parity is "same inputs -> same outputs", so the generator
-only has to be deterministic.  Also the strip / slab partitioner used for the multi-GPU runs
-(chain topology, like the XGC picparts)."""
+only has to be deterministic.  The strip / slab partitioner for the multi-GPU runs is in partition.py."""
 import numpy as np
 
 
@@ -51,38 +50,3 @@ def _alloc(shape, dtype, pinned):
     import torch
     t = torch.empty(shape, dtype={np.float64: torch.float64, np.int32: torch.int32}[dtype], pin_memory=True)
     return t.numpy()
-
-
-def chain_partition(cells, coords, nparts, axis=None):
-    """Element partition into `nparts` strips/slabs of (nearly) equal element count along one
-    coordinate axis, vertex owner = lowest part among the elements touching it (so ghosts of part
-    r live on parts < r, the XGC picpart convention)."""
-    dim = coords.shape[1]
-    if axis is None:
-        axis = dim - 1
-    cent = coords[cells][:, :, axis].mean(axis=1)
-    order = np.argsort(cent, kind="stable")
-    elem_owner = np.empty(cells.shape[0], dtype=np.int32)
-    bounds = np.linspace(0, cells.shape[0], nparts + 1).astype(np.int64)
-    for r in range(nparts):
-        elem_owner[order[bounds[r]:bounds[r + 1]]] = r
-    vert_owner = np.full(coords.shape[0], nparts, dtype=np.int32)
-    np.minimum.at(vert_owner, cells.reshape(-1), np.repeat(elem_owner, cells.shape[1]))
-    return elem_owner, vert_owner
-
-
-def local_part(cells, coords, elem_owner, vert_owner, rank):
-    """Rank-local mesh for the owner-computes assembly: every element touching a vertex owned by
-    `rank` (owned elements + one layer of overlap), its vertices in ascending global order, and
-    the ghost list (local vertex, owner rank, GLOBAL vertex id of the root)."""
-    touch = (vert_owner[cells] == rank).any(axis=1)
-    lc = cells[touch]
-    gverts = np.unique(lc.reshape(-1))
-    g2l = np.full(coords.shape[0], -1, dtype=np.int64)
-    g2l[gverts] = np.arange(gverts.size)
-    lcells = g2l[lc].astype(np.int32)
-    lcoords = np.ascontiguousarray(coords[gverts])
-    ghost = np.nonzero(vert_owner[gverts] != rank)[0].astype(np.int32)
-    return dict(cells=lcells, coords=lcoords, gverts=gverts, ghost_local=ghost,
-                ghost_owner=vert_owner[gverts[ghost]].astype(np.int32), ghost_gvert=gverts[ghost],
-                elem_global=np.nonzero(touch)[0])

@@ -1,0 +1,132 @@
+"""Multi-GPU parity worker: run under torch.distributed.run with one rank per GPU.
+Correctness reference = the single-process oracle on the UNPARTITIONED mesh: the global
+numbering differs from the serial one by a permutation (ranks concatenated), so rows, columns and
+vector entries are compared through global VERTEX ids."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import omegahpetsc_b200 as ohp  # noqa: E402
+from omegahpetsc_b200 import meshgen, partition  # noqa: E402
+
+
+def load(name, world):
+    from conftest import golden_mesh_path
+    if name == "24k_4p":  # the reference's own 4-part XGC partition (ex12.cpp:810-813 inputs)
+        o = ohp.Osh(golden_mesh_path("24k_4p_0.osh"))
+        cells, coords = o.elem_verts(), o.coords()
+        eo, vo = o.tag(2, "ownership"), o.tag(0, "ownership")
+        if world != 4:  # fewer GPUs: merge consecutive parts
+            eo, vo = eo * world // 4, vo * world // 4
+        return cells, coords, eo.astype(np.int32), vo.astype(np.int32)
+    if name.startswith("box2d_"):
+        n = int(name.split("_")[1])
+        cells, coords = meshgen.box2d(n, n + 3)
+    elif name.startswith("box3d_"):
+        n = int(name.split("_")[1])
+        cells, coords = meshgen.box3d(n, n + 1, n + 2)
+    else:
+        raise SystemExit("unknown mesh " + name)
+    eo, vo = partition.chain_partition(cells, coords, world)
+    return cells, coords, eo, vo
+
+
+def main():
+    name = sys.argv[1]
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = ohp.Context(local)
+    ids = [ohp.Context.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    ctx.comm_init(world, rank, ids[0])
+    assert ctx.rank_size() == (rank, world)
+
+    cells, coords, eo, vo = load(name, world)
+    part = partition.local_part(cells, coords, eo, vo, rank)
+    m = ohp.Mesh(ctx, part["cells"], part["coords"])
+    m.set_ghosts(part["ghost_local"], part["ghost_owner"],
+                 partition.resolve_ghost_roots(part, vo, rank, world, dist.all_gather_object))
+    m.setup()
+    info = m.info()
+
+    import oracle
+    nV = coords.shape[0]
+    bnd = oracle.mark_boundary(cells, nV)
+    gidx, N = oracle.numbering(bnd)
+    rowptr, colidx = oracle.pattern(cells, gidx, N)
+    gv = part["gverts"]
+    owned = vo[gv] == rank
+    # boundary labels (owners' truth on ghosts) and numbering: owned free vertices, ascending, ranks concatenated
+    assert np.array_equal(m.boundary(), bnd[gv]), "boundary label"
+    counts = [None] * world
+    dist.all_gather_object(counts, int((owned & (bnd[gv] == 0)).sum()))
+    start = int(np.sum(counts[:rank]))
+    assert (info.n_owned, info.row_start, info.n_global) == (counts[rank], start, N)
+    num = m.numbering()
+    free_owned = owned & (bnd[gv] == 0)
+    assert np.array_equal(num[free_owned], start + np.arange(counts[rank])), "owned numbering"
+    assert (num[bnd[gv] == 1] == -1).all()
+    # global dof -> global vertex table, to compare columns
+    tabs = [None] * world
+    dist.all_gather_object(tabs, gv[free_owned])
+    dof2vert = np.concatenate(tabs)
+    assert np.array_equal(np.sort(dof2vert), np.nonzero(bnd == 0)[0])
+    ghost_free = (~owned) & (bnd[gv] == 0)
+    assert np.array_equal(dof2vert[num[ghost_free]], gv[ghost_free]), "ghost numbering comes from the owner"
+    # pattern: every local row == the oracle's row, as sets of vertex ids (bit-exact after the permutation)
+    rp, ci = m.csr()
+    ser_vert = np.nonzero(gidx >= 0)[0]  # serial dof -> vertex
+    u_or = np.sin(3 * coords[ser_vert, 0]) * np.cos(2 * coords[ser_vert, 1])
+    J, u, F = m.create_matrix(), m.create_global_vector(), m.create_global_vector()
+    vert2mine = np.full(nV, -1)
+    vert2mine[dof2vert[start:start + info.n_owned]] = np.arange(info.n_owned)
+    u.from_host(np.sin(3 * coords[dof2vert[start:start + info.n_owned], 0]) * np.cos(2 * coords[dof2vert[start:start + info.n_owned], 1]))
+    for problem in (0, 2):
+        vals_or = oracle.jacobian(problem, cells, coords, gidx, N, u_or, rowptr, colidx)
+        F_or = oracle.residual(problem, cells, coords, gidx, N, u_or)
+        vals = m.jacobian(problem, u, J).values()
+        Fd = m.residual(problem, u, F).to_host()
+        for r in range(info.n_owned):
+            v = dof2vert[start + r]
+            sr = gidx[v]
+            cols_v = dof2vert[ci[rp[r]:rp[r + 1]]]
+            order = np.argsort(cols_v)
+            assert np.array_equal(cols_v[order], ser_vert[colidx[rowptr[sr]:rowptr[sr + 1]]]), "row pattern"
+            ref = vals_or[rowptr[sr]:rowptr[sr + 1]]
+            assert np.abs(vals[rp[r]:rp[r + 1]][order] - ref).max() <= 1e-12 * np.abs(ref).max(), "jacobian values"
+        Fref = F_or[gidx[dof2vert[start:start + info.n_owned]]]
+        assert np.abs(Fd - Fref).max() <= 1e-12 * np.abs(F_or).max(), "residual"
+    # SpMV with halo, dots, full Newton solve
+    m.jacobian(0, u, J)
+    y = m.create_global_vector()
+    J.mult(u, y)
+    vals_or = oracle.jacobian(0, cells, coords, gidx, N, u_or, rowptr, colidx)
+    y_or = oracle.spmv(rowptr, colidx, vals_or, u_or)
+    assert np.abs(y.to_host() - y_or[gidx[dof2vert[start:start + info.n_owned]]]).max() <= 1e-13 * np.abs(y_or).max(), "spmv"
+    assert abs(u.dot(y) - float(u_or @ y_or)) <= 1e-12 * abs(float(u_or @ y_or)), "global dot"
+    m.project(0, 0, u)
+    res = m.snes_solve(0, J, u, ksp=ohp.ksp_options(rtol=1e-9, max_it=100000))
+    ref = oracle.newton(0, cells, coords, gidx, N, rowptr, colidx, ksp_rtol=1e-9, ksp_maxit=100000)
+    assert (res["its"], res["reason"]) == (1, 3), res
+    assert abs(res["ksp_its"] - ref["ksp_its"]) <= max(2, ref["ksp_its"] // 40), (res["ksp_its"], ref["ksp_its"])
+    uref = ref["u"][gidx[dof2vert[start:start + info.n_owned]]]
+    assert np.abs(u.to_host() - uref).max() <= 1e-7 * np.abs(ref["u"]).max(), "solution"
+    dist.barrier()
+    if rank == 0:
+        print("MGPU_OK %s world=%d N=%d ksp_its=%d (oracle %d) ghosts(rank0)=%d" % (
+            name, world, N, res["ksp_its"], ref["ksp_its"], info.n_ghost))
+    m.destroy()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
