@@ -241,7 +241,10 @@ def run_ours(args):
         if part is not None:
             m.set_ghosts(part["ghost_local"], part["ghost_owner"],
                          partition.resolve_ghost_roots(part, vo, rank, world, dist.all_gather_object))
-        return m.setup()
+        m.setup()
+        if part is not None and os.environ.get("OHP_COMM", "p2p") != "nccl":
+            m.p2p_enable(dist.all_gather_object, world)
+        return m
 
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
     t0 = time.perf_counter()
@@ -360,7 +363,7 @@ def run_ours(args):
             "config": {"workload": "%s: %d cells, %d verts, N=%d dofs, nnz=%d, dim %d; one -run_type full Newton step = 2 residual + "
                                    "1 Jacobian assemblies + CG (pc none, rtol %g, %d its)" % (
                                        args.workload, n_cells_global, n_verts_global, N, info.nnz if world == 1 else -1, dim, KSP_RTOL, int(round(its_step))),
-                       "sizes": list(sizes), "parallelism": "1 GPU" if world == 1 else "%d-way chain partition, halo + allreduce over NCCL" % world,
+                       "sizes": list(sizes), "parallelism": "1 GPU" if world == 1 else "%d-way chain partition; halo push + dot all-reduce %s" % (world, "over NCCL" if os.environ.get("OHP_COMM") == "nccl" else "fused into the CG kernels over NVLink peer memory"),
                        "l2": "inputs larger than L2 (matrix %.0f MB + vectors %.0f MB per rank vs 126 MB)" % (12 * info.nnz / 1e6, 40 * info.n_owned / 1e6),
                        "setup_ms_excluded": t_setup * 1e3},
             "e2e": {"value": N / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e * 1e3,

@@ -155,6 +155,15 @@ typedef struct {
 } ohp_mesh_info;
 int ohp_mesh_get_info(ohp_mesh mesh, ohp_mesh_info *info);
 
+/* NVLink peer-to-peer fast path for the partitioned CG solve (optional; without it halos and dot
+ * products go through NCCL).  After ohp_mesh_setup every rank exports a 64-byte CUDA IPC handle of
+ * its exchange heap, the launcher all-gathers the handles (nranks x 64 bytes, rank order) and every
+ * rank attaches.  The CG kernels then push halo values straight into the neighbours' vectors and
+ * all-reduce their dot products through peer mailboxes, inside the kernels that produce them.
+ * Plays the role PETSc's PetscSF/VecScatter + MPI_Allreduce play under SNESSolve (ex12.cpp:1609). */
+int ohp_mesh_p2p_export(ohp_mesh mesh, void *handle64);
+int ohp_mesh_p2p_attach(ohp_mesh mesh, const void *handles /* nranks x 64 bytes */);
+
 /* label "marker" (ex12.cpp:1023-1026): bnd[v] in {0,1}, n_verts bytes */
 int ohp_mesh_get_boundary(ohp_mesh mesh, uint8_t *bnd);
 /* global section: gidx[v] = global dof of vertex v, -1 if constrained; n_verts int64 */

@@ -402,6 +402,15 @@ class Mesh:
         self._info = None
         return self
 
+    def p2p_enable(self, all_gather_object, world):
+        """ohp_mesh_p2p_export + all-gather of the CUDA IPC handles + ohp_mesh_p2p_attach."""
+        buf = (ctypes.c_uint8 * 64)()
+        _chk(lib().ohp_mesh_p2p_export(self.h, buf))
+        handles = [None] * world
+        all_gather_object(handles, bytes(buf))
+        blob = (ctypes.c_uint8 * (64 * world)).from_buffer_copy(b"".join(handles))
+        _chk(lib().ohp_mesh_p2p_attach(self.h, blob))
+
     def info(self):
         if self._info is None:
             i = MeshInfo()

@@ -178,6 +178,7 @@ struct ohp_halo {
   int32_t *d_send_ldof = nullptr;
   double *d_sbuf = nullptr;
   int64_t d_ns = 0, d_nr = 0;
+  std::vector<int64_t> d_dst_off;            /* per neighbour: first index of my block in ITS vector */
 };
 
 void ohp_halo_free(ohp_halo *h) {
@@ -338,6 +339,90 @@ int ohp_halo_build(ohp_mesh m) {
   OHP_CUDA(cudaMalloc(&h->d_sbuf, sizeof(double) * std::max<int64_t>(1, h->d_ns)));
   OHP_CUDA(cudaMemcpyAsync(h->d_send_ldof, send_ldof.data(), sizeof(int32_t) * h->d_ns, cudaMemcpyHostToDevice, st));
   OHP_CUDA(cudaStreamSynchronize(st));
+  /* tell every rank that serves me where its block starts in my vector (used by the P2P push) */
+  std::vector<std::vector<int32_t>> tell(P), told;
+  for (size_t k = 0; k < h->d_nbr.size(); ++k)
+    if (h->d_roff[k + 1] > h->d_roff[k]) tell[h->d_nbr[k]].push_back(m->n_owned + (int32_t)h->d_roff[k]);
+  OHP_TRY(exchange_lists(ctx, tell, told));
+  h->d_dst_off.assign(h->d_nbr.size(), -1);
+  for (size_t k = 0; k < h->d_nbr.size(); ++k)
+    if (!told[h->d_nbr[k]].empty()) h->d_dst_off[k] = told[h->d_nbr[k]][0];
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* NVLink peer-to-peer mapping (CUDA IPC between the per-GPU processes)                  */
+/* ------------------------------------------------------------------------------------ */
+void ohp_p2p_free(ohp_p2p *p) {
+  if (!p) return;
+  for (int q = 0; q < kMaxRanks; ++q)
+    if (p->peer[q] && p->peer[q] != p->heap) cudaIpcCloseMemHandle(p->peer[q]);
+  cudaFree(p->heap);
+  delete p;
+}
+
+extern "C" int ohp_mesh_p2p_export(ohp_mesh m, void *handle64) {
+  if (!m || !m->setup_done || !handle64) OHP_FAIL(OHP_ERR_ORDER, "ohp_mesh_p2p_export: mesh not set up");
+  ohp_context ctx = m->ctx;
+  if (ctx->nranks < 2) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_mesh_p2p_export: no communicator attached");
+  if (ctx->nranks > kMaxRanks) OHP_FAIL(OHP_ERR_SUP, "ohp_mesh_p2p_export: more than %d ranks", kMaxRanks);
+  if (m->p2p) OHP_FAIL(OHP_ERR_ORDER, "ohp_mesh_p2p_export: already exported");
+  OHP_CUDA(cudaSetDevice(ctx->device));
+  std::vector<int64_t> lens;
+  OHP_TRY(ohp_allgather_i64(ctx, (int64_t)m->n_owned + m->n_ghost, lens));
+  ohp_p2p *p = new ohp_p2p();
+  p->pcap = (*std::max_element(lens.begin(), lens.end()) + 63) / 64 * 64 + 64;
+  p->off_slots = 0;
+  p->off_hflags = 2 * kMaxRanks * sizeof(ohp_ar_slot);
+  p->off_p0 = 4096;
+  p->off_p1 = p->off_p0 + (size_t)p->pcap * sizeof(double);
+  p->bytes = p->off_p1 + (size_t)p->pcap * sizeof(double) + 256; /* + local sequence counters at the end */
+  OHP_CUDA(cudaMalloc(&p->heap, p->bytes));
+  OHP_CUDA(cudaMemset(p->heap, 0, p->bytes));
+  cudaIpcMemHandle_t hnd;
+  OHP_CUDA(cudaIpcGetMemHandle(&hnd, p->heap));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  memcpy(handle64, &hnd, 64);
+  m->p2p = p;
+  return 0;
+}
+
+extern "C" int ohp_mesh_p2p_attach(ohp_mesh m, const void *handles) {
+  if (!m || !m->p2p || !handles) OHP_FAIL(OHP_ERR_ORDER, "ohp_mesh_p2p_attach: call ohp_mesh_p2p_export first");
+  ohp_context ctx = m->ctx;
+  ohp_p2p *p = m->p2p;
+  ohp_halo *h = m->halo;
+  OHP_CUDA(cudaSetDevice(ctx->device));
+  for (int q = 0; q < ctx->nranks; ++q) {
+    if (q == ctx->rank) { p->peer[q] = p->heap; continue; }
+    cudaIpcMemHandle_t hnd;
+    memcpy(&hnd, (const char *)handles + 64 * q, 64);
+    OHP_CUDA(cudaIpcOpenMemHandle(&p->peer[q], hnd, cudaIpcMemLazyEnablePeerAccess));
+  }
+  ohp_p2p_dev &d = p->dev;
+  memset(&d, 0, sizeof(d));
+  d.rank = ctx->rank; d.nranks = ctx->nranks;
+  if ((int)h->d_nbr.size() > kMaxRanks) OHP_FAIL(OHP_ERR_SUP, "p2p: too many halo neighbours");
+  d.n_nbr = 0;
+  for (size_t k = 0; k < h->d_nbr.size(); ++k) {
+    /* every neighbour gets a (possibly empty) push so that flags advance in lockstep */
+    d.nbr[d.n_nbr] = h->d_nbr[k];
+    d.soff[d.n_nbr] = (int)h->d_soff[k];
+    d.soff[d.n_nbr + 1] = (int)h->d_soff[k + 1];
+    d.dst_off[d.n_nbr] = h->d_dst_off[k];
+    if (h->d_soff[k + 1] > h->d_soff[k] && h->d_dst_off[k] < 0) OHP_FAIL(OHP_ERR_LIB, "p2p: missing destination offset for rank %d", h->d_nbr[k]);
+    d.n_nbr++;
+  }
+  d.send_ldof = h->d_send_ldof;
+  for (int q = 0; q < ctx->nranks; ++q) {
+    char *base = (char *)p->peer[q];
+    d.slots[q] = (ohp_ar_slot *)(base + p->off_slots);
+    d.hflags[q] = (unsigned long long *)(base + p->off_hflags);
+    d.p[0][q] = (double *)(base + p->off_p0);
+    d.p[1][q] = (double *)(base + p->off_p1);
+  }
+  d.seq = (unsigned long long *)((char *)p->heap + p->bytes - 256);
+  p->attached = true;
   return 0;
 }
 

@@ -223,7 +223,7 @@ extern "C" int ohp_mesh_create(ohp_context ctx, int dim, int32_t nC, int32_t nV,
   m->ctx = ctx; m->dim = dim; m->nc = nc; m->nC = nC; m->nV = nV;
   m->cells = nullptr; m->coords = nullptr; m->owned = nullptr; m->setup_done = false;
   m->v2c_ptr = m->v2c = nullptr; m->bnd = nullptr; m->lidx = m->row_vertex = nullptr; m->ldof_gid = nullptr;
-  m->rowptr = m->colidx = nullptr; m->slot = nullptr; m->tile_row = nullptr; m->halo = nullptr;
+  m->rowptr = m->colidx = nullptr; m->slot = nullptr; m->tile_row = nullptr; m->halo = nullptr; m->p2p = nullptr;
   m->n_owned = m->n_ghost = m->n_bnd = 0; m->n_global = m->row_start = m->nnz = 0; m->max_row = 0; m->n_tiles = 0; m->max_tile_rows = 0;
   OHP_CUDA(cudaMalloc(&m->cells, sizeof(int32_t) * std::max<int64_t>(1, (int64_t)nC * nc)));
   OHP_CUDA(cudaMalloc(&m->coords, sizeof(double) * std::max<int64_t>(1, (int64_t)nV * dim)));
@@ -242,6 +242,7 @@ extern "C" int ohp_mesh_destroy(ohp_mesh m) {
   cudaFree(m->bnd); cudaFree(m->lidx); cudaFree(m->row_vertex); cudaFree(m->ldof_gid); cudaFree(m->rowptr);
   cudaFree(m->colidx); cudaFree(m->slot); cudaFree(m->tile_row);
   ohp_halo_free(m->halo);
+  ohp_p2p_free(m->p2p);
   delete m;
   return 0;
 }

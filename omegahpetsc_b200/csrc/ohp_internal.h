@@ -52,6 +52,30 @@ struct ohp_cg_state {
 
 struct ohp_halo;  /* ohp_comm.cu */
 
+/* ---- peer-to-peer (NVLink) view of the communicator, passed BY VALUE to the CG kernels ---- */
+constexpr int kMaxRanks = 8;
+struct ohp_ar_slot { double v[2]; unsigned long long seq; unsigned long long pad; }; /* 32 B */
+struct ohp_p2p_dev {
+  int rank, nranks;
+  int n_nbr;                         /* halo neighbours */
+  int nbr[kMaxRanks];
+  int soff[kMaxRanks + 1];           /* send-list offsets per neighbour */
+  long long dst_off[kMaxRanks];      /* where my values land in the neighbour's vector (its ghost tail) */
+  const int32_t *send_ldof;          /* my dofs to push, grouped by neighbour */
+  ohp_ar_slot *slots[kMaxRanks];     /* slots[q]: rank q's all-reduce mailbox (2 parities x kMaxRanks sources) */
+  unsigned long long *hflags[kMaxRanks]; /* hflags[q][src]: sequence number of src's last halo push into q */
+  double *p[2][kMaxRanks];           /* p[b][q]: rank q's search-direction buffer b (owned dofs + ghost tail) */
+  unsigned long long *seq;           /* local counters: [0] all-reduces issued, [1] halo pushes issued */
+};
+struct ohp_p2p {
+  void *heap = nullptr;              /* cudaMalloc'ed, exported with cudaIpcGetMemHandle */
+  size_t bytes = 0, off_slots = 0, off_hflags = 0, off_p0 = 0, off_p1 = 0;
+  int64_t pcap = 0;                  /* capacity (doubles) of each p buffer: max over ranks */
+  void *peer[kMaxRanks] = {nullptr};
+  bool attached = false;
+  ohp_p2p_dev dev;
+};
+
 struct ohp_context_s {
   int device;
   int num_sms;
@@ -108,6 +132,7 @@ struct ohp_mesh_s {
   int32_t n_tiles;
   int32_t max_tile_rows; /* most rows starting inside one tile */
   ohp_halo *halo;    /* dof-level halo plan (NULL when serial) */
+  ohp_p2p *p2p;      /* NVLink peer mapping (NULL until ohp_mesh_p2p_attach) */
 };
 
 struct ohp_vec_s {
@@ -119,8 +144,9 @@ struct ohp_vec_s {
 struct ohp_mat_s {
   ohp_mesh mesh;
   double *vals;
-  /* CG work vectors, allocated on first solve */
-  double *r, *z, *p, *w, *dinv;
+  /* CG work vectors, allocated on first solve; the search direction is double-buffered
+   * (p[its & 1] is written from p[(its & 1) ^ 1]) so that a halo push never races its own update */
+  double *r, *z, *p, *p1, *w, *dinv;
   double *hist;
   int32_t hist_cap;
 };
@@ -138,6 +164,7 @@ int ohp_allreduce_sum(ohp_context ctx, double *d_vals, int n);
 int ohp_vertex_halo_i32(ohp_mesh mesh, int32_t *vertex_data_dev);
 int ohp_allgather_i64(ohp_context ctx, int64_t mine, std::vector<int64_t> &all);
 void ohp_comm_destroy(ohp_context ctx);
+void ohp_p2p_free(ohp_p2p *p);
 
 /* ohp_linalg.cu */
 int ohp_spmv_launch(ohp_mat A, const double *x, double *y);

@@ -79,6 +79,67 @@ __device__ __forceinline__ bool grid_sum(double (&v)[NV], double *partials, unsi
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* NVLink peer-to-peer all-reduce, fused into the kernel that produces the partial sums.   */
+/* Called by every thread of the LAST block (grid_sum returned true); warp 0 does the work: */
+/* lane q stores this rank's totals into rank q's mailbox (release store of the sequence    */
+/* number after the payload), then spins (acquire) on the mailbox rank q fills here; the    */
+/* totals are added in rank order, so every rank gets bitwise the same sum.  Mailboxes are  */
+/* double-buffered by sequence parity: a rank can be at most one all-reduce ahead.          */
+/* ------------------------------------------------------------------------------------ */
+enum { OHP_MODE_SERIAL = 0, OHP_MODE_NCCL = 1, OHP_MODE_P2P = 2 };
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+/* spin until *flag >= seq; a peer that died must not hang this GPU: after 4 s raise seq[2] and go on */
+__device__ __forceinline__ void p2p_wait(const unsigned long long *flag, unsigned long long seq, unsigned long long *err) {
+  if (ld_acquire_sys(flag) >= seq) return;
+  const unsigned long long t0 = global_ns();
+  while (ld_acquire_sys(flag) < seq) {
+    if (global_ns() - t0 > 4000000000ull) { *err = 1ull; return; }
+  }
+}
+
+template <int NV> __device__ __forceinline__ void p2p_allreduce(const ohp_p2p_dev &pd, double (&v)[NV]) {
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  unsigned long long seq = 0;
+  if (lane == 0) { seq = pd.seq[0] + 1; pd.seq[0] = seq; }
+  seq = __shfl_sync(0xffffffffu, seq, 0);
+  double mine[NV], got[NV], tot[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) { mine[k] = __shfl_sync(0xffffffffu, v[k], 0); got[k] = mine[k]; tot[k] = 0.0; }
+  const int par = (int)(seq & 1ull);
+  const bool peer = lane < pd.nranks && lane != pd.rank;
+  if (peer) {
+    ohp_ar_slot *s = pd.slots[lane] + par * kMaxRanks + pd.rank;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) s->v[k] = mine[k];
+    st_release_sys(&s->seq, seq);
+    const ohp_ar_slot *r = pd.slots[pd.rank] + par * kMaxRanks + lane;
+    p2p_wait(&r->seq, seq, pd.seq + 2);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) got[k] = r->v[k];
+  }
+  for (int q = 0; q < pd.nranks; ++q) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) tot[k] += __shfl_sync(0xffffffffu, got[k], q);
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = tot[k];
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* CG scalar recurrences (KSPSolve_CG + KSPConvergedDefault), run by one thread          */
 /* ------------------------------------------------------------------------------------ */
 __device__ __forceinline__ void cg_converged(ohp_cg_state *st, double dp) {
@@ -132,9 +193,10 @@ __global__ void __launch_bounds__(kSpmvThreads)
 k_spmv_stream(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
               const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
               const int32_t *__restrict__ tile_row, int n_tiles, ohp_cg_state *st, double *partials,
-              unsigned *ticket, double *sums, int fin_inline) {
+              unsigned *ticket, double *sums, int mode, const double *__restrict__ x_alt, const ohp_p2p_dev pd) {
   extern __shared__ double s_prod[];
   if (CG && st->done) return;
+  if (CG && (st->its & 1)) x = x_alt; /* double-buffered search direction */
   double dot[1] = {0.0};
   for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const int r0 = __ldg(tile_row + t), r1 = __ldg(tile_row + t + 1);
@@ -153,9 +215,12 @@ k_spmv_stream(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ co
     __syncthreads();
   }
   if (CG) {
-    if (grid_sum<1>(dot, partials, ticket) && threadIdx.x == 0) {
-      sums[0] = dot[0];
-      if (fin_inline) cg_fin_spmv(st, dot[0]);
+    if (grid_sum<1>(dot, partials, ticket)) {
+      if (mode == OHP_MODE_P2P) p2p_allreduce<1>(pd, dot);
+      if (threadIdx.x == 0) {
+        sums[0] = dot[0];
+        if (mode != OHP_MODE_NCCL) cg_fin_spmv(st, dot[0]);
+      }
     }
   }
 }
@@ -228,10 +293,12 @@ template <bool CG, int kTmaStages, int kTmaConsumers>
 __global__ void __launch_bounds__(kTmaConsumers + 32, 1)
 k_spmv_tma(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, const double *__restrict__ vals,
            const double *__restrict__ x, double *__restrict__ y, const int32_t *__restrict__ tile_row, int n_tiles,
-           ohp_cg_state *st, double *partials, unsigned *ticket, double *sums, int fin_inline) {
+           ohp_cg_state *st, double *partials, unsigned *ticket, double *sums, int mode,
+           const double *__restrict__ x_alt, const ohp_p2p_dev pd) {
   constexpr int T = kSpmvTile, S = kTmaStages, NC = kTmaConsumers;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   if (CG && st->done) return;
+  if (CG && (st->its & 1)) x = x_alt;
   double *vals_s = reinterpret_cast<double *>(smem_raw);
   int32_t *cols_s = reinterpret_cast<int32_t *>(vals_s + S * T);
   int32_t *rp_s = cols_s + S * T;
@@ -297,9 +364,12 @@ k_spmv_tma(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colid
     }
   }
   if (CG) {
-    if (grid_sum<1>(dot, partials, ticket) && threadIdx.x == 0) {
-      sums[0] = dot[0];
-      if (fin_inline) cg_fin_spmv(st, dot[0]);
+    if (grid_sum<1>(dot, partials, ticket)) {
+      if (mode == OHP_MODE_P2P) p2p_allreduce<1>(pd, dot);
+      if (threadIdx.x == 0) {
+        sums[0] = dot[0];
+        if (mode != OHP_MODE_NCCL) cg_fin_spmv(st, dot[0]);
+      }
     }
   }
 }
@@ -321,7 +391,8 @@ static int spmv_configure(ohp_mesh m) {
 }
 
 template <int S, int NC>
-static int spmv_tma_launch(ohp_mat A, const double *x, double *y, ohp_cg_state *st, double *sums, int fin_inline) {
+static int spmv_tma_launch(ohp_mat A, const double *x, double *y, ohp_cg_state *st, double *sums, int mode,
+                           const double *x_alt, const ohp_p2p_dev &pd) {
   ohp_mesh m = A->mesh;
   ohp_context ctx = m->ctx;
   static bool configured = false;
@@ -332,15 +403,16 @@ static int spmv_tma_launch(ohp_mat A, const double *x, double *y, ohp_cg_state *
   }
   const int grid = std::max(1, std::min(m->n_tiles, ctx->num_sms));
   if (st) k_spmv_tma<true, S, NC><<<grid, NC + 32, tma_smem_bytes(S), ctx->stream>>>(
-      m->rowptr, m->colidx, A->vals, x, y, m->tile_row, m->n_tiles, st, ctx->d_partials, ctx->d_ticket + 1, sums, fin_inline);
+      m->rowptr, m->colidx, A->vals, x, y, m->tile_row, m->n_tiles, st, ctx->d_partials, ctx->d_ticket + 1, sums, mode, x_alt, pd);
   else k_spmv_tma<false, S, NC><<<grid, NC + 32, tma_smem_bytes(S), ctx->stream>>>(
-      m->rowptr, m->colidx, A->vals, x, y, m->tile_row, m->n_tiles, nullptr, nullptr, nullptr, nullptr, 0);
+      m->rowptr, m->colidx, A->vals, x, y, m->tile_row, m->n_tiles, nullptr, nullptr, nullptr, nullptr, 0, nullptr, pd);
   OHP_CHECK_LAUNCH(ctx);
   return 0;
 }
 
 /* y = A x on the context stream; with `st` the (x, y) dot and the CG scalar update are fused in */
-static int spmv_enqueue(ohp_mat A, const double *x, double *y, ohp_cg_state *st, double *sums, int fin_inline) {
+static int spmv_enqueue(ohp_mat A, const double *x, double *y, ohp_cg_state *st, double *sums, int mode,
+                        const double *x_alt, const ohp_p2p_dev &pd) {
   ohp_mesh m = A->mesh;
   ohp_context ctx = m->ctx;
   static const char *force = getenv("OHP_SPMV"); /* "stream" forces the fallback kernel; "0".."5" pick a TMA config (A/B runs) */
@@ -348,25 +420,26 @@ static int spmv_enqueue(ohp_mat A, const double *x, double *y, ohp_cg_state *st,
   if (tma) {
     const int cfg = (force && force[0] >= '0' && force[0] <= '9') ? force[0] - '0' : 0;
     switch (cfg) {
-      case 1: return spmv_tma_launch<3, 384>(A, x, y, st, sums, fin_inline);
-      case 2: return spmv_tma_launch<3, 768>(A, x, y, st, sums, fin_inline);
-      case 3: return spmv_tma_launch<2, 640>(A, x, y, st, sums, fin_inline);
-      default: return spmv_tma_launch<3, 608>(A, x, y, st, sums, fin_inline);
+      case 1: return spmv_tma_launch<3, 384>(A, x, y, st, sums, mode, x_alt, pd);
+      case 2: return spmv_tma_launch<3, 768>(A, x, y, st, sums, mode, x_alt, pd);
+      case 3: return spmv_tma_launch<2, 640>(A, x, y, st, sums, mode, x_alt, pd);
+      default: return spmv_tma_launch<3, 608>(A, x, y, st, sums, mode, x_alt, pd);
     }
   }
   OHP_TRY(spmv_configure(m));
   const int grid = std::max(1, std::min(m->n_tiles, kMaxPartials));
   if (st) k_spmv_stream<true><<<grid, kSpmvThreads, spmv_smem_bytes(m), ctx->stream>>>(
-      m->rowptr, m->colidx, A->vals, x, y, m->tile_row, m->n_tiles, st, ctx->d_partials, ctx->d_ticket + 1, sums, fin_inline);
+      m->rowptr, m->colidx, A->vals, x, y, m->tile_row, m->n_tiles, st, ctx->d_partials, ctx->d_ticket + 1, sums, mode, x_alt, pd);
   else k_spmv_stream<false><<<grid, kSpmvThreads, spmv_smem_bytes(m), ctx->stream>>>(
-      m->rowptr, m->colidx, A->vals, x, y, m->tile_row, m->n_tiles, nullptr, nullptr, nullptr, nullptr, 0);
+      m->rowptr, m->colidx, A->vals, x, y, m->tile_row, m->n_tiles, nullptr, nullptr, nullptr, nullptr, 0, nullptr, pd);
   OHP_CHECK_LAUNCH(ctx);
   return 0;
 }
 
 int ohp_spmv_launch(ohp_mat A, const double *x, double *y) {
   if (A->mesh->n_owned == 0) return 0;
-  return spmv_enqueue(A, x, y, nullptr, nullptr, 0);
+  static const ohp_p2p_dev none = {};
+  return spmv_enqueue(A, x, y, nullptr, nullptr, 0, nullptr, none);
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -493,7 +566,7 @@ extern "C" int ohp_mat_create(ohp_mesh m, ohp_mat *out) {
   if (!m || !m->setup_done) OHP_FAIL(OHP_ERR_ORDER, "ohp_mat_create: mesh not set up");
   OHP_CUDA(cudaSetDevice(m->ctx->device));
   ohp_mat A = new ohp_mat_s();
-  A->mesh = m; A->r = A->z = A->p = A->w = A->dinv = A->hist = nullptr; A->hist_cap = 0;
+  A->mesh = m; A->r = A->z = A->p = A->p1 = A->w = A->dinv = A->hist = nullptr; A->hist_cap = 0;
   OHP_CUDA(cudaMalloc(&A->vals, sizeof(double) * ohp_padded_nnz(m->nnz)));
   OHP_CUDA(cudaMemsetAsync(A->vals, 0, sizeof(double) * ohp_padded_nnz(m->nnz), m->ctx->stream));
   *out = A;
@@ -503,7 +576,7 @@ extern "C" int ohp_mat_destroy(ohp_mat A) {
   if (!A) return 0;
   cudaSetDevice(A->mesh->ctx->device);
   cudaStreamSynchronize(A->mesh->ctx->stream);
-  cudaFree(A->vals); cudaFree(A->r); cudaFree(A->z); cudaFree(A->p); cudaFree(A->w); cudaFree(A->dinv); cudaFree(A->hist);
+  cudaFree(A->vals); cudaFree(A->r); cudaFree(A->z); cudaFree(A->p); cudaFree(A->p1); cudaFree(A->w); cudaFree(A->dinv); cudaFree(A->hist);
   delete A;
   return 0;
 }
@@ -533,7 +606,7 @@ template <bool JACOBI>
 __global__ void __launch_bounds__(256)
 k_cg_init(const double *__restrict__ b, double *__restrict__ x, double *__restrict__ r, double *__restrict__ z,
           const double *__restrict__ dinv, int n, ohp_cg_state *st, double *partials, unsigned *ticket,
-          double *sums, double *hist, int fin_inline) {
+          double *sums, double *hist, int mode, const ohp_p2p_dev pd) {
   double s[2] = {0.0, 0.0};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const double bi = b[i];
@@ -544,37 +617,80 @@ k_cg_init(const double *__restrict__ b, double *__restrict__ x, double *__restri
     s[0] += zi * zi;
     s[1] += zi * bi;
   }
-  if (grid_sum<2>(s, partials, ticket) && threadIdx.x == 0) {
-    sums[0] = s[0]; sums[1] = s[1];
-    if (fin_inline) cg_fin_init(st, s[0], s[1], hist);
+  if (grid_sum<2>(s, partials, ticket)) {
+    if (mode == OHP_MODE_P2P) p2p_allreduce<2>(pd, s);
+    if (threadIdx.x == 0) {
+      sums[0] = s[0]; sums[1] = s[1];
+      if (mode != OHP_MODE_NCCL) cg_fin_init(st, s[0], s[1], hist);
+    }
   }
 }
 
-/* x += alpha_prev p (the x update of the PREVIOUS iteration, deferred so that p is read once);
- * p = z + (beta/betaold) p  (first iteration: p = z) */
+/* x += alpha_prev p_old (the x update of the PREVIOUS iteration, deferred so that p is read once);
+ * p_new = z + (beta/betaold) p_old  (first iteration: p_new = z).  The search direction is
+ * double-buffered: p_new = P[its & 1], p_old = P[(its & 1) ^ 1].
+ * P2P mode: block 0 is the halo block.  It recomputes p_new for the dofs the neighbours ghost and
+ * stores them straight into the neighbours' vectors over NVLink (no pack buffer, no extra launch),
+ * publishes a sequence flag per neighbour, then waits for the neighbours' flags, so that when this
+ * kernel retires the ghost tail of P[its & 1] is complete: halo exchange fused into the p update. */
+template <int MODE>
 __global__ void __launch_bounds__(256)
-k_cg_pupdate(double *__restrict__ p, const double *__restrict__ z, double *__restrict__ x, int n,
-             const ohp_cg_state *st) {
+k_cg_pupdate(double *__restrict__ p0, double *__restrict__ p1, const double *__restrict__ z, double *__restrict__ x,
+             int n, const ohp_cg_state *st, const ohp_p2p_dev pd, int n_halo_blocks, unsigned *halo_ticket) {
   if (st->done) return;
-  const bool first = (st->its == 0);
+  const int its = st->its;
+  const bool first = (its == 0);
   const double bb = first ? 0.0 : st->beta / st->betaold;
   const double a = st->alpha;
+  double *__restrict__ pn = (its & 1) ? p1 : p0;
+  const double *__restrict__ po = (its & 1) ? p0 : p1;
+  int b = blockIdx.x, nb = gridDim.x;
+  if (MODE == OHP_MODE_P2P) {
+    if (b < n_halo_blocks) {
+      const int nsend = pd.soff[pd.n_nbr];
+      for (int i = b * blockDim.x + threadIdx.x; i < nsend; i += n_halo_blocks * blockDim.x) {
+        const int l = pd.send_ldof[i];
+        const double val = first ? z[l] : fma(bb, po[l], z[l]);
+        int k = 0;
+        while (i >= pd.soff[k + 1]) ++k;
+        pd.p[its & 1][pd.nbr[k]][pd.dst_off[k] + (i - pd.soff[k])] = val;
+      }
+      __threadfence_system();
+      __syncthreads();
+      __shared__ unsigned long long s_seq;
+      __shared__ bool s_last;
+      if (threadIdx.x == 0) {
+        s_last = (atomicInc(halo_ticket, n_halo_blocks - 1) == (unsigned)(n_halo_blocks - 1));
+        if (s_last) { __threadfence(); s_seq = pd.seq[1] + 1; pd.seq[1] = s_seq; }
+      }
+      __syncthreads();
+      if (s_last && threadIdx.x < pd.n_nbr) { /* every push of this rank has landed: publish, then wait for the neighbours */
+        const int q = pd.nbr[threadIdx.x];
+        st_release_sys(pd.hflags[q] + pd.rank, s_seq);
+        p2p_wait(pd.hflags[pd.rank] + q, s_seq, pd.seq + 2);
+      }
+      return;
+    }
+    b -= n_halo_blocks; nb -= n_halo_blocks;
+  }
   if (first) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = z[i];
+    for (int i = b * blockDim.x + threadIdx.x; i < n; i += nb * blockDim.x) pn[i] = z[i];
   } else {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-      const double pi = p[i];
+    for (int i = b * blockDim.x + threadIdx.x; i < n; i += nb * blockDim.x) {
+      const double pi = po[i];
       x[i] += a * pi;
-      p[i] = z[i] + bb * pi;
+      pn[i] = fma(bb, pi, z[i]);
     }
   }
 }
 
 /* the x update still pending when the iteration stops */
 __global__ void __launch_bounds__(256)
-k_cg_final_x(double *__restrict__ x, const double *__restrict__ p, int n, ohp_cg_state *st) {
+k_cg_final_x(double *__restrict__ x, const double *__restrict__ p0, const double *__restrict__ p1, int n,
+             ohp_cg_state *st) {
   if (!st->x_pending) return;
   const double a = st->alpha;
+  const double *__restrict__ p = ((st->its - 1) & 1) ? p1 : p0; /* direction of the last completed iteration */
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] += a * p[i];
 }
 
@@ -583,7 +699,8 @@ template <bool JACOBI>
 __global__ void __launch_bounds__(256)
 k_cg_update(double *__restrict__ r, double *__restrict__ z, const double *__restrict__ w,
             const double *__restrict__ dinv, int n, ohp_cg_state *st,
-            double *partials, unsigned *ticket, double *sums, double *hist, int hist_cap, int fin_inline) {
+            double *partials, unsigned *ticket, double *sums, double *hist, int hist_cap, int mode,
+            const ohp_p2p_dev pd) {
   if (st->done) return;
   const double a = st->alpha;
   double s[2] = {0.0, 0.0};
@@ -595,9 +712,12 @@ k_cg_update(double *__restrict__ r, double *__restrict__ z, const double *__rest
     s[0] += zi * zi;
     s[1] += zi * ri;
   }
-  if (grid_sum<2>(s, partials, ticket) && threadIdx.x == 0) {
-    sums[0] = s[0]; sums[1] = s[1];
-    if (fin_inline) cg_fin_update(st, s[0], s[1], hist, hist_cap);
+  if (grid_sum<2>(s, partials, ticket)) {
+    if (mode == OHP_MODE_P2P) p2p_allreduce<2>(pd, s);
+    if (threadIdx.x == 0) {
+      sums[0] = s[0]; sums[1] = s[1];
+      if (mode != OHP_MODE_NCCL) cg_fin_update(st, s[0], s[1], hist, hist_cap);
+    }
   }
 }
 
@@ -629,9 +749,18 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
   if (!A->r) {
     OHP_CUDA(cudaMalloc(&A->r, sizeof(double) * len));
     OHP_CUDA(cudaMalloc(&A->p, sizeof(double) * len));
+    OHP_CUDA(cudaMalloc(&A->p1, sizeof(double) * len));
     OHP_CUDA(cudaMalloc(&A->w, sizeof(double) * len));
     OHP_CUDA(cudaMemsetAsync(A->p, 0, sizeof(double) * len, st));
+    OHP_CUDA(cudaMemsetAsync(A->p1, 0, sizeof(double) * len, st));
   }
+  /* transport: serial | NCCL (pack + send/recv + all-reduce + scalar kernel) | NVLink P2P fused into the kernels */
+  static const char *force_nccl = getenv("OHP_COMM"); /* "nccl" disables the P2P path (A/B runs) */
+  const bool p2p = ctx->nranks > 1 && m->p2p && m->p2p->attached && !(force_nccl && force_nccl[0] == 'n');
+  const int mode = ctx->nranks == 1 ? OHP_MODE_SERIAL : (p2p ? OHP_MODE_P2P : OHP_MODE_NCCL);
+  static const ohp_p2p_dev no_p2p = {};
+  const ohp_p2p_dev &pd = p2p ? m->p2p->dev : no_p2p;
+  double *P0 = p2p ? pd.p[0][ctx->rank] : A->p, *P1 = p2p ? pd.p[1][ctx->rank] : A->p1;
   const bool jac = (o->pc == OHP_PC_JACOBI);
   if (jac) {
     if (!A->z) { OHP_CUDA(cudaMalloc(&A->z, sizeof(double) * len)); OHP_CUDA(cudaMalloc(&A->dinv, sizeof(double) * len)); }
@@ -656,14 +785,15 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
   init.rtol = o->rtol; init.abstol = o->abstol; init.dtol = o->dtol; init.maxit = o->max_it;
   *ctx->h_cg = init;
   OHP_CUDA(cudaMemcpyAsync(ctx->d_cg, ctx->h_cg, sizeof(init), cudaMemcpyHostToDevice, st));
-  const int serial = (ctx->nranks == 1);
+  const bool nccl = (mode == OHP_MODE_NCCL);
+  const int nhalo = p2p ? std::max(1, std::min(16, (pd.soff[pd.n_nbr] + 255) / 256)) : 0;
   const int vgrid = vec_grid(ctx, n);
   double *sums = ctx->d_scalars;
 
-  if (jac) k_cg_init<true><<<vgrid, 256, 0, st>>>(b->d, x->d, A->r, z, A->dinv, n, ctx->d_cg, ctx->d_partials, ctx->d_ticket, sums, hist, serial);
-  else k_cg_init<false><<<vgrid, 256, 0, st>>>(b->d, x->d, A->r, z, A->dinv, n, ctx->d_cg, ctx->d_partials, ctx->d_ticket, sums, hist, serial);
+  if (jac) k_cg_init<true><<<vgrid, 256, 0, st>>>(b->d, x->d, A->r, z, A->dinv, n, ctx->d_cg, ctx->d_partials, ctx->d_ticket, sums, hist, mode, pd);
+  else k_cg_init<false><<<vgrid, 256, 0, st>>>(b->d, x->d, A->r, z, A->dinv, n, ctx->d_cg, ctx->d_partials, ctx->d_ticket, sums, hist, mode, pd);
   OHP_CHECK_LAUNCH(ctx);
-  if (!serial) {
+  if (nccl) {
     OHP_TRY(ohp_allreduce_sum(ctx, sums, 2));
     k_cg_fin<<<1, 1, 0, st>>>(ctx->d_cg, sums, 0, hist, hist_cap); OHP_CHECK_LAUNCH(ctx);
   }
@@ -682,28 +812,40 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
     if (ctx->h_cg->done) break;
     if (launched > o->max_it + check_every) OHP_FAIL(OHP_ERR_LIB, "ohp_ksp_cg: device-side iteration control did not terminate");
     for (int it = 0; it < check_every; ++it) {
-      k_cg_pupdate<<<vgrid, 256, 0, st>>>(A->p, z, x->d, n, ctx->d_cg); OHP_CHECK_LAUNCH(ctx);
-      if (!serial) OHP_TRY(ohp_halo_exchange(m, A->p));
+      if (p2p) k_cg_pupdate<OHP_MODE_P2P><<<vgrid + nhalo, 256, 0, st>>>(P0, P1, z, x->d, n, ctx->d_cg, pd, nhalo, ctx->d_ticket + 2);
+      else k_cg_pupdate<OHP_MODE_SERIAL><<<vgrid, 256, 0, st>>>(P0, P1, z, x->d, n, ctx->d_cg, pd, 0, nullptr);
+      OHP_CHECK_LAUNCH(ctx);
+      if (nccl) {
+        /* the host does not know the iteration parity on the device: exchange both buffers' tails is
+         * wasteful, so the NCCL path tracks parity on the host (it never runs ahead of `done`) */
+        OHP_TRY(ohp_halo_exchange(m, ((launched + it) & 1) ? P1 : P0));
+      }
       const bool timed = (int)prof.size() < 2 * nprof && (launched > 0 || o->max_it <= check_every);
       if (timed) { cudaEvent_t e; OHP_CUDA(cudaEventCreate(&e)); OHP_CUDA(cudaEventRecord(e, st)); prof.push_back(e); }
-      OHP_TRY(spmv_enqueue(A, A->p, A->w, ctx->d_cg, sums, serial));
+      OHP_TRY(spmv_enqueue(A, P0, A->w, ctx->d_cg, sums, mode, P1, pd));
       if (timed) { cudaEvent_t e; OHP_CUDA(cudaEventCreate(&e)); OHP_CUDA(cudaEventRecord(e, st)); prof.push_back(e); }
-      if (!serial) {
+      if (nccl) {
         OHP_TRY(ohp_allreduce_sum(ctx, sums, 1));
         k_cg_fin<<<1, 1, 0, st>>>(ctx->d_cg, sums, 1, hist, hist_cap); OHP_CHECK_LAUNCH(ctx);
       }
-      if (jac) k_cg_update<true><<<vgrid, 256, 0, st>>>(A->r, z, A->w, A->dinv, n, ctx->d_cg, ctx->d_partials, ctx->d_ticket, sums, hist, hist_cap, serial);
-      else k_cg_update<false><<<vgrid, 256, 0, st>>>(A->r, z, A->w, A->dinv, n, ctx->d_cg, ctx->d_partials, ctx->d_ticket, sums, hist, hist_cap, serial);
+      if (jac) k_cg_update<true><<<vgrid, 256, 0, st>>>(A->r, z, A->w, A->dinv, n, ctx->d_cg, ctx->d_partials, ctx->d_ticket, sums, hist, hist_cap, mode, pd);
+      else k_cg_update<false><<<vgrid, 256, 0, st>>>(A->r, z, A->w, A->dinv, n, ctx->d_cg, ctx->d_partials, ctx->d_ticket, sums, hist, hist_cap, mode, pd);
       OHP_CHECK_LAUNCH(ctx);
-      if (!serial) {
+      if (nccl) {
         OHP_TRY(ohp_allreduce_sum(ctx, sums, 2));
         k_cg_fin<<<1, 1, 0, st>>>(ctx->d_cg, sums, 2, hist, hist_cap); OHP_CHECK_LAUNCH(ctx);
       }
     }
     launched += check_every;
   }
-  k_cg_final_x<<<vgrid, 256, 0, st>>>(x->d, A->p, n, ctx->d_cg); OHP_CHECK_LAUNCH(ctx);
+  k_cg_final_x<<<vgrid, 256, 0, st>>>(x->d, P0, P1, n, ctx->d_cg); OHP_CHECK_LAUNCH(ctx);
   res->its = ctx->h_cg->its; res->reason = ctx->h_cg->reason; res->rnorm = ctx->h_cg->dp; res->rnorm0 = ctx->h_cg->rnorm0;
+  if (p2p) {
+    unsigned long long err = 0;
+    OHP_CUDA(cudaMemcpyAsync(&err, pd.seq + 2, sizeof(err), cudaMemcpyDeviceToHost, st));
+    OHP_CUDA(cudaStreamSynchronize(st));
+    if (err) OHP_FAIL(OHP_ERR_LIB, "ohp_ksp_cg: a peer-to-peer wait timed out (a neighbouring rank stopped responding)");
+  }
   OHP_CUDA(cudaEventRecord(ev_t1, st));
   OHP_CUDA(cudaEventSynchronize(ev_t1));
   res->total_ms = 0.f;

@@ -55,6 +55,8 @@ def main():
     m.set_ghosts(part["ghost_local"], part["ghost_owner"],
                  partition.resolve_ghost_roots(part, vo, rank, world, dist.all_gather_object))
     m.setup()
+    if os.environ.get("OHP_COMM", "p2p") != "nccl":
+        m.p2p_enable(dist.all_gather_object, world)
     info = m.info()
 
     import oracle

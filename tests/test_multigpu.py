@@ -16,18 +16,19 @@ def ngpus():
     return torch.cuda.device_count()
 
 
-def run_worker(world, mesh, port):
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+def run_worker(world, mesh, port, comm="p2p"):
+    cmd = ["timeout", "300", sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py"), mesh]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, OHP_COMM=comm))
     assert p.returncode == 0 and "MGPU_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
 
 
+@pytest.mark.parametrize("comm", ["p2p", "nccl"])
 @pytest.mark.parametrize("mesh", ["box2d_40", "24k_4p", "box3d_9"])
-def test_two_gpus(mesh):
+def test_two_gpus(mesh, comm):
     if ngpus() < 2:
         pytest.skip("needs 2 GPUs")
-    run_worker(2, mesh, 29611)
+    run_worker(2, mesh, 29611, comm)
 
 
 @pytest.mark.parametrize("mesh", ["24k_4p", "box2d_40"])
