@@ -133,6 +133,13 @@ int ohp_mesh_destroy(ohp_mesh mesh);
 int ohp_mesh_set_ghosts(ohp_mesh mesh, int32_t n_leaves, const int32_t *ghost_vertex,
                         const int32_t *owner_rank, const int32_t *owner_vertex);
 
+/* The same graph given exactly as ex12 gives it to PetscSFSetGraph: Plex POINT numbers.  Leaf =
+ * n_cells + local vertex (ex12.cpp:868,924); root = owner's n_cells + owner's vertex index
+ * (ex12.cpp:870,926, which the reference obtains with getNeighborElmCounts, ex12.cpp:528-577).
+ * Collective: all-gathers the ranks' cell counts to undo the offsets. */
+int ohp_mesh_set_point_sf(ohp_mesh mesh, int32_t n_leaves, const int32_t *leaf_point,
+                          const int32_t *root_rank, const int32_t *root_point);
+
 /* Everything ex12 does between mesh creation and the first solve, on the device:
  *   DMPlexInterpolate + boundary marking, facets with support size 1 -> label "marker"
  *     (ex12.cpp:958-1033),

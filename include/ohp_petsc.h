@@ -1,0 +1,521 @@
+/*
+ * ohp_petsc.h -- PETSc-shaped C++ facade over the C-ABI (include/ohp.h), so that an ex12-style
+ * main() keeps its call sequence and its pointwise callbacks (ex12.cpp:1472-1703) while every
+ * numerical step runs in libohp.so's sm_100a kernels.
+ *
+ * Only the calls on the reference's hot path are provided (SURVEY 8b "object calls on the path"):
+ *   SNESCreate/SetDM/SetJacobian/SetFromOptions/Solve/GetSolution/GetDM/ComputeFunction/ComputeJacobian,
+ *   DMPlexCreateFromCellListPetsc, DMGetPointSF + PetscSFSetGraph, DMPlexInterpolate (identity),
+ *   DMCreateLabel + DMPlexMarkBoundaryFaces (the reference's CreateBCLabel, ex12.cpp:515-526; replaces
+ *   the host loops over edge supports at ex12.cpp:986-1033), PetscFECreateDefault, DMSetField, DMCreateDS,
+ *   DMGetDS, PetscDSSetResidual/SetJacobian/SetExactSolution, DMAddBoundary, DMCreateGlobalVector,
+ *   DMCreateMatrix, DMPlexSetSNESLocalFEM, DMProjectFunction, DMComputeL2Diff, MatMult,
+ *   VecSet/AXPY/AYPX/Norm/Dot/Chop/Copy/Duplicate/GetSize, destroy calls, a PetscOptions subset.
+ * Same names, argument order and meaning, PetscErrorCode returns, CHKERRQ propagation.
+ *
+ * Callbacks run ON THE DEVICE, so a translation unit that defines them is compiled by nvcc (the
+ * reference already compiles ex12.cpp as CUDA, CMakeLists.txt:33-37) and needs two additions:
+ *   1. qualify each callback with PETSC_HOSTDEVICE (= __host__ __device__);
+ *   2. one line per callback set, after the definitions:
+ *        OHP_DEFINE_PROBLEM(name, f0, f1, g3, bc, exact)
+ *      which instantiates the assembly kernels of include/ohp_fem.cuh with the callbacks inlined and
+ *      registers them under the tuple of host function pointers; PetscDSSetResidual/SetJacobian/
+ *      DMAddBoundary then find the instantiation from the pointers they are given at run time.
+ * A callback set that was not declared this way is refused with PETSC_ERR_SUP (no silent CPU path).
+ */
+#ifndef OHP_PETSC_H
+#define OHP_PETSC_H
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "ohp.h"
+#ifdef __CUDACC__
+#include "ohp_fem.cuh"
+#define PETSC_HOSTDEVICE __host__ __device__
+#else
+#define PETSC_HOSTDEVICE
+#endif
+
+/* ---- scalar types (PETSc configured with 32-bit indices and real double scalars; hazard H4) ---- */
+typedef int PetscErrorCode;
+typedef int32_t PetscInt;
+typedef double PetscReal;
+typedef double PetscScalar;
+typedef int PetscMPIInt;
+typedef enum { PETSC_FALSE, PETSC_TRUE } PetscBool;
+typedef int MPI_Comm;
+#define PETSC_COMM_WORLD 0
+#define PETSC_COMM_SELF 1
+#define PETSC_DEFAULT (-2)
+#define PETSC_ERR_SUP OHP_ERR_SUP
+#define PETSC_ERR_ARG_WRONG OHP_ERR_ARG_WRONG
+#define PETSC_ERR_ARG_OUTOFRANGE OHP_ERR_ARG_OUTOFRANGE
+#define PETSC_ERR_ORDER OHP_ERR_ORDER
+#define PETSC_ERR_LIB OHP_ERR_LIB
+typedef enum { NORM_1 = 0, NORM_2 = 1, NORM_FROBENIUS = 2, NORM_INFINITY = 3 } NormType;
+typedef enum { INSERT_VALUES = 1, ADD_VALUES = 2, INSERT_ALL_VALUES = 5, INSERT_BC_VALUES = 7 } InsertMode;
+typedef enum { DM_BC_ESSENTIAL = 1, DM_BC_ESSENTIAL_FIELD = 5, DM_BC_NATURAL = 2 } DMBoundaryConditionType;
+typedef enum { PETSC_COPY_VALUES, PETSC_OWN_POINTER, PETSC_USE_POINTER } PetscCopyMode;
+typedef struct { PetscInt rank, index; } PetscSFNode;
+
+/* ---- error handling: `ierr = f();CHKERRQ(ierr);` (ex12.cpp:1491-1501) ---- */
+#define PetscFunctionBeginUser do { } while (0)
+#define PetscFunctionReturn(x) return (x)
+#define CHKERRQ(ierr)                                                                               \
+  do {                                                                                              \
+    if (ierr) {                                                                                     \
+      fprintf(stderr, "[0]PETSC ERROR: %s() line %d in %s: error %d: %s\n", __func__, __LINE__, __FILE__, (int)(ierr), \
+              ohp_last_error());                                                                    \
+      return (ierr);                                                                                \
+    }                                                                                               \
+  } while (0)
+#define SETERRQ(comm, code, msg) do { fprintf(stderr, "[0]PETSC ERROR: %s\n", msg); return (code); } while (0)
+#define SETERRQ1(comm, code, fmt, a) do { fprintf(stderr, "[0]PETSC ERROR: " fmt "\n", a); return (code); } while (0)
+#define SETERRQ2(comm, code, fmt, a, b) do { fprintf(stderr, "[0]PETSC ERROR: " fmt "\n", a, b); return (code); } while (0)
+
+/* ---- callback ABI (ex12.cpp:147-150, :209-212, :113) ---- */
+typedef void (*PetscPointFunc)(PetscInt, PetscInt, PetscInt, const PetscInt[], const PetscInt[], const PetscScalar[],
+                               const PetscScalar[], const PetscScalar[], const PetscInt[], const PetscInt[],
+                               const PetscScalar[], const PetscScalar[], const PetscScalar[], PetscReal, const PetscReal[],
+                               PetscInt, const PetscScalar[], PetscScalar[]);
+typedef void (*PetscPointJac)(PetscInt, PetscInt, PetscInt, const PetscInt[], const PetscInt[], const PetscScalar[],
+                              const PetscScalar[], const PetscScalar[], const PetscInt[], const PetscInt[],
+                              const PetscScalar[], const PetscScalar[], const PetscScalar[], PetscReal, PetscReal,
+                              const PetscReal[], PetscInt, const PetscScalar[], PetscScalar[]);
+typedef PetscErrorCode (*PetscSimplePointFunc)(PetscInt, PetscReal, const PetscReal[], PetscInt, PetscScalar *, void *);
+
+namespace ohp {
+
+/* ---- options database (the -key value subset SNESSetFromOptions / ProcessOptions read) ---- */
+inline std::map<std::string, std::string> &options_db() { static std::map<std::string, std::string> db; return db; }
+inline ohp_context &global_context() { static ohp_context c = nullptr; return c; }
+
+struct ProblemKey {
+  void *f0, *f1, *g3, *bc;
+  bool operator<(const ProblemKey &o) const {
+    if (f0 != o.f0) return f0 < o.f0;
+    if (f1 != o.f1) return f1 < o.f1;
+    if (g3 != o.g3) return g3 < o.g3;
+    return bc < o.bc;
+  }
+};
+struct ProblemRecord { int id; void *exact; };
+inline std::map<ProblemKey, ProblemRecord> &problem_registry() { static std::map<ProblemKey, ProblemRecord> r; return r; }
+
+#ifdef __CUDACC__
+template <class P> int register_problem(void *f0, void *f1, void *g3, void *bc, void *exact) {
+  int id = -1;
+  if (ohp_problem_register(launch_residual_any<P>, launch_jacobian_any<P>, launch_project_exact_any<P>, &id)) return -1;
+  problem_registry()[ProblemKey{f0, f1, g3, bc}] = ProblemRecord{id, exact};
+  return id;
+}
+#endif
+
+}  // namespace ohp
+
+/* Instantiates the device kernels for one callback set and registers them (file scope, nvcc only). */
+#define OHP_DEFINE_PROBLEM(name, F0, F1, G3, BC, EXACT)                                                         \
+  struct ohp_problem_##name {                                                                                   \
+    static constexpr bool kJacobianUsesU = true;                                                                \
+    OHP_HD static void f0(OHP_PF_ARGS, double f[]) {                                                            \
+      F0(dim, Nf, NfAux, uOff, uOff_x, u, u_t, u_x, aOff, aOff_x, a, a_t, a_x, t, x, numConstants, constants, f); \
+    }                                                                                                           \
+    OHP_HD static void f1(OHP_PF_ARGS, double f[]) {                                                            \
+      F1(dim, Nf, NfAux, uOff, uOff_x, u, u_t, u_x, aOff, aOff_x, a, a_t, a_x, t, x, numConstants, constants, f); \
+    }                                                                                                           \
+    OHP_HD static void g3(OHP_PJ_ARGS, double g[]) {                                                            \
+      G3(dim, Nf, NfAux, uOff, uOff_x, u, u_t, u_x, aOff, aOff_x, a, a_t, a_x, t, u_tShift, x, numConstants, constants, g); \
+    }                                                                                                           \
+    OHP_HD static int bc(int dim, double time, const double x[], int Nc, double *u, void *ctx) {                \
+      return BC(dim, time, x, Nc, u, ctx);                                                                      \
+    }                                                                                                           \
+    OHP_HD static int exact(int dim, double time, const double x[], int Nc, double *u, void *ctx) {             \
+      return EXACT(dim, time, x, Nc, u, ctx);                                                                   \
+    }                                                                                                           \
+  };                                                                                                            \
+  static const int ohp_problem_id_##name = ohp::register_problem<ohp_problem_##name>(                           \
+      (void *)(PetscPointFunc)F0, (void *)(PetscPointFunc)F1, (void *)(PetscPointJac)G3,                        \
+      (void *)(PetscSimplePointFunc)BC, (void *)(PetscSimplePointFunc)EXACT);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* objects                                                                                          */
+/* ------------------------------------------------------------------------------------------------ */
+struct _p_PetscSF {
+  struct _p_DM *dm;
+};
+struct _p_PetscDS {
+  PetscPointFunc f0 = nullptr, f1 = nullptr;
+  PetscPointJac g3 = nullptr;
+  PetscSimplePointFunc bc = nullptr, exact = nullptr;
+  void *exact_ctx = nullptr;
+  int problem = -1;
+};
+struct _p_PetscFE { PetscInt dim, Nc; PetscBool simplex; };
+struct _p_DMLabel { std::string name; };
+struct _p_DM {
+  ohp_mesh mesh = nullptr;
+  int refs = 1;
+  bool set_up = false;
+  void *app_ctx = nullptr;
+  _p_PetscSF sf;
+  _p_PetscDS ds;
+  _p_DMLabel marker;
+  bool has_marker = false, has_field = false, has_bc = false;
+  PetscInt dim = 0;
+};
+struct _p_Vec { ohp_vec v = nullptr; _p_DM *dm = nullptr; std::string name; };
+struct _p_Mat { ohp_mat m = nullptr; _p_DM *dm = nullptr; };
+struct _p_SNES {
+  _p_DM *dm = nullptr;
+  _p_Mat *A = nullptr, *J = nullptr;
+  _p_Vec *sol = nullptr;
+  ohp_snes_options opts;
+  ohp_snes_result last;
+  bool monitor = false, ksp_monitor = false, converged_reason = false, ksp_converged_reason = false;
+  std::string ksp_type = "cg";
+};
+typedef _p_DM *DM;
+typedef _p_Vec *Vec;
+typedef _p_Mat *Mat;
+typedef _p_SNES *SNES;
+typedef _p_PetscDS *PetscDS;
+typedef _p_PetscFE *PetscFE;
+typedef _p_PetscSF *PetscSF;
+typedef _p_DMLabel *DMLabel;
+typedef void *PetscObject;
+typedef struct _p_MatNullSpace *MatNullSpace;
+
+/* ---- init / options ---- */
+inline PetscErrorCode PetscInitialize(int *argc, char ***argv, const char *, const char *) {
+  for (int i = 1; i < *argc; ++i) {
+    const char *a = (*argv)[i];
+    if (a[0] == '-' && !(a[1] >= '0' && a[1] <= '9')) {
+      std::string key(a + 1), val;
+      if (i + 1 < *argc && !((*argv)[i + 1][0] == '-' && !((*argv)[i + 1][1] >= '0' && (*argv)[i + 1][1] <= '9') && (*argv)[i + 1][1] != '.')) val = (*argv)[++i];
+      ohp::options_db()[key] = val;
+    }
+  }
+  int device = 0;
+  const char *lr = getenv("LOCAL_RANK");
+  if (lr) device = atoi(lr);
+  return ohp_init(device, &ohp::global_context());
+}
+inline PetscErrorCode PetscFinalize(void) {
+  PetscErrorCode ierr = ohp_finalize(ohp::global_context());
+  ohp::global_context() = nullptr;
+  return ierr;
+}
+inline PetscErrorCode PetscOptionsGetString(void *, const char *, const char *name, char *out, size_t len, PetscBool *set) {
+  auto it = ohp::options_db().find(name + 1);
+  if (set) *set = it != ohp::options_db().end() ? PETSC_TRUE : PETSC_FALSE;
+  if (it != ohp::options_db().end()) { strncpy(out, it->second.c_str(), len); out[len - 1] = 0; }
+  return 0;
+}
+inline PetscErrorCode PetscOptionsGetInt(void *, const char *, const char *name, PetscInt *v, PetscBool *set) {
+  auto it = ohp::options_db().find(name + 1);
+  if (set) *set = it != ohp::options_db().end() ? PETSC_TRUE : PETSC_FALSE;
+  if (it != ohp::options_db().end()) *v = atoi(it->second.c_str());
+  return 0;
+}
+inline PetscErrorCode PetscOptionsGetReal(void *, const char *, const char *name, PetscReal *v, PetscBool *set) {
+  auto it = ohp::options_db().find(name + 1);
+  if (set) *set = it != ohp::options_db().end() ? PETSC_TRUE : PETSC_FALSE;
+  if (it != ohp::options_db().end()) *v = atof(it->second.c_str());
+  return 0;
+}
+inline PetscErrorCode PetscOptionsHasName(void *, const char *, const char *name, PetscBool *set) {
+  *set = ohp::options_db().count(name + 1) ? PETSC_TRUE : PETSC_FALSE;
+  return 0;
+}
+inline PetscErrorCode PetscOptionsGetIntArray(void *, const char *, const char *name, PetscInt v[], PetscInt *n, PetscBool *set) {
+  auto it = ohp::options_db().find(name + 1);
+  if (set) *set = it != ohp::options_db().end() ? PETSC_TRUE : PETSC_FALSE;
+  if (it == ohp::options_db().end()) { *n = 0; return 0; }
+  PetscInt k = 0;
+  const char *s = it->second.c_str();
+  while (*s && k < *n) { v[k++] = (PetscInt)strtol(s, (char **)&s, 10); if (*s == ',') ++s; }
+  *n = k;
+  return 0;
+}
+#define PetscPrintf(comm, ...) (printf(__VA_ARGS__), 0)
+inline PetscErrorCode PetscObjectSetName(PetscObject, const char *) { return 0; }
+
+/* ---- DM: mesh ---- */
+inline PetscErrorCode DMPlexCreateFromCellListPetsc(MPI_Comm, PetscInt dim, PetscInt numCells, PetscInt numVertices,
+                                                    PetscInt numCorners, PetscBool /*interpolate*/, const PetscInt cells[],
+                                                    PetscInt spaceDim, const PetscReal vertexCoords[], DM *dm) {
+  if (numCorners != dim + 1 || spaceDim != dim) { ohp_last_error(); return PETSC_ERR_SUP; }
+  DM d = new _p_DM();
+  d->dim = dim;
+  d->sf.dm = d;
+  PetscErrorCode ierr = ohp_mesh_create(ohp::global_context(), dim, numCells, numVertices, cells, vertexCoords, &d->mesh);
+  if (ierr) { delete d; return ierr; }
+  *dm = d;
+  return 0;
+}
+inline PetscErrorCode DMGetPointSF(DM dm, PetscSF *sf) { *sf = &dm->sf; return 0; }
+/* ex12.cpp:864-876: leaves and roots are Plex POINTS (local: nCells + vertex; remote: the owner's
+ * nCells + its vertex index, ex12.cpp:868-870,924-926).  ohp_mesh_set_point_sf converts them to vertex
+ * indices (it all-gathers the ranks' cell counts).  PETSC_OWN_POINTER: the arrays are released here. */
+inline PetscErrorCode PetscSFSetGraph(PetscSF sf, PetscInt /*nroots*/, PetscInt nleaves, PetscInt *ilocal, PetscCopyMode lmode,
+                                      PetscSFNode *iremote, PetscCopyMode rmode) {
+  std::vector<int32_t> orank(nleaves), opoint(nleaves);
+  for (PetscInt i = 0; i < nleaves; ++i) { orank[i] = iremote[i].rank; opoint[i] = iremote[i].index; }
+  PetscErrorCode ierr = ohp_mesh_set_point_sf(sf->dm->mesh, nleaves, ilocal, orank.data(), opoint.data());
+  if (lmode == PETSC_OWN_POINTER) free(ilocal);
+  if (rmode == PETSC_OWN_POINTER) free(iremote);
+  return ierr;
+}
+inline PetscErrorCode PetscMalloc1(size_t n, void *out, size_t elem) { *(void **)out = malloc(n * elem); return *(void **)out ? 0 : OHP_ERR_MEM; }
+#define PetscMalloc1(n, pp) PetscMalloc1((size_t)(n), (void *)(pp), sizeof(**(pp)))
+inline PetscErrorCode DMPlexInterpolate(DM dm, DM *idm) { dm->refs++; *idm = dm; return 0; } /* edges are implicit here */
+inline PetscErrorCode DMCreateLabel(DM dm, const char *name) { dm->marker.name = name; return 0; }
+inline PetscErrorCode DMGetLabel(DM dm, const char *, DMLabel *label) { *label = &dm->marker; return 0; }
+inline PetscErrorCode DMHasLabel(DM dm, const char *, PetscBool *has) { *has = dm->has_marker ? PETSC_TRUE : PETSC_FALSE; return 0; }
+
+inline PetscErrorCode ohp_dm_setup(DM dm) {
+  if (dm->set_up) return 0;
+  PetscErrorCode ierr = ohp_mesh_setup(dm->mesh);
+  if (!ierr) dm->set_up = true;
+  return ierr;
+}
+/* CreateBCLabel (ex12.cpp:515-526): faces with one supporting cell, completed to their vertices */
+inline PetscErrorCode DMPlexMarkBoundaryFaces(DM dm, PetscInt value, DMLabel) {
+  if (value != 1) return PETSC_ERR_SUP;
+  dm->has_marker = true;
+  return 0; /* evaluated on the device by ohp_mesh_setup, once ghosts are known */
+}
+inline PetscErrorCode DMPlexLabelComplete(DM, DMLabel) { return 0; }
+inline PetscErrorCode DMDestroy(DM *dm) {
+  if (!*dm) return 0;
+  if (--(*dm)->refs == 0) { ohp_mesh_destroy((*dm)->mesh); delete *dm; }
+  *dm = nullptr;
+  return 0;
+}
+inline PetscErrorCode DMSetApplicationContext(DM dm, void *ctx) { dm->app_ctx = ctx; return 0; }
+inline PetscErrorCode DMGetApplicationContext(DM dm, void *ctx) { *(void **)ctx = dm->app_ctx; return 0; }
+inline PetscErrorCode DMGetDimension(DM dm, PetscInt *dim) { *dim = dm->dim; return 0; }
+
+/* ---- discretisation ---- */
+inline PetscErrorCode PetscFECreateDefault(MPI_Comm, PetscInt dim, PetscInt Nc, PetscBool simplex, const char *, PetscInt qorder, PetscFE *fe) {
+  if (!simplex || Nc != 1 || (qorder != -1 && qorder != PETSC_DEFAULT)) return PETSC_ERR_SUP; /* P1 simplices, default quadrature (ex12.cpp:1309) */
+  PetscInt degree = 1;
+  PetscOptionsGetInt(NULL, NULL, "-petscspace_degree", &degree, NULL);
+  if (degree != 1) { fprintf(stderr, "[0]PETSC ERROR: only -petscspace_degree 1 is built\n"); return PETSC_ERR_SUP; }
+  *fe = new _p_PetscFE{dim, Nc, simplex};
+  return 0;
+}
+inline PetscErrorCode PetscFEDestroy(PetscFE *fe) { delete *fe; *fe = nullptr; return 0; }
+inline PetscErrorCode DMSetField(DM dm, PetscInt f, DMLabel, PetscObject) { if (f != 0) return PETSC_ERR_SUP; dm->has_field = true; return 0; }
+inline PetscErrorCode DMCreateDS(DM) { return 0; }
+inline PetscErrorCode DMGetDS(DM dm, PetscDS *ds) { *ds = &dm->ds; return 0; }
+inline PetscErrorCode PetscDSSetResidual(PetscDS ds, PetscInt f, PetscPointFunc f0, PetscPointFunc f1) {
+  if (f != 0) return PETSC_ERR_SUP;
+  ds->f0 = f0; ds->f1 = f1; ds->problem = -1;
+  return 0;
+}
+inline PetscErrorCode PetscDSSetJacobian(PetscDS ds, PetscInt f, PetscInt g, PetscPointJac g0, PetscPointJac g1, PetscPointJac g2, PetscPointJac g3) {
+  if (f != 0 || g != 0 || g0 || g1 || g2) return PETSC_ERR_SUP; /* only g3 is used on this path (ex12.cpp:1182) */
+  ds->g3 = g3; ds->problem = -1;
+  return 0;
+}
+inline PetscErrorCode PetscDSSetExactSolution(PetscDS ds, PetscInt f, PetscSimplePointFunc sol, void *ctx) {
+  if (f != 0) return PETSC_ERR_SUP;
+  ds->exact = sol; ds->exact_ctx = ctx;
+  return 0;
+}
+inline PetscErrorCode DMAddBoundary(DM dm, DMBoundaryConditionType type, const char *, const char *labelname, PetscInt field,
+                                    PetscInt numcomps, const PetscInt *, void (*bcFunc)(void), void (*)(void), PetscInt numids,
+                                    const PetscInt *ids, void *) {
+  if (type != DM_BC_ESSENTIAL || field != 0 || numcomps != 0 || numids != 1 || ids[0] != 1 || strcmp(labelname, "marker")) {
+    fprintf(stderr, "[0]PETSC ERROR: only the essential condition on label \"marker\" = 1 is built (ex12.cpp:1237-1239)\n");
+    return PETSC_ERR_SUP;
+  }
+  dm->ds.bc = (PetscSimplePointFunc)bcFunc;
+  dm->ds.problem = -1;
+  dm->has_bc = true;
+  return 0;
+}
+/* resolves the registered device instantiation of the DS's callback set */
+inline PetscErrorCode ohp_ds_problem(PetscDS ds, int *problem) {
+  if (ds->problem < 0) {
+    auto &reg = ohp::problem_registry();
+    auto it = reg.find(ohp::ProblemKey{(void *)ds->f0, (void *)ds->f1, (void *)ds->g3, (void *)ds->bc});
+    if (it == reg.end()) {
+      fprintf(stderr, "[0]PETSC ERROR: this (f0, f1, g3, bc) callback set has no device instantiation: declare it with "
+                      "OHP_DEFINE_PROBLEM(...) in the translation unit that defines the callbacks\n");
+      return PETSC_ERR_SUP;
+    }
+    ds->problem = it->second.id;
+  }
+  *problem = ds->problem;
+  return 0;
+}
+
+/* ---- Vec / Mat ---- */
+inline PetscErrorCode DMCreateGlobalVector(DM dm, Vec *v) {
+  PetscErrorCode ierr = ohp_dm_setup(dm); if (ierr) return ierr;
+  Vec x = new _p_Vec(); x->dm = dm;
+  ierr = ohp_vec_create(dm->mesh, &x->v);
+  if (ierr) { delete x; return ierr; }
+  *v = x;
+  return 0;
+}
+inline PetscErrorCode VecDuplicate(Vec v, Vec *w) {
+  Vec x = new _p_Vec(); x->dm = v->dm;
+  PetscErrorCode ierr = ohp_vec_duplicate(v->v, &x->v);
+  if (ierr) { delete x; return ierr; }
+  *w = x;
+  return 0;
+}
+inline PetscErrorCode VecDestroy(Vec *v) { if (*v) { ohp_vec_destroy((*v)->v); delete *v; *v = nullptr; } return 0; }
+inline PetscErrorCode VecSet(Vec v, PetscScalar a) { return ohp_vec_set(v->v, a); }
+inline PetscErrorCode VecCopy(Vec x, Vec y) { return ohp_vec_copy(x->v, y->v); }
+inline PetscErrorCode VecAXPY(Vec y, PetscScalar a, Vec x) { return ohp_vec_axpy(y->v, a, x->v); }
+inline PetscErrorCode VecAYPX(Vec y, PetscScalar a, Vec x) { return ohp_vec_aypx(y->v, a, x->v); }
+inline PetscErrorCode VecDot(Vec x, Vec y, PetscScalar *r) { return ohp_vec_dot(x->v, y->v, r); }
+inline PetscErrorCode VecChop(Vec v, PetscReal tol) { return ohp_vec_chop(v->v, tol); }
+inline PetscErrorCode VecNorm(Vec v, NormType t, PetscReal *r) { if (t != NORM_2) return PETSC_ERR_SUP; return ohp_vec_norm2(v->v, r); }
+inline PetscErrorCode VecGetLocalSize(Vec v, PetscInt *n) { return ohp_vec_size(v->v, n); }
+inline PetscErrorCode VecGetSize(Vec v, PetscInt *n) {
+  ohp_mesh_info info;
+  PetscErrorCode ierr = ohp_mesh_get_info(v->dm->mesh, &info);
+  *n = (PetscInt)info.n_global;
+  return ierr;
+}
+/* host copy of the local part (VecGetArrayRead + copy) */
+inline PetscErrorCode VecGetValuesHost(Vec v, std::vector<PetscScalar> &out) {
+  PetscInt n; ohp_vec_size(v->v, &n);
+  out.resize(n);
+  return ohp_vec_to_host(v->v, out.data());
+}
+inline PetscErrorCode DMCreateMatrix(DM dm, Mat *J) {
+  PetscErrorCode ierr = ohp_dm_setup(dm); if (ierr) return ierr;
+  Mat A = new _p_Mat(); A->dm = dm;
+  ierr = ohp_mat_create(dm->mesh, &A->m);
+  if (ierr) { delete A; return ierr; }
+  *J = A;
+  return 0;
+}
+inline PetscErrorCode MatDestroy(Mat *A) { if (*A) { ohp_mat_destroy((*A)->m); delete *A; *A = nullptr; } return 0; }
+inline PetscErrorCode MatMult(Mat A, Vec x, Vec y) { return ohp_mat_mult(A->m, x->v, y->v); }
+inline PetscErrorCode MatGetSize(Mat A, PetscInt *M, PetscInt *N) {
+  ohp_mesh_info info;
+  PetscErrorCode ierr = ohp_mesh_get_info(A->dm->mesh, &info);
+  if (M) *M = (PetscInt)info.n_global;
+  if (N) *N = (PetscInt)info.n_global;
+  return ierr;
+}
+inline PetscErrorCode MatSetNullSpace(Mat, MatNullSpace) { return 0; }
+
+/* ---- projection / error ---- */
+inline PetscErrorCode DMProjectFunction(DM dm, PetscReal, PetscSimplePointFunc *funcs, void **, InsertMode, Vec u) {
+  int problem;
+  PetscErrorCode ierr = ohp_dm_setup(dm); if (ierr) return ierr;
+  ierr = ohp_ds_problem(&dm->ds, &problem); if (ierr) return ierr;
+  if (funcs[0] == dm->ds.exact) return ohp_project(dm->mesh, problem, 1, u->v);
+  /* the only other function ex12 projects is zero() (ex12.cpp:76-80,1598-1602): recognised by value */
+  PetscScalar val = 1.0; const PetscReal x0[3] = {0.3, 0.7, 0.2};
+  funcs[0](dm->dim, 0.0, x0, 1, &val, NULL);
+  if (val == 0.0) return ohp_project(dm->mesh, problem, 0, u->v);
+  fprintf(stderr, "[0]PETSC ERROR: DMProjectFunction: only the registered exact solution and zero are built\n");
+  return PETSC_ERR_SUP;
+}
+inline PetscErrorCode DMComputeL2Diff(DM dm, PetscReal, PetscSimplePointFunc *, void **, Vec u, PetscReal *err) {
+  int problem;
+  PetscErrorCode ierr = ohp_ds_problem(&dm->ds, &problem); if (ierr) return ierr;
+  return ohp_l2_error(dm->mesh, problem < 3 ? problem : 0, u->v, err);
+}
+
+/* ---- SNES ---- */
+inline PetscErrorCode SNESCreate(MPI_Comm, SNES *snes) {
+  SNES s = new _p_SNES();
+  ohp_snes_default_options(&s->opts);
+  memset(&s->last, 0, sizeof(s->last));
+  *snes = s;
+  return 0;
+}
+inline PetscErrorCode SNESDestroy(SNES *snes) {
+  if (*snes) { delete *snes; *snes = nullptr; }
+  return 0;
+}
+inline PetscErrorCode SNESSetDM(SNES snes, DM dm) { snes->dm = dm; return 0; }
+inline PetscErrorCode SNESGetDM(SNES snes, DM *dm) { *dm = snes->dm; return 0; }
+inline PetscErrorCode DMPlexSetSNESLocalFEM(DM dm, void *, void *, void *) {
+  int problem;
+  return ohp_ds_problem(&dm->ds, &problem); /* fail early if the callbacks have no device instantiation */
+}
+inline PetscErrorCode SNESSetJacobian(SNES snes, Mat A, Mat J, void *, void *) { snes->A = A; snes->J = J; return 0; }
+inline PetscErrorCode SNESSetFromOptions(SNES snes) {
+  char buf[64];
+  PetscBool set;
+  PetscOptionsGetReal(NULL, NULL, "-snes_rtol", &snes->opts.rtol, NULL);
+  PetscOptionsGetReal(NULL, NULL, "-snes_atol", &snes->opts.abstol, NULL);
+  PetscOptionsGetReal(NULL, NULL, "-snes_stol", &snes->opts.stol, NULL);
+  PetscOptionsGetInt(NULL, NULL, "-snes_max_it", &snes->opts.max_it, NULL);
+  PetscOptionsGetReal(NULL, NULL, "-ksp_rtol", &snes->opts.ksp.rtol, NULL);
+  PetscOptionsGetReal(NULL, NULL, "-ksp_atol", &snes->opts.ksp.abstol, NULL);
+  PetscOptionsGetReal(NULL, NULL, "-ksp_divtol", &snes->opts.ksp.dtol, NULL);
+  PetscOptionsGetInt(NULL, NULL, "-ksp_max_it", &snes->opts.ksp.max_it, NULL);
+  PetscOptionsGetString(NULL, NULL, "-ksp_type", buf, sizeof(buf), &set);
+  if (set && strcmp(buf, "cg")) { fprintf(stderr, "[0]PETSC ERROR: -ksp_type %s: only cg is built (north_star)\n", buf); return PETSC_ERR_SUP; }
+  snes->opts.ksp.pc = OHP_PC_NONE;
+  PetscOptionsGetString(NULL, NULL, "-pc_type", buf, sizeof(buf), &set);
+  if (set) {
+    if (!strcmp(buf, "none")) snes->opts.ksp.pc = OHP_PC_NONE;
+    else if (!strcmp(buf, "jacobi")) snes->opts.ksp.pc = OHP_PC_JACOBI;
+    else { fprintf(stderr, "[0]PETSC ERROR: -pc_type %s: only none and jacobi are built\n", buf); return PETSC_ERR_SUP; }
+  }
+  PetscBool b;
+  PetscOptionsHasName(NULL, NULL, "-snes_monitor_short", &b); snes->monitor = b;
+  PetscOptionsHasName(NULL, NULL, "-snes_monitor", &b); snes->monitor = snes->monitor || b;
+  PetscOptionsHasName(NULL, NULL, "-snes_converged_reason", &b); snes->converged_reason = b;
+  PetscOptionsHasName(NULL, NULL, "-ksp_converged_reason", &b); snes->ksp_converged_reason = b;
+  return 0;
+}
+inline PetscErrorCode SNESComputeFunction(SNES snes, Vec u, Vec F) {
+  int problem;
+  PetscErrorCode ierr = ohp_ds_problem(&snes->dm->ds, &problem); if (ierr) return ierr;
+  return ohp_residual(snes->dm->mesh, problem, u->v, F->v);
+}
+inline PetscErrorCode SNESComputeJacobian(SNES snes, Vec u, Mat A, Mat) {
+  int problem;
+  PetscErrorCode ierr = ohp_ds_problem(&snes->dm->ds, &problem); if (ierr) return ierr;
+  return ohp_jacobian(snes->dm->mesh, problem, u->v, A->m);
+}
+inline const char *ohp_snes_reason_name(int r) {
+  switch (r) {
+    case 2: return "CONVERGED_FNORM_ABS"; case 3: return "CONVERGED_FNORM_RELATIVE"; case 4: return "CONVERGED_SNORM_RELATIVE";
+    case -3: return "DIVERGED_LINEAR_SOLVE"; case -5: return "DIVERGED_MAX_IT"; default: return "UNKNOWN";
+  }
+}
+inline PetscErrorCode SNESSolve(SNES snes, Vec b, Vec u) {
+  if (b) return PETSC_ERR_SUP;
+  if (!snes->J) return PETSC_ERR_ORDER;
+  int problem;
+  PetscErrorCode ierr = ohp_ds_problem(&snes->dm->ds, &problem); if (ierr) return ierr;
+  ierr = ohp_snes_solve(snes->dm->mesh, problem, snes->J->m, u->v, &snes->opts, &snes->last); if (ierr) return ierr;
+  if (snes->monitor) {
+    printf("  0 SNES Function norm %g\n", snes->last.fnorm0);
+    printf("  %d SNES Function norm %g\n", snes->last.its, snes->last.fnorm);
+  }
+  if (snes->ksp_converged_reason) printf("  Linear solve %s: total iterations %d\n", snes->last.reason == -3 ? "did not converge" : "converged", snes->last.ksp_its);
+  if (snes->converged_reason)
+    printf("Nonlinear solve %s due to %s iterations %d\n", snes->last.reason > 0 ? "converged" : "did not converge",
+           ohp_snes_reason_name(snes->last.reason), snes->last.its);
+  snes->sol = u; /* borrowed reference, as SNESGetSolution returns (ex12.cpp:1610) */
+  return 0;
+}
+inline PetscErrorCode SNESGetSolution(SNES snes, Vec *u) { *u = snes->sol; return 0; }
+inline PetscErrorCode SNESGetIterationNumber(SNES snes, PetscInt *its) { *its = snes->last.its; return 0; }
+inline PetscErrorCode SNESGetLinearSolveIterations(SNES snes, PetscInt *its) { *its = snes->last.ksp_its; return 0; }
+inline PetscErrorCode SNESGetConvergedReason(SNES snes, int *reason) { *reason = snes->last.reason; return 0; }
+
+#endif /* OHP_PETSC_H */

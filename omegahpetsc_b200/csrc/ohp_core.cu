@@ -263,6 +263,21 @@ extern "C" int ohp_mesh_set_ghosts(ohp_mesh m, int32_t n, const int32_t *gv, con
   return 0;
 }
 
+extern "C" int ohp_mesh_set_point_sf(ohp_mesh m, int32_t n, const int32_t *leaf, const int32_t *rrank,
+                                     const int32_t *rpoint) {
+  if (!m) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_mesh_set_point_sf: null mesh");
+  std::vector<int64_t> ncells;
+  OHP_TRY(ohp_allgather_i64(m->ctx, m->nC, ncells)); /* getNeighborElmCounts, ex12.cpp:528-577 */
+  std::vector<int32_t> gv(n), ov(n);
+  for (int i = 0; i < n; ++i) {
+    if (rrank[i] < 0 || rrank[i] >= m->ctx->nranks) OHP_FAIL(OHP_ERR_ARG_OUTOFRANGE, "ohp_mesh_set_point_sf: leaf %d root rank %d", i, rrank[i]);
+    gv[i] = leaf[i] - m->nC;
+    ov[i] = rpoint[i] - (int32_t)ncells[rrank[i]];
+    if (ov[i] < 0) OHP_FAIL(OHP_ERR_ARG_OUTOFRANGE, "ohp_mesh_set_point_sf: root point %d of leaf %d is a cell of rank %d, not a vertex", rpoint[i], i, rrank[i]);
+  }
+  return ohp_mesh_set_ghosts(m, n, gv.data(), rrank, ov.data());
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* setup kernels                                                                         */
 /* ------------------------------------------------------------------------------------ */

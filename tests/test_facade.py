@@ -1,0 +1,88 @@
+"""The PETSc-shaped C++ facade (include/ohp_petsc.h, include/ohp_omega_h.h) through the ex12-style
+driver examples/ex12_b200.cu: user callbacks compiled by nvcc, registered with OHP_DEFINE_PROBLEM,
+found again from the host function pointers PetscDSSetResidual/SetJacobian/DMAddBoundary receive."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_mesh_path, load_osh_oracle
+
+EXE = os.path.join(ROOT, "examples", "ex12_b200")
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "omegahpetsc_b200", "csrc"), "-j8"], check=True)
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "examples")], check=True)
+
+
+def test_example_builds_with_user_callbacks_inlined():
+    build()
+    out = subprocess.run(["cuobjdump", "-elf", "-lelf", EXE], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    sym = subprocess.run("cuobjdump -symbols %s | grep -c ohp_problem_coeff_none" % EXE, shell=True, capture_output=True, text=True).stdout
+    assert int(sym.strip() or 0) >= 2, "assembly kernels must be instantiated on the user's callback set"
+
+
+def oracle_l2_error(oracle, cells, coords, gidx, u):
+    xi, w = oracle.quadrature(2)
+    full = (coords ** 2).sum(axis=1)
+    full[gidx >= 0] = u
+    X = coords[cells]
+    J = 0.5 * np.stack([X[:, 1] - X[:, 0], X[:, 2] - X[:, 0]], axis=2)
+    detJ = J[:, 0, 0] * J[:, 1, 1] - J[:, 0, 1] * J[:, 1, 0]
+    err = 0.0
+    for q in range(4):
+        phi = np.array([-(xi[q, 0] + xi[q, 1]) / 2, (1 + xi[q, 0]) / 2, (1 + xi[q, 1]) / 2])
+        xq = X[:, 0] + J @ (xi[q] + 1.0)
+        uq = full[cells] @ phi
+        err += (w[q] * np.abs(detJ) * (uq - (xq ** 2).sum(axis=1)) ** 2).sum()
+    return float(np.sqrt(err))
+
+
+@pytest.mark.gpu
+def test_full_run_on_24k_fixture(oracle_mod):
+    build()
+    p = subprocess.run([EXE, "-mesh", golden_mesh_path("24k.osh"), "-run_type", "full", "-ksp_rtol", "1e-9", "-ksp_max_it", "100000",
+                        "-snes_converged_reason", "-snes_monitor_short"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    m = re.search(r"N: (\d+) Newton its: (\d+) CG its: (\d+) L_2 Error: ([0-9.e+-]+)", p.stdout)
+    assert m, p.stdout
+    cells, coords, _ = load_osh_oracle("24k.osh")
+    bnd = oracle_mod.mark_boundary(cells, coords.shape[0])
+    gidx, N = oracle_mod.numbering(bnd)
+    rowptr, colidx = oracle_mod.pattern(cells, gidx, N)
+    ref = oracle_mod.newton(0, cells, coords, gidx, N, rowptr, colidx, ksp_rtol=1e-9, ksp_maxit=100000)
+    assert int(m.group(1)) == N and int(m.group(2)) == 1
+    assert abs(int(m.group(3)) - ref["ksp_its"]) <= ref["ksp_its"] // 40
+    assert float(m.group(4)) == pytest.approx(oracle_l2_error(oracle_mod, cells, coords, gidx, ref["u"]), rel=1e-4)
+    assert "Nonlinear solve converged due to CONVERGED_FNORM_RELATIVE iterations 1" in p.stdout
+    assert "0 SNES Function norm 181.915" in p.stdout
+
+
+@pytest.mark.gpu
+def test_run_type_test_and_perf_and_analytic():
+    build()
+    p = subprocess.run([EXE, "-mesh", "box", "-cells", "48,40", "-run_type", "test"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    lin = float(re.search(r"Linear L_2 Residual: ([0-9.e+-]+)", p.stdout).group(1))
+    assert lin < 1e-9, p.stdout  # A u + F(0) = F(u), ex12.cpp:1651-1661
+    res = float(re.search(r"\nL_2 Residual: ([0-9.e+-]+)", p.stdout).group(1))
+    assert res < 1e-9, "the nodal interpolant of x^2+y^2 solves the P1 system on the same-diagonal box"
+    p = subprocess.run([EXE, "-mesh", golden_mesh_path("23elm.osh"), "-run_type", "perf"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "L_2 Residual: 10.9345" in p.stdout, p.stdout + p.stderr
+    p = subprocess.run([EXE, "-mesh", "box", "-cells", "32,32", "-variable_coefficient", "analytic", "-ksp_rtol", "1e-10", "-pc_type", "jacobi"],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert float(re.search(r"L_2 Error: ([0-9.e+-]+)", p.stdout).group(1)) < 2e-3
+
+
+@pytest.mark.gpu
+def test_unsupported_requests_fail_loudly():
+    build()
+    p = subprocess.run([EXE, "-mesh", "box", "-cells", "8,8", "-ksp_type", "gmres"], capture_output=True, text=True, timeout=120)
+    assert p.returncode != 0 and "only cg is built" in p.stderr
+    p = subprocess.run([EXE, "-mesh", "/nonexistent.osh"], capture_output=True, text=True, timeout=120)
+    assert p.returncode != 0
