@@ -153,8 +153,13 @@ __device__ __forceinline__ void load_cell(const ohp_assembly_view &vw, int c, in
   for (int j = 0; j < NC; ++j) cv[j] = __ldg(vw.cells_dev + (size_t)c * NC + j);
 #pragma unroll
   for (int j = 0; j < NC; ++j) {
+    if constexpr (DIM == 2) { /* one 16-byte load per vertex (cudaMalloc'ed base, 16-byte stride) */
+      const double2 xy = __ldg(reinterpret_cast<const double2 *>(vw.coords_dev) + cv[j]);
+      X[j][0] = xy.x; X[j][1] = xy.y;
+    } else {
 #pragma unroll
-    for (int d = 0; d < DIM; ++d) X[j][d] = __ldg(vw.coords_dev + (size_t)cv[j] * DIM + d);
+      for (int d = 0; d < DIM; ++d) X[j][d] = __ldg(vw.coords_dev + (size_t)cv[j] * DIM + d);
+    }
   }
   if (WITH_U) {
 #pragma unroll
@@ -167,82 +172,163 @@ __device__ __forceinline__ void load_cell(const ohp_assembly_view &vw, int c, in
 }
 
 /* ------------------------------------------------------------------------------------ */
-/* Residual: F[r] = sum over cells c in star(v_r), ascending, of Fe_c[b]                 */
+/* Per-incidence work: what cell c contributes to the row of its corner b.                */
 /* ------------------------------------------------------------------------------------ */
+/* Fe_c[b] = sum_q w_q detJ ( phi_b f0 + grad(phi_b) . f1 ) */
 template <int DIM, class P>
-__global__ void __launch_bounds__(256) k_residual_rows(const ohp_assembly_view vw) {
+__device__ __forceinline__ double cell_residual_entry(const ohp_assembly_view &vw, int c, int b) {
   constexpr int NC = DIM + 1;
+  const int uOff[2] = {0, 1}, uOff_x[2] = {0, DIM};
+  int cv[NC];
+  double X[NC][DIM], ue[NC];
+  load_cell<DIM, P, true>(vw, c, cv, X, ue);
+  CellGeom<DIM> g;
+  cell_geometry<DIM>(X, g);
+  double ux[DIM], Gb[DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) s += g.G[j][d] * ue[j];
+    ux[d] = s;
+    double gb = g.G[0][d];
+#pragma unroll
+    for (int j = 1; j < NC; ++j) gb = (b == j) ? g.G[j][d] : gb;
+    Gb[d] = gb;
+  }
+  double fe = 0.0;
+#pragma unroll
+  for (int q = 0; q < Quadrature<DIM>::NQ; ++q) {
+    double phi[NC], xq[DIM], uq = 0.0;
+    p1_basis<DIM>(q, phi);
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      double s = g.v0[d];
+#pragma unroll
+      for (int f = 0; f < DIM; ++f) s += g.J[d * DIM + f] * (Quadrature<DIM>::xi(q, f) + 1.0);
+      xq[d] = s;
+    }
+    double phib = phi[0];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) { uq += phi[j] * ue[j]; phib = (b == j) ? phi[j] : phib; }
+    double f0[1] = {0.0}, f1[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) f1[d] = 0.0;
+    P::f0(DIM, 1, 0, uOff, uOff_x, &uq, nullptr, ux, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, xq, 0, nullptr, f0);
+    P::f1(DIM, 1, 0, uOff, uOff_x, &uq, nullptr, ux, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, xq, 0, nullptr, f1);
+    const double w = g.detJ * Quadrature<DIM>::w(q);
+    double s = phib * (f0[0] * w);
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) s += Gb[d] * (f1[d] * w);
+    fe += s;
+  }
+  return fe;
+}
+
+/* Ke_c[b][j] = detJ * G_b^T (sum_q w_q g3_q) G_j   (P1: gradients constant per cell) */
+template <int DIM, class P>
+__device__ __forceinline__ void cell_jacobian_row(const ohp_assembly_view &vw, int c, int b, double (&ke)[DIM + 1]) {
+  constexpr int NC = DIM + 1;
+  const int uOff[2] = {0, 1}, uOff_x[2] = {0, DIM};
+  int cv[NC];
+  double X[NC][DIM], ue[NC];
+  load_cell<DIM, P, P::kJacobianUsesU>(vw, c, cv, X, ue);
+  CellGeom<DIM> g;
+  cell_geometry<DIM>(X, g);
+  double ux[DIM], Gb[DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) {
+    double s = 0.0;
+    if (P::kJacobianUsesU) {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) s += g.G[j][d] * ue[j];
+    }
+    ux[d] = s;
+    double gb = g.G[0][d];
+#pragma unroll
+    for (int j = 1; j < NC; ++j) gb = (b == j) ? g.G[j][d] : gb;
+    Gb[d] = gb;
+  }
+  double S[DIM * DIM];
+#pragma unroll
+  for (int i = 0; i < DIM * DIM; ++i) S[i] = 0.0;
+#pragma unroll
+  for (int q = 0; q < Quadrature<DIM>::NQ; ++q) {
+    double xq[DIM], uq = 0.0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      double s = g.v0[d];
+#pragma unroll
+      for (int f = 0; f < DIM; ++f) s += g.J[d * DIM + f] * (Quadrature<DIM>::xi(q, f) + 1.0);
+      xq[d] = s;
+    }
+    if (P::kJacobianUsesU) {
+      double phi[NC];
+      p1_basis<DIM>(q, phi);
+#pragma unroll
+      for (int j = 0; j < NC; ++j) uq += phi[j] * ue[j];
+    }
+    double g3[DIM * DIM];
+#pragma unroll
+    for (int i = 0; i < DIM * DIM; ++i) g3[i] = 0.0; /* the integrator zeroes g3: g3_uu writes only the diagonal (ex12.cpp:215) */
+    P::g3(DIM, 1, 0, uOff, uOff_x, &uq, nullptr, ux, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, 0.0, xq, 0, nullptr, g3);
+    const double w = Quadrature<DIM>::w(q);
+#pragma unroll
+    for (int i = 0; i < DIM * DIM; ++i) S[i] += w * g3[i];
+  }
+  double t[DIM];
+#pragma unroll
+  for (int e2 = 0; e2 < DIM; ++e2) {
+    double s = 0.0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) s += Gb[d] * S[d * DIM + e2];
+    t[e2] = g.detJ * s;
+  }
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    double s = 0.0;
+#pragma unroll
+    for (int e2 = 0; e2 < DIM; ++e2) s += t[e2] * g.G[j][e2];
+    ke[j] = s;
+  }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Assembly kernels: "owner computes".  One thread owns one matrix row and walks the star   */
+/* of its vertex IN ASCENDING CELL ORDER (PETSc's cell-loop order): no atomics, no           */
+/* colouring, bitwise reproducible.  Jacobian rows accumulate in shared memory (a thread     */
+/* only touches its own row) and leave as one coalesced stream per block; a block whose      */
+/* rows do not fit accumulates in place in HBM.                                             */
+/* (An incidence-parallel variant that staged every (vertex, cell) contribution through      */
+/* shared memory first was measured 2x SLOWER on B200: the kernels are bound by L1 gather    */
+/* wavefronts, not by per-thread latency, and the staging buffers halve the occupancy.)      */
+/* ------------------------------------------------------------------------------------ */
+constexpr int kAsmThreads = 256;
+constexpr int kAsmAccCap = 6144; /* row entries accumulated per block: 48 KB */
+
+template <int DIM, class P>
+__global__ void __launch_bounds__(kAsmThreads) k_residual_rows(const ohp_assembly_view vw) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= vw.n_rows) return;
   const int v = __ldg(vw.row_vertex_dev + r);
   const int k0 = __ldg(vw.v2c_ptr_dev + v), k1 = __ldg(vw.v2c_ptr_dev + v + 1);
-  const int uOff[2] = {0, 1}, uOff_x[2] = {0, DIM};
   double acc = 0.0;
   for (int k = k0; k < k1; ++k) {
     const int e = __ldg(vw.v2c_dev + k);
-    const int c = e >> 2, b = e & 3;
-    int cv[NC];
-    double X[NC][DIM], ue[NC];
-    load_cell<DIM, P, true>(vw, c, cv, X, ue);
-    CellGeom<DIM> g;
-    cell_geometry<DIM>(X, g);
-    double ux[DIM], Gb[DIM];
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) {
-      double s = 0.0;
-#pragma unroll
-      for (int j = 0; j < NC; ++j) s += g.G[j][d] * ue[j];
-      ux[d] = s;
-      double gb = g.G[0][d];
-#pragma unroll
-      for (int j = 1; j < NC; ++j) gb = (b == j) ? g.G[j][d] : gb;
-      Gb[d] = gb;
-    }
-    double fe = 0.0;
-#pragma unroll
-    for (int q = 0; q < Quadrature<DIM>::NQ; ++q) {
-      double phi[NC], xq[DIM], uq = 0.0;
-      p1_basis<DIM>(q, phi);
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) {
-        double s = g.v0[d];
-#pragma unroll
-        for (int f = 0; f < DIM; ++f) s += g.J[d * DIM + f] * (Quadrature<DIM>::xi(q, f) + 1.0);
-        xq[d] = s;
-      }
-      double phib = phi[0];
-#pragma unroll
-      for (int j = 0; j < NC; ++j) { uq += phi[j] * ue[j]; phib = (b == j) ? phi[j] : phib; }
-      double f0[1] = {0.0}, f1[DIM];
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) f1[d] = 0.0;
-      P::f0(DIM, 1, 0, uOff, uOff_x, &uq, nullptr, ux, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, xq, 0, nullptr, f0);
-      P::f1(DIM, 1, 0, uOff, uOff_x, &uq, nullptr, ux, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, xq, 0, nullptr, f1);
-      const double w = g.detJ * Quadrature<DIM>::w(q);
-      double s = phib * (f0[0] * w);
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) s += Gb[d] * (f1[d] * w);
-      fe += s;
-    }
-    acc += fe;
+    acc += cell_residual_entry<DIM, P>(vw, e >> 2, e & 3);
   }
   vw.out_dev[r] = acc;
 }
 
-/* ------------------------------------------------------------------------------------ */
-/* Jacobian: one thread per row; row b of every star cell's element matrix,               */
-/*   Ke[b][j] = detJ * G_b^T (sum_q w_q g3_q) G_j   (P1: gradients constant per cell),   */
-/* added to the row's slots in shared memory, flushed coalesced.                         */
-/* ------------------------------------------------------------------------------------ */
 template <int DIM, class P>
-__global__ void __launch_bounds__(256) k_jacobian_rows(const ohp_assembly_view vw, int smem_doubles) {
+__global__ void __launch_bounds__(kAsmThreads) k_jacobian_rows(const ohp_assembly_view vw) {
   constexpr int NC = DIM + 1;
-  extern __shared__ double s_vals[];
+  extern __shared__ double acc_s[];
   const int r0 = blockIdx.x * blockDim.x;
   const int r1 = min(r0 + (int)blockDim.x, vw.n_rows);
   const int s0 = __ldg(vw.rowptr_dev + r0), s1 = __ldg(vw.rowptr_dev + r1);
-  const bool in_smem = (s1 - s0) <= smem_doubles;
-  double *acc_base = in_smem ? s_vals : (vw.out_dev + s0);
+  const bool acc_in_smem = (s1 - s0) <= kAsmAccCap;
+  double *acc_base = acc_in_smem ? acc_s : (vw.out_dev + s0);
   for (int i = threadIdx.x; i < s1 - s0; i += blockDim.x) acc_base[i] = 0.0;
   __syncthreads();
   const int r = r0 + threadIdx.x;
@@ -250,81 +336,21 @@ __global__ void __launch_bounds__(256) k_jacobian_rows(const ohp_assembly_view v
     const int v = __ldg(vw.row_vertex_dev + r);
     const int k0 = __ldg(vw.v2c_ptr_dev + v), k1 = __ldg(vw.v2c_ptr_dev + v + 1);
     double *row = acc_base + (__ldg(vw.rowptr_dev + r) - s0);
-    const int uOff[2] = {0, 1}, uOff_x[2] = {0, DIM};
     for (int k = k0; k < k1; ++k) {
       const int e = __ldg(vw.v2c_dev + k);
-      const int c = e >> 2, b = e & 3;
-      int cv[NC];
-      double X[NC][DIM], ue[NC];
-      load_cell<DIM, P, P::kJacobianUsesU>(vw, c, cv, X, ue);
-      CellGeom<DIM> g;
-      cell_geometry<DIM>(X, g);
-      double ux[DIM], Gb[DIM];
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) {
-        double s = 0.0;
-        if (P::kJacobianUsesU) {
-#pragma unroll
-          for (int j = 0; j < NC; ++j) s += g.G[j][d] * ue[j];
-        }
-        ux[d] = s;
-        double gb = g.G[0][d];
-#pragma unroll
-        for (int j = 1; j < NC; ++j) gb = (b == j) ? g.G[j][d] : gb;
-        Gb[d] = gb;
-      }
-      double S[DIM * DIM];
-#pragma unroll
-      for (int i = 0; i < DIM * DIM; ++i) S[i] = 0.0;
-#pragma unroll
-      for (int q = 0; q < Quadrature<DIM>::NQ; ++q) {
-        double xq[DIM], uq = 0.0;
-#pragma unroll
-        for (int d = 0; d < DIM; ++d) {
-          double s = g.v0[d];
-#pragma unroll
-          for (int f = 0; f < DIM; ++f) s += g.J[d * DIM + f] * (Quadrature<DIM>::xi(q, f) + 1.0);
-          xq[d] = s;
-        }
-        if (P::kJacobianUsesU) {
-          double phi[NC];
-          p1_basis<DIM>(q, phi);
-#pragma unroll
-          for (int j = 0; j < NC; ++j) uq += phi[j] * ue[j];
-        }
-        double g3[DIM * DIM];
-#pragma unroll
-        for (int i = 0; i < DIM * DIM; ++i) g3[i] = 0.0; /* the integrator zeroes g3: g3_uu writes only the diagonal (ex12.cpp:215) */
-        P::g3(DIM, 1, 0, uOff, uOff_x, &uq, nullptr, ux, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, 0.0, xq, 0, nullptr, g3);
-        const double w = Quadrature<DIM>::w(q);
-#pragma unroll
-        for (int i = 0; i < DIM * DIM; ++i) S[i] += w * g3[i];
-      }
-      /* t[e] = detJ * sum_d Gb[d] S[d][e] */
-      double t[DIM];
-#pragma unroll
-      for (int e2 = 0; e2 < DIM; ++e2) {
-        double s = 0.0;
-#pragma unroll
-        for (int d = 0; d < DIM; ++d) s += Gb[d] * S[d * DIM + e2];
-        t[e2] = g.detJ * s;
-      }
+      double ke[NC];
+      cell_jacobian_row<DIM, P>(vw, e >> 2, e & 3, ke);
       const uint8_t *sl = vw.slot_dev + (size_t)k * NC;
 #pragma unroll
       for (int j = 0; j < NC; ++j) {
         const int slot = __ldg(sl + j);
-        if (slot != 255) {
-          double s = 0.0;
-#pragma unroll
-          for (int e2 = 0; e2 < DIM; ++e2) s += t[e2] * g.G[j][e2];
-          row[slot] += s;
-        }
+        if (slot != 255) row[slot] += ke[j];
       }
     }
   }
-  if (in_smem) {
+  if (acc_in_smem) {
     __syncthreads();
-    for (int i = threadIdx.x; i < s1 - s0; i += blockDim.x) vw.out_dev[s0 + i] = s_vals[i];
+    for (int i = threadIdx.x; i < s1 - s0; i += blockDim.x) vw.out_dev[s0 + i] = acc_s[i];
   }
 }
 
@@ -340,8 +366,6 @@ template <int DIM, class P> __global__ void k_project_exact(const ohp_assembly_v
   vw.out_dev[r] = val;
 }
 
-constexpr int kJacobianSmemDoubles = 6144; /* 48 KB per 256-row block */
-
 template <int DIM, class P> int launch_residual(const ohp_assembly_view *vw) {
   if (vw->n_rows <= 0) return 0;
   const int bs = 128;
@@ -350,9 +374,8 @@ template <int DIM, class P> int launch_residual(const ohp_assembly_view *vw) {
 }
 template <int DIM, class P> int launch_jacobian(const ohp_assembly_view *vw) {
   if (vw->n_rows <= 0) return 0;
-  const int bs = 256;
-  k_jacobian_rows<DIM, P><<<(vw->n_rows + bs - 1) / bs, bs, kJacobianSmemDoubles * sizeof(double),
-                            (cudaStream_t)vw->stream>>>(*vw, kJacobianSmemDoubles);
+  k_jacobian_rows<DIM, P><<<(vw->n_rows + kAsmThreads - 1) / kAsmThreads, kAsmThreads, kAsmAccCap * sizeof(double),
+                            (cudaStream_t)vw->stream>>>(*vw);
   return cudaGetLastError() == cudaSuccess ? 0 : OHP_ERR_LIB;
 }
 template <int DIM, class P> int launch_project_exact(const ohp_assembly_view *vw) {
