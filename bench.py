@@ -64,7 +64,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "500"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -340,6 +340,7 @@ def run_ours(args):
     }
     for k in kernels.values():
         k["frac_of_peak"] = k["GBps"] / peak
+    kernels["phase_ms_per_step"] = {k: phase[k] / args.steps for k in ("ms_residual", "ms_jacobian", "ms_ksp")}
 
     cpu = None
     if args.gpus == 1 and not args.no_cpu:

@@ -1,0 +1,171 @@
+/* Device-side building blocks shared by the Vec/Mat/CG translation units of libohp.so:
+ * deterministic two-stage reductions, NVLink peer-to-peer flag / mailbox primitives, mbarrier +
+ * bulk-async-copy (TMA) wrappers and the row dot product of the SpMV kernels. */
+#ifndef OHP_DEV_CUH
+#define OHP_DEV_CUH
+
+#include "ohp_internal.h"
+
+/* ------------------------------------------------------------------------------------ */
+/* block reduction + last-block ticket                                                   */
+/* ------------------------------------------------------------------------------------ */
+template <int NV> __device__ __forceinline__ void block_sum(double (&v)[NV], double *s_red /* NV*32 */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if (lane == 0) s_red[k * 32 + wid] = v[k];
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double t = lane < nw ? s_red[k * 32 + lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      v[k] = t;
+    }
+  }
+  __syncthreads();
+}
+
+/* returns true in every thread of the last block to arrive, with the grid totals in v
+ * (valid in thread 0).  Summation order is fixed => bitwise reproducible. */
+template <int NV>
+__device__ __forceinline__ bool grid_sum(double (&v)[NV], double *partials, unsigned *ticket) {
+  __shared__ double s_red[NV * 32];
+  __shared__ bool s_last;
+  block_sum<NV>(v, s_red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) partials[(size_t)blockIdx.x * NV + k] = v[k];
+    __threadfence();
+    const unsigned t = atomicInc(ticket, gridDim.x - 1); /* wraps back to 0: self-resetting */
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = 0.0;
+  for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] += __ldcg(partials + (size_t)b * NV + k);
+  }
+  block_sum<NV>(v, s_red);
+  return true;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* NVLink peer-to-peer all-reduce, fused into the kernel that produces the partial sums.   */
+/* Called by every thread of the LAST block (grid_sum returned true); warp 0 does the work: */
+/* lane q stores this rank's totals into rank q's mailbox (release store of the sequence    */
+/* number after the payload), then spins (acquire) on the mailbox rank q fills here; the    */
+/* totals are added in rank order, so every rank gets bitwise the same sum.  Mailboxes are  */
+/* double-buffered by sequence parity: a rank can be at most one all-reduce ahead.          */
+/* ------------------------------------------------------------------------------------ */
+enum { OHP_MODE_SERIAL = 0, OHP_MODE_NCCL = 1, OHP_MODE_P2P = 2 };
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+/* spin until *flag >= seq; a peer that died must not hang this GPU: after 4 s raise seq[2] and go on */
+__device__ __forceinline__ void p2p_wait(const unsigned long long *flag, unsigned long long seq, unsigned long long *err) {
+  if (ld_acquire_sys(flag) >= seq) return;
+  const unsigned long long t0 = global_ns();
+  while (ld_acquire_sys(flag) < seq) {
+    if (global_ns() - t0 > 4000000000ull) { *err = 1ull; return; }
+  }
+}
+
+template <int NV> __device__ __forceinline__ void p2p_allreduce(const ohp_p2p_dev &pd, double (&v)[NV]) {
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  unsigned long long seq = 0;
+  if (lane == 0) { seq = pd.seq[0] + 1; pd.seq[0] = seq; }
+  seq = __shfl_sync(0xffffffffu, seq, 0);
+  double mine[NV], got[NV], tot[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) { mine[k] = __shfl_sync(0xffffffffu, v[k], 0); got[k] = mine[k]; tot[k] = 0.0; }
+  const int par = (int)(seq & 1ull);
+  const bool peer = lane < pd.nranks && lane != pd.rank;
+  if (peer) {
+    ohp_ar_slot *s = pd.slots[lane] + par * kMaxRanks + pd.rank;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) s->v[k] = mine[k];
+    st_release_sys(&s->seq, seq);
+    const ohp_ar_slot *r = pd.slots[pd.rank] + par * kMaxRanks + lane;
+    p2p_wait(&r->seq, seq, pd.seq + 2);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) got[k] = r->v[k];
+  }
+  for (int q = 0; q < pd.nranks; ++q) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) tot[k] += __shfl_sync(0xffffffffu, got[k], q);
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = tot[k];
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+/* sum_{k in [a,b)} vs[k] * x[cs[k]], ascending k; loads batched 8 at a time for memory-level parallelism */
+__device__ __forceinline__ double row_dot(const double *__restrict__ vs, const int32_t *__restrict__ cs,
+                                          int a, int b, const double *__restrict__ x, double s) {
+  for (int k = a; k < b; k += 8) {
+    double xv[8], vv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool ok = (k + j) < b;
+      const int c = ok ? cs[k + j] : 0;
+      vv[j] = ok ? vs[k + j] : 0.0;
+      xv[j] = ok ? __ldg(x + c) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if ((k + j) < b) s += vv[j] * xv[j];
+  }
+  return s;
+}
+
+constexpr int kTmaRpStride = kSpmvRowCap + 4;           /* rowptr slice + (first row, end row) of the tile */
+constexpr int tma_smem_bytes(int stages) { return stages * (kSpmvTile * 12 + kTmaRpStride * 4) + 2 * stages * 8; }
+
+#endif

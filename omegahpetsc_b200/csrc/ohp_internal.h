@@ -54,7 +54,7 @@ struct ohp_halo;  /* ohp_comm.cu */
 
 /* ---- peer-to-peer (NVLink) view of the communicator, passed BY VALUE to the CG kernels ---- */
 constexpr int kMaxRanks = 8;
-struct ohp_ar_slot { double v[2]; unsigned long long seq; unsigned long long pad; }; /* 32 B */
+struct ohp_ar_slot { double v[3]; unsigned long long seq; }; /* 32 B: payload, then the sequence number (release-stored last) */
 struct ohp_p2p_dev {
   int rank, nranks;
   int n_nbr;                         /* halo neighbours */
@@ -146,7 +146,7 @@ struct ohp_mat_s {
   double *vals;
   /* CG work vectors, allocated on first solve; the search direction is double-buffered
    * (p[its & 1] is written from p[(its & 1) ^ 1]) so that a halo push never races its own update */
-  double *r, *z, *p, *p1, *w, *dinv;
+  double *r, *z, *p, *p1, *w, *dinv, *s;
   double *hist;
   int32_t hist_cap;
 };
@@ -168,6 +168,10 @@ void ohp_p2p_free(ohp_p2p *p);
 
 /* ohp_linalg.cu */
 int ohp_spmv_launch(ohp_mat A, const double *x, double *y);
+int ohp_extract_dinv(ohp_mat A);
+
+/* ohp_cg_persistent.cu */
+int ohp_cg_persistent_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o, ohp_ksp_result *res, bool p2p);
 
 /* ohp_problems.cu */
 int ohp_problem_lookup(int id, ohp_assembly_launcher *res, ohp_assembly_launcher *jac,

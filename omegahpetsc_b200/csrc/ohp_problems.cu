@@ -8,6 +8,8 @@
  * evaluators; SNESSolve (ex12.cpp:1609) runs newtonls + bt over KSP.
  */
 #include <math.h>
+#include <stdlib.h>
+#include <time.h>
 #include <string.h>
 
 #include <algorithm>
@@ -266,7 +268,12 @@ extern "C" int ohp_snes_solve(ohp_mesh m, int problem, ohp_mat J, ohp_vec u, con
   memset(res, 0, sizeof(*res));
   int rc = 0, its = 0, kits = 0, reason = 0;
   double fnorm = 0.0, fnorm0 = 0.0;
-#define SN_TRY(e) do { rc = (e); if (rc) goto done; } while (0)
+  /* OHP_TRACE=1: wall-clock per call (stream drained first), to find host-side gaps */
+  static const bool trace = getenv("OHP_TRACE") != nullptr;
+  auto now = []() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+  double t_last = now();
+#define SN_TRY(e) do { rc = (e); if (rc) goto done; if (trace) { cudaStreamSynchronize(ctx->stream); const double t__ = now(); \
+    fprintf(stderr, "[ohp trace r%d] %8.3f ms  %s\n", ctx->rank, t__ - t_last, #e); t_last = t__; } } while (0)
   tm.begin(0);
   SN_TRY(ohp_residual(m, problem, u, F));
   tm.end(0);

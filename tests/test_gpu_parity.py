@@ -356,3 +356,56 @@ def test_full_size_16M_triangles(ctx):
     Au.aypx(-1.0, F0)  # r = b - A x
     assert Au.norm() == pytest.approx(out["rnorm"], rel=1e-6)
     m.destroy()
+
+
+def test_persistent_cg_kernel_small_mesh(ctx, oracle_mod):
+    """The persistent single-reduction kernel (auto-selected below 400k rows) against the oracle on the
+    24k XGC mesh: same converged solution, iteration count within the rounding-order band, history."""
+    cells, coords = get_mesh("T24k")
+    bnd, gidx, N, rowptr, colidx = oracle_setup(oracle_mod, cells, coords)
+    m = ohp.Mesh(ctx, cells, coords).setup()
+    J = m.create_matrix()
+    u, b, x = (m.create_global_vector() for _ in range(3))
+    m.jacobian(0, u, J)
+    m.residual(0, u, b)
+    for pc in (0, 1):
+        out = ohp.ksp_cg(J, b, x, ohp.ksp_options(rtol=1e-9, max_it=20000, pc=pc, check_every=64), history=True)
+        ref = oracle_mod.cg(rowptr, colidx, J.values(), b.to_host(), rtol=1e-9, maxit=20000, pc=pc, history=True)
+        assert out["reason"] == 2 and abs(out["its"] - ref["its"]) <= ref["its"] // 40
+        assert np.allclose(out["hist"][:6], ref["hist"][:6], rtol=1e-9)
+        assert np.abs(x.to_host() - ref["x"]).max() <= 1e-7 * np.abs(ref["x"]).max()
+    out = ohp.ksp_cg(J, b, x, ohp.ksp_options(rtol=1e-9, max_it=41, check_every=7))
+    assert (out["its"], out["reason"]) == (41, -3)
+    m.destroy()
+
+
+def test_full_size_3d_8M_tets(ctx):
+    """BASELINE config 5 (110^3 x 6 Kuhn tets = 7 986 000 tets): closed-form counts, linearity, symmetry,
+    and the manufactured solution u = 2/3 r^2 reproduced at the nodes after the Newton solve."""
+    n = 110
+    from omegahpetsc_b200 import meshgen
+    cells, coords = meshgen.box3d(n, n, n)
+    m = ohp.Mesh(ctx, cells, coords).setup()
+    info = m.info()
+    N = (n - 1) ** 3
+    assert (info.n_cells, info.n_verts, info.n_owned) == (7986000, 1367631, N)
+    assert info.n_boundary_verts == (n + 1) ** 3 - N and info.max_row == 15
+    J = m.create_matrix()
+    u, F0, Fu, Au, y = (m.create_global_vector() for _ in range(5))
+    rng = np.random.default_rng(4)
+    m.residual(0, u.set(0.0), F0)
+    m.jacobian(0, u, J)
+    u.from_host(rng.standard_normal(N))
+    y.from_host(rng.standard_normal(N))
+    m.residual(0, u, Fu)
+    J.mult(u, Au)
+    yAu = y.dot(Au)
+    Au.axpy(1.0, F0).axpy(-1.0, Fu)
+    assert Au.norm() <= 1e-11 * Fu.norm()
+    J.mult(y, Au)
+    assert u.dot(Au) == pytest.approx(yAu, rel=1e-10)
+    res = m.snes_solve(0, J, u.set(0.0), ksp=ohp.ksp_options(rtol=1e-10, max_it=100000))
+    assert res["reason"] == 3 and res["its"] == 1
+    exact = m.project(0, 1, m.create_global_vector()).to_host()
+    assert np.abs(u.to_host() - exact).max() < 1e-7
+    m.destroy()
