@@ -601,7 +601,7 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
     static const char *force_comm = getenv("OHP_COMM");
     const bool can_p2p = ctx->nranks > 1 && m->p2p && m->p2p->attached && !(force_comm && force_comm[0] == 'n');
     const bool feasible = spmv_use_tma(m) && n > 0 && (ctx->nranks == 1 || can_p2p);
-    bool persistent = feasible && (can_p2p || n < kPersistentBelowRows);
+    bool persistent = feasible && ctx->nranks == 1 && n < kPersistentBelowRows; /* measured: see DESIGN.md section 5 */
     if (force && force[0] == 'c') persistent = false;
     if (force && force[0] == 'p') persistent = feasible;
     if (persistent) return ohp_cg_persistent_solve(A, b, x, o, res, can_p2p);
