@@ -69,6 +69,13 @@ class ClockSampler:
         except OSError:
             self.p = None
 
+    def mark(self):
+        """Start of the timed region: samples written before this point (warm-up) are ignored."""
+        try:
+            self.offset = os.path.getsize(self.f.name)
+        except OSError:
+            self.offset = 0
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
@@ -79,7 +86,7 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.p.kill()
         self.f.flush()
-        self.f.seek(0)
+        self.f.seek(getattr(self, "offset", 0))
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().splitlines():
@@ -267,10 +274,14 @@ def run_ours(args):
         return mesh.snes_solve(0, J, u, ksp=ksp)
 
     res = None
+    # the sampler starts BEFORE the warm-up: the first nvidia-smi query on a fresh box stalls the driver for
+    # seconds, which must not land inside the timed region; only samples taken after mark() are reported
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
         res = step()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.mark()
     l0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)

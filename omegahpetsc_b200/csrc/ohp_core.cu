@@ -223,7 +223,7 @@ extern "C" int ohp_mesh_create(ohp_context ctx, int dim, int32_t nC, int32_t nV,
   m->ctx = ctx; m->dim = dim; m->nc = nc; m->nC = nC; m->nV = nV;
   m->cells = nullptr; m->coords = nullptr; m->owned = nullptr; m->setup_done = false;
   m->v2c_ptr = m->v2c = nullptr; m->bnd = nullptr; m->lidx = m->row_vertex = nullptr; m->ldof_gid = nullptr;
-  m->rowptr = m->colidx = nullptr; m->slot = nullptr; m->tile_row = nullptr; m->halo = nullptr; m->p2p = nullptr;
+  m->rowptr = m->colidx = nullptr; m->col16 = nullptr; m->slot = nullptr; m->tile_row = nullptr; m->halo = nullptr; m->p2p = nullptr;
   m->n_owned = m->n_ghost = m->n_bnd = 0; m->n_global = m->row_start = m->nnz = 0; m->max_row = 0; m->n_tiles = 0; m->max_tile_rows = 0;
   OHP_CUDA(cudaMalloc(&m->cells, sizeof(int32_t) * std::max<int64_t>(1, (int64_t)nC * nc)));
   OHP_CUDA(cudaMalloc(&m->coords, sizeof(double) * std::max<int64_t>(1, (int64_t)nV * dim)));
@@ -240,7 +240,7 @@ extern "C" int ohp_mesh_destroy(ohp_mesh m) {
   cudaStreamSynchronize(m->ctx->stream);
   cudaFree(m->cells); cudaFree(m->coords); cudaFree(m->owned); cudaFree(m->v2c_ptr); cudaFree(m->v2c);
   cudaFree(m->bnd); cudaFree(m->lidx); cudaFree(m->row_vertex); cudaFree(m->ldof_gid); cudaFree(m->rowptr);
-  cudaFree(m->colidx); cudaFree(m->slot); cudaFree(m->tile_row);
+  cudaFree(m->colidx); cudaFree(m->col16); cudaFree(m->slot); cudaFree(m->tile_row);
   ohp_halo_free(m->halo);
   ohp_p2p_free(m->p2p);
   delete m;
@@ -448,6 +448,19 @@ __global__ void k_slot_map(const int32_t *cells, const int32_t *ptr, const int32
   }
 }
 
+/* compressed column stream for the SpMV: offset of every column from its row, if all fit 16 bits */
+__global__ void k_col16(const int32_t *rowptr, const int32_t *colidx, int n_rows, int16_t *col16, int *overflow) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  bool bad = false;
+  for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+    const int d = colidx[k] - r;
+    bad |= (d < -32768 || d > 32767);
+    col16[k] = (int16_t)d;
+  }
+  if (bad) atomicExch(overflow, 1);
+}
+
 __global__ void k_max_rowlen(const int32_t *rowptr, int n_rows, int32_t *out) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   int len = r < n_rows ? rowptr[r + 1] - rowptr[r] : 0;
@@ -604,6 +617,21 @@ extern "C" int ohp_mesh_setup(ohp_mesh m) {
     OHP_CHECK_LAUNCH(ctx);
   }
   OHP_TRY(check_flag(ctx, "ohp_mesh_setup (pattern fill)"));
+
+  /* 16-bit column offsets (2 B/nnz less SpMV traffic) when the ordering keeps every row's columns within +-32767 */
+  if (N) {
+    OHP_CUDA(cudaMalloc(&m->col16, sizeof(int16_t) * ohp_padded_nnz(m->nnz)));
+    OHP_CUDA(cudaMemsetAsync(m->col16, 0, sizeof(int16_t) * ohp_padded_nnz(m->nnz), st));
+    k_col16<<<nblk(N, BS), BS, 0, st>>>(m->rowptr, m->colidx, N, m->col16, ctx->d_flag); OHP_CHECK_LAUNCH(ctx);
+    int overflow = 0;
+    OHP_CUDA(cudaMemcpyAsync(&overflow, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    OHP_CUDA(cudaStreamSynchronize(st));
+    if (overflow) {
+      OHP_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), st));
+      cudaFree(m->col16);
+      m->col16 = nullptr;
+    }
+  }
 
   /* longest row + SpMV tiles */
   int32_t *d_max;

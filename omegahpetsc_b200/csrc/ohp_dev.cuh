@@ -147,14 +147,17 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
 }
 
 /* sum_{k in [a,b)} vs[k] * x[cs[k]], ascending k; loads batched 8 at a time for memory-level parallelism */
-__device__ __forceinline__ double row_dot(const double *__restrict__ vs, const int32_t *__restrict__ cs,
-                                          int a, int b, const double *__restrict__ x, double s) {
+/* IDX = int32_t: absolute local column ids.  IDX = int16_t: column = row + delta (the compressed
+ * index stream used when every |column - row| fits 16 bits, which mesh-ordered matrices do). */
+template <class IDX>
+__device__ __forceinline__ double row_dot(const double *__restrict__ vs, const IDX *__restrict__ cs,
+                                          int a, int b, const double *__restrict__ x, double s, int row) {
   for (int k = a; k < b; k += 8) {
     double xv[8], vv[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const bool ok = (k + j) < b;
-      const int c = ok ? cs[k + j] : 0;
+      const int c = ok ? (sizeof(IDX) == 2 ? row + (int)cs[k + j] : (int)cs[k + j]) : 0;
       vv[j] = ok ? vs[k + j] : 0.0;
       xv[j] = ok ? __ldg(x + c) : 0.0;
     }
@@ -166,6 +169,6 @@ __device__ __forceinline__ double row_dot(const double *__restrict__ vs, const i
 }
 
 constexpr int kTmaRpStride = kSpmvRowCap + 4;           /* rowptr slice + (first row, end row) of the tile */
-constexpr int tma_smem_bytes(int stages) { return stages * (kSpmvTile * 12 + kTmaRpStride * 4) + 2 * stages * 8; }
+constexpr int tma_smem_bytes(int stages, int idx_bytes = 4) { return stages * (kSpmvTile * (8 + idx_bytes) + kTmaRpStride * 4) + 2 * stages * 8; }
 
 #endif

@@ -124,6 +124,7 @@ struct ohp_mesh_s {
   int64_t n_global, row_start;
   /* CSR */
   int32_t *rowptr, *colidx;
+  int16_t *col16;       /* column - row per entry, or NULL when some offset does not fit 16 bits */
   uint8_t *slot;
   int64_t nnz;
   int32_t max_row;

@@ -128,9 +128,9 @@ k_spmv_stream(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ co
 /* A row that straddles a tile boundary is carried in a register by the thread that       */
 /* started it (same thread finishes it in the next tile), so the order stays serial.      */
 /* ------------------------------------------------------------------------------------ */
-template <bool CG, int kTmaStages, int kTmaConsumers>
+template <bool CG, int kTmaStages, int kTmaConsumers, class IDX>
 __global__ void __launch_bounds__(kTmaConsumers + 32, 1)
-k_spmv_tma(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, const double *__restrict__ vals,
+k_spmv_tma(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colidx, const double *__restrict__ vals,
            const double *__restrict__ x, double *__restrict__ y, const int32_t *__restrict__ tile_row, int n_tiles,
            ohp_cg_state *st, double *partials, unsigned *ticket, double *sums, int mode,
            const double *__restrict__ x_alt, const ohp_p2p_dev pd) {
@@ -139,8 +139,8 @@ k_spmv_tma(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colid
   if (CG && st->done) return;
   if (CG && (st->its & 1)) x = x_alt;
   double *vals_s = reinterpret_cast<double *>(smem_raw);
-  int32_t *cols_s = reinterpret_cast<int32_t *>(vals_s + S * T);
-  int32_t *rp_s = cols_s + S * T;
+  IDX *cols_s = reinterpret_cast<IDX *>(vals_s + S * T);
+  int32_t *rp_s = reinterpret_cast<int32_t *>(cols_s + S * T);
   uint64_t *bars = reinterpret_cast<uint64_t *>(rp_s + S * kTmaRpStride);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -160,9 +160,9 @@ k_spmv_tma(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colid
       mbar_wait(empty0 + 8 * s, ((i / S) & 1) ^ 1);
       const int rs = __ldg(tile_row + t), re = __ldg(tile_row + t + 1);
       if (lane == 0) {
-        mbar_expect_tx(full0 + 8 * s, T * 12);
+        mbar_expect_tx(full0 + 8 * s, T * (8 + (int)sizeof(IDX)));
         tma_load_1d(smem_u32(vals_s + s * T), vals + (size_t)t * T, T * 8, full0 + 8 * s);
-        tma_load_1d(smem_u32(cols_s + s * T), colidx + (size_t)t * T, T * 4, full0 + 8 * s);
+        tma_load_1d(smem_u32(cols_s + s * T), colidx + (size_t)t * T, T * (int)sizeof(IDX), full0 + 8 * s);
       }
       int32_t *rp = rp_s + s * kTmaRpStride;
       for (int j = lane; j <= re - rs; j += 32) cp_async4(smem_u32(rp + j), rowptr + rs + j);
@@ -178,17 +178,17 @@ k_spmv_tma(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colid
       mbar_wait(full0 + 8 * s, (i / S) & 1);
       const int32_t *rp = rp_s + s * kTmaRpStride;
       const double *vs = vals_s + s * T;
-      const int32_t *cs = cols_s + s * T;
+      const IDX *cs = cols_s + s * T;
       const int rs = rp[kSpmvRowCap + 2], re = rp[kSpmvRowCap + 3];
       const int base = t * T, lim = base + T;
       if (pend >= 0) { /* finish (or continue) the row this thread carried over the tile boundary */
         const int end = rp[0];
-        carry = row_dot(vs, cs, 0, min(end, lim) - base, x, carry);
+        carry = row_dot<IDX>(vs, cs, 0, min(end, lim) - base, x, carry, pend);
         if (end <= lim) { y[pend] = carry; if (CG) dot[0] += carry * __ldg(x + pend); pend = -1; }
       }
       for (int r = rs + tid; r < re; r += NC) {
         const int a = rp[r - rs], b = rp[r - rs + 1];
-        const double sum = row_dot(vs, cs, a - base, min(b, lim) - base, x, 0.0);
+        const double sum = row_dot<IDX>(vs, cs, a - base, min(b, lim) - base, x, 0.0, r);
         if (b > lim) { carry = sum; pend = r; }
         else { y[r] = sum; if (CG) dot[0] += sum * __ldg(x + r); }
       }
@@ -197,7 +197,7 @@ k_spmv_tma(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colid
     }
     if (pend >= 0) { /* the row runs past this CTA's last tile: finish it straight from HBM */
       const int end = __ldg(rowptr + pend + 1);
-      for (int k = t1 * T; k < end; ++k) carry += vals[k] * __ldg(x + colidx[k]);
+      for (int k = t1 * T; k < end; ++k) carry += vals[k] * __ldg(x + (sizeof(IDX) == 2 ? pend + (int)colidx[k] : (int)colidx[k]));
       y[pend] = carry;
       if (CG) dot[0] += carry * __ldg(x + pend);
     }
@@ -230,24 +230,33 @@ static int spmv_configure(ohp_mesh m) {
   return 0;
 }
 
+template <int S, int NC, class IDX>
+static int spmv_tma_launch_t(ohp_mat A, const IDX *cols, const double *x, double *y, ohp_cg_state *st, double *sums, int mode,
+                             const double *x_alt, const ohp_p2p_dev &pd) {
+  ohp_mesh m = A->mesh;
+  ohp_context ctx = m->ctx;
+  constexpr int smem = tma_smem_bytes(S, (int)sizeof(IDX));
+  static bool configured = false;
+  if (!configured) {
+    OHP_CUDA(cudaFuncSetAttribute(k_spmv_tma<true, S, NC, IDX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    OHP_CUDA(cudaFuncSetAttribute(k_spmv_tma<false, S, NC, IDX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int grid = std::max(1, std::min(m->n_tiles, ctx->num_sms));
+  if (st) k_spmv_tma<true, S, NC, IDX><<<grid, NC + 32, smem, ctx->stream>>>(
+      m->rowptr, cols, A->vals, x, y, m->tile_row, m->n_tiles, st, ctx->d_partials, ctx->d_ticket + 1, sums, mode, x_alt, pd);
+  else k_spmv_tma<false, S, NC, IDX><<<grid, NC + 32, smem, ctx->stream>>>(
+      m->rowptr, cols, A->vals, x, y, m->tile_row, m->n_tiles, nullptr, nullptr, nullptr, nullptr, 0, nullptr, pd);
+  OHP_CHECK_LAUNCH(ctx);
+  return 0;
+}
 template <int S, int NC>
 static int spmv_tma_launch(ohp_mat A, const double *x, double *y, ohp_cg_state *st, double *sums, int mode,
                            const double *x_alt, const ohp_p2p_dev &pd) {
   ohp_mesh m = A->mesh;
-  ohp_context ctx = m->ctx;
-  static bool configured = false;
-  if (!configured) {
-    OHP_CUDA(cudaFuncSetAttribute(k_spmv_tma<true, S, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_smem_bytes(S)));
-    OHP_CUDA(cudaFuncSetAttribute(k_spmv_tma<false, S, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_smem_bytes(S)));
-    configured = true;
-  }
-  const int grid = std::max(1, std::min(m->n_tiles, ctx->num_sms));
-  if (st) k_spmv_tma<true, S, NC><<<grid, NC + 32, tma_smem_bytes(S), ctx->stream>>>(
-      m->rowptr, m->colidx, A->vals, x, y, m->tile_row, m->n_tiles, st, ctx->d_partials, ctx->d_ticket + 1, sums, mode, x_alt, pd);
-  else k_spmv_tma<false, S, NC><<<grid, NC + 32, tma_smem_bytes(S), ctx->stream>>>(
-      m->rowptr, m->colidx, A->vals, x, y, m->tile_row, m->n_tiles, nullptr, nullptr, nullptr, nullptr, 0, nullptr, pd);
-  OHP_CHECK_LAUNCH(ctx);
-  return 0;
+  static const char *idx = getenv("OHP_IDX"); /* "32" keeps absolute 32-bit column ids (A/B runs) */
+  if (m->col16 && !(idx && idx[0] == '3')) return spmv_tma_launch_t<S, NC, int16_t>(A, m->col16, x, y, st, sums, mode, x_alt, pd);
+  return spmv_tma_launch_t<S, NC, int32_t>(A, m->colidx, x, y, st, sums, mode, x_alt, pd);
 }
 
 /* y = A x on the context stream; with `st` the (x, y) dot and the CG scalar update are fused in */
