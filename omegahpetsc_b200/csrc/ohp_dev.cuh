@@ -6,6 +6,25 @@
 
 #include "ohp_internal.h"
 
+/* Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization
+ * attribute may start while its predecessor drains; pdl_wait() blocks until the predecessor has
+ * completed and its writes are visible, pdl_launch() lets the successor's CTAs be scheduled.
+ * Both are no-ops for a kernel launched without the attribute. */
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t ohp_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* block reduction + last-block ticket                                                   */
 /* ------------------------------------------------------------------------------------ */

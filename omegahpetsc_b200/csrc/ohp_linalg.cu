@@ -136,6 +136,8 @@ k_spmv_tma(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colidx, c
            const double *__restrict__ x_alt, const ohp_p2p_dev pd) {
   constexpr int T = kSpmvTile, S = kTmaStages, NC = kTmaConsumers;
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  pdl_wait();
+  pdl_launch();
   if (CG && st->done) return;
   if (CG && (st->its & 1)) x = x_alt;
   double *vals_s = reinterpret_cast<double *>(smem_raw);
@@ -243,8 +245,11 @@ static int spmv_tma_launch_t(ohp_mat A, const IDX *cols, const double *x, double
     configured = true;
   }
   const int grid = std::max(1, std::min(m->n_tiles, ctx->num_sms));
-  if (st) k_spmv_tma<true, S, NC, IDX><<<grid, NC + 32, smem, ctx->stream>>>(
-      m->rowptr, cols, A->vals, x, y, m->tile_row, m->n_tiles, st, ctx->d_partials, ctx->d_ticket + 1, sums, mode, x_alt, pd);
+  if (st) {
+    static const char *nopdl = getenv("OHP_NOPDL");
+    OHP_CUDA(ohp_launch(k_spmv_tma<true, S, NC, IDX>, dim3(grid), dim3(NC + 32), (size_t)smem, ctx->stream, mode != OHP_MODE_NCCL && !nopdl,
+                        m->rowptr, cols, A->vals, x, y, m->tile_row, m->n_tiles, st, ctx->d_partials, ctx->d_ticket + 1, sums, mode, x_alt, pd));
+  }
   else k_spmv_tma<false, S, NC, IDX><<<grid, NC + 32, smem, ctx->stream>>>(
       m->rowptr, cols, A->vals, x, y, m->tile_row, m->n_tiles, nullptr, nullptr, nullptr, nullptr, 0, nullptr, pd);
   OHP_CHECK_LAUNCH(ctx);
@@ -486,6 +491,8 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
 k_cg_pupdate(double *__restrict__ p0, double *__restrict__ p1, const double *__restrict__ z, double *__restrict__ x,
              int n, const ohp_cg_state *st, const ohp_p2p_dev pd, int n_halo_blocks, unsigned *halo_ticket) {
+  pdl_wait();
+  pdl_launch();
   if (st->done) return;
   const int its = st->its;
   const bool first = (its == 0);
@@ -550,6 +557,8 @@ k_cg_update(double *__restrict__ r, double *__restrict__ z, const double *__rest
             const double *__restrict__ dinv, int n, ohp_cg_state *st,
             double *partials, unsigned *ticket, double *sums, double *hist, int hist_cap, int mode,
             const ohp_p2p_dev pd) {
+  pdl_wait();
+  pdl_launch();
   if (st->done) return;
   const double a = st->alpha;
   double s[2] = {0.0, 0.0};
@@ -656,6 +665,8 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
   *ctx->h_cg = init;
   OHP_CUDA(cudaMemcpyAsync(ctx->d_cg, ctx->h_cg, sizeof(init), cudaMemcpyHostToDevice, st));
   const bool nccl = (mode == OHP_MODE_NCCL);
+  static const char *nopdl = getenv("OHP_NOPDL"); /* A/B switch for programmatic dependent launch */
+  const bool pdl = !nccl && !nopdl;
   const int nhalo = p2p ? std::max(1, std::min(16, (pd.soff[pd.n_nbr] + 255) / 256)) : 0;
   const int vgrid = vec_grid(ctx, n);
   double *sums = ctx->d_scalars;
@@ -682,8 +693,8 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
     if (ctx->h_cg->done) break;
     if (launched > o->max_it + check_every) OHP_FAIL(OHP_ERR_LIB, "ohp_ksp_cg: device-side iteration control did not terminate");
     for (int it = 0; it < check_every; ++it) {
-      if (p2p) k_cg_pupdate<OHP_MODE_P2P><<<vgrid + nhalo, 256, 0, st>>>(P0, P1, z, x->d, n, ctx->d_cg, pd, nhalo, ctx->d_ticket + 2);
-      else k_cg_pupdate<OHP_MODE_SERIAL><<<vgrid, 256, 0, st>>>(P0, P1, z, x->d, n, ctx->d_cg, pd, 0, nullptr);
+      if (p2p) OHP_CUDA(ohp_launch(k_cg_pupdate<OHP_MODE_P2P>, dim3(vgrid + nhalo), dim3(256), 0, st, pdl, P0, P1, z, x->d, n, ctx->d_cg, pd, nhalo, ctx->d_ticket + 2));
+      else OHP_CUDA(ohp_launch(k_cg_pupdate<OHP_MODE_SERIAL>, dim3(vgrid), dim3(256), 0, st, pdl, P0, P1, z, x->d, n, ctx->d_cg, pd, 0, (unsigned *)nullptr));
       OHP_CHECK_LAUNCH(ctx);
       if (nccl) {
         /* the host does not know the iteration parity on the device: exchange both buffers' tails is
@@ -698,8 +709,8 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
         OHP_TRY(ohp_allreduce_sum(ctx, sums, 1));
         k_cg_fin<<<1, 1, 0, st>>>(ctx->d_cg, sums, 1, hist, hist_cap); OHP_CHECK_LAUNCH(ctx);
       }
-      if (jac) k_cg_update<true><<<vgrid, 256, 0, st>>>(A->r, z, A->w, A->dinv, n, ctx->d_cg, ctx->d_partials, ctx->d_ticket, sums, hist, hist_cap, mode, pd);
-      else k_cg_update<false><<<vgrid, 256, 0, st>>>(A->r, z, A->w, A->dinv, n, ctx->d_cg, ctx->d_partials, ctx->d_ticket, sums, hist, hist_cap, mode, pd);
+      if (jac) OHP_CUDA(ohp_launch(k_cg_update<true>, dim3(vgrid), dim3(256), 0, st, pdl, A->r, z, A->w, A->dinv, n, ctx->d_cg, ctx->d_partials, ctx->d_ticket, sums, hist, hist_cap, mode, pd));
+      else OHP_CUDA(ohp_launch(k_cg_update<false>, dim3(vgrid), dim3(256), 0, st, pdl, A->r, z, A->w, A->dinv, n, ctx->d_cg, ctx->d_partials, ctx->d_ticket, sums, hist, hist_cap, mode, pd));
       OHP_CHECK_LAUNCH(ctx);
       if (nccl) {
         OHP_TRY(ohp_allreduce_sum(ctx, sums, 2));
