@@ -130,43 +130,6 @@ __device__ __forceinline__ double row_dot_weak(const double *vs, const int32_t *
   return s;
 }
 
-__device__ void pcg_scalars(const PcgArgs &a, double g, double d, double nn) {
-  ohp_cg_state *st = a.st;
-  const double dp = sqrt(nn);
-  st->dp = dp;
-  int reason = 0;
-  if (st->x_pending == 0) { /* first pass: r0, u0, w0 are known (x_pending doubles as the phase flag here) */
-    st->x_pending = 1;
-    st->its = 0;
-    st->rnorm0 = dp;
-    st->ttol = fmax(st->rtol * dp, st->abstol);
-    if (a.hist) a.hist[0] = dp;
-    if (dp != dp) reason = -9;
-    else if (dp <= st->ttol) reason = (dp < st->abstol) ? 3 : 2;
-    if (!reason && st->maxit <= 0) reason = -3;
-    if (!reason && g == 0.0) reason = 3;
-    if (!reason) {
-      if (!(d > 0.0)) reason = (d != d) ? -9 : -8;
-      else { st->alpha = g / d; st->beta = 0.0; st->betaold = g; }
-    }
-  } else {
-    st->its += 1;
-    if (a.hist && st->its < a.hist_cap) a.hist[st->its] = dp;
-    if (dp != dp) reason = -9;
-    else if (dp <= st->ttol) reason = (dp < st->abstol) ? 3 : 2;
-    else if (dp >= st->dtol * st->rnorm0) reason = -4;
-    if (!reason && st->its >= st->maxit) reason = -3;
-    if (!reason && g == 0.0) reason = 3;
-    if (!reason) {
-      const double beta = g / st->betaold; /* betaold holds gamma of the previous iteration */
-      const double denom = d - beta * g / st->alpha;
-      if (!(denom > 0.0)) reason = (denom != denom) ? -9 : -8;
-      else { st->beta = beta; st->alpha = g / denom; st->betaold = g; }
-    }
-  }
-  if (reason) { st->reason = reason; st->done = 1; }
-}
-
 __global__ void __launch_bounds__(PNC + 32, 1) k_cg_persistent(const PcgArgs a) {
   constexpr int T = kSpmvTile, S = PS, NC = PNC;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -346,7 +309,7 @@ __global__ void __launch_bounds__(PNC + 32, 1) k_cg_persistent(const PcgArgs a) 
       }
       cons_block_sum<3>(tot, s_red);
       if (a.mode == OHP_MODE_P2P) p2p_allreduce<3>(a.pd, tot); /* warp 0; totals in thread 0 */
-      if (tid == 0) pcg_scalars(a, tot[0], tot[1], jac ? tot[2] : tot[0]);
+      if (tid == 0) cgcg_scalars(a.st, a.hist, a.hist_cap, tot[0], tot[1], jac ? tot[2] : tot[0]);
       gbar_release(a.sync + 1, bar_k);
     } else {
       gbar_wait(a.sync + 1, bar_k);

@@ -190,4 +190,51 @@ __device__ __forceinline__ double row_dot(const double *__restrict__ vs, const I
 constexpr int kTmaRpStride = kSpmvRowCap + 4;           /* rowptr slice + (first row, end row) of the tile */
 constexpr int tma_smem_bytes(int stages, int idx_bytes = 4) { return stages * (kSpmvTile * (8 + idx_bytes) + kTmaRpStride * 4) + 2 * stages * 8; }
 
+/* scalar recurrences of the single-reduction (Chronopoulos-Gear) CG: g = (r,u), d = (A u,u), nn = (u,u).
+ * st->x_pending == 0 marks the first pass (r0, u0, w0 just computed); betaold carries gamma. */
+__device__ __forceinline__ void cgcg_scalars(ohp_cg_state *st, double *hist, int hist_cap, double g, double d, double nn) {
+  const double dp = sqrt(nn);
+  st->dp = dp;
+  int reason = 0;
+  if (st->x_pending == 0) { /* first pass: r0, u0, w0 are known (x_pending doubles as the phase flag here) */
+    st->x_pending = 1;
+    st->its = 0;
+    st->rnorm0 = dp;
+    st->ttol = fmax(st->rtol * dp, st->abstol);
+    if (hist) hist[0] = dp;
+    if (dp != dp) reason = -9;
+    else if (dp <= st->ttol) reason = (dp < st->abstol) ? 3 : 2;
+    if (!reason && st->maxit <= 0) reason = -3;
+    if (!reason && g == 0.0) reason = 3;
+    if (!reason) {
+      if (!(d > 0.0)) reason = (d != d) ? -9 : -8;
+      else { st->alpha = g / d; st->beta = 0.0; st->betaold = g; }
+    }
+  } else {
+    st->its += 1;
+    if (hist && st->its < hist_cap) hist[st->its] = dp;
+    if (dp != dp) reason = -9;
+    else if (dp <= st->ttol) reason = (dp < st->abstol) ? 3 : 2;
+    else if (dp >= st->dtol * st->rnorm0) reason = -4;
+    if (!reason && st->its >= st->maxit) reason = -3;
+    if (!reason && g == 0.0) reason = 3;
+    if (!reason) {
+      const double beta = g / st->betaold; /* betaold holds gamma of the previous iteration */
+      const double denom = d - beta * g / st->alpha;
+      if (!(denom > 0.0)) reason = (denom != denom) ? -9 : -8;
+      else { st->beta = beta; st->alpha = g / denom; st->betaold = g; }
+    }
+  }
+  if (reason) { st->reason = reason; st->done = 1; }
+}
+
+
+/* extra inputs of the SpMV epilogue when it closes a single-reduction CG iteration: the partial sums
+ * (r,u), (u,u) left by the vector kernel's blocks, summed here in a fixed order */
+struct ohp_cgcg_epi {
+  const double *vpart; /* nvpart x 2, NULL = classic recurrence */
+  int nvpart, jacobi, hist_cap;
+  double *hist;
+};
+
 #endif

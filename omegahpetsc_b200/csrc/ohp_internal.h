@@ -148,6 +148,7 @@ struct ohp_mat_s {
   /* CG work vectors, allocated on first solve; the search direction is double-buffered
    * (p[its & 1] is written from p[(its & 1) ^ 1]) so that a halo push never races its own update */
   double *r, *z, *p, *p1, *w, *dinv, *s;
+  double *r1, *z1, *s1; /* second buffers of the single-reduction recurrence (r, u, s are double-buffered there) */
   double *hist;
   int32_t hist_cap;
 };

@@ -74,6 +74,34 @@ __global__ void k_cg_fin(ohp_cg_state *st, const double *sums, int which, double
   else cg_fin_update(st, sums[0], sums[1], hist, hist_cap);
 }
 
+/* which buffer the CG SpMV multiplies: classic recurrence -> P[its & 1]; single-reduction recurrence ->
+ * U[0] on the first pass, then the buffer the vector kernel of this iteration wrote, U[(its + 1) & 1] */
+__device__ __forceinline__ const double *cg_pick_input(const ohp_cg_state *st, const ohp_cgcg_epi &epi, const double *x0,
+                                                       const double *x1) {
+  if (epi.vpart) return (st->x_pending != 0 && ((st->its + 1) & 1)) ? x1 : x0;
+  return (st->its & 1) ? x1 : x0;
+}
+
+/* run by every thread of the LAST block of a CG SpMV (dot[0] = (x, A x) valid in thread 0) */
+__device__ __forceinline__ void cg_spmv_epilogue(ohp_cg_state *st, double (&dot)[1], double *sums, int mode,
+                                                 const ohp_p2p_dev &pd, const ohp_cgcg_epi &epi) {
+  if (!epi.vpart) { /* classic: (p, Ap) -> alpha */
+    if (mode == OHP_MODE_P2P) p2p_allreduce<1>(pd, dot);
+    if (threadIdx.x == 0) {
+      sums[0] = dot[0];
+      if (mode != OHP_MODE_NCCL) cg_fin_spmv(st, dot[0]);
+    }
+    return;
+  }
+  /* single reduction: add the vector kernel's per-block partials of (r,u), (u,u) in a fixed order */
+  __shared__ double s_red3[3 * 32];
+  double tot[3] = {0.0, threadIdx.x == 0 ? dot[0] : 0.0, 0.0};
+  for (int b = threadIdx.x; b < epi.nvpart; b += blockDim.x) { tot[0] += __ldcg(epi.vpart + 2 * b); tot[2] += __ldcg(epi.vpart + 2 * b + 1); }
+  block_sum<3>(tot, s_red3);
+  if (mode == OHP_MODE_P2P) p2p_allreduce<3>(pd, tot);
+  if (threadIdx.x == 0) cgcg_scalars(st, epi.hist, epi.hist_cap, tot[0], tot[1], epi.jacobi ? tot[2] : tot[0]);
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* SpMV (CSR-stream) with optional fused (x, y) dot                                      */
 /* ------------------------------------------------------------------------------------ */
@@ -82,10 +110,11 @@ __global__ void __launch_bounds__(kSpmvThreads)
 k_spmv_stream(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
               const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
               const int32_t *__restrict__ tile_row, int n_tiles, ohp_cg_state *st, double *partials,
-              unsigned *ticket, double *sums, int mode, const double *__restrict__ x_alt, const ohp_p2p_dev pd) {
+              unsigned *ticket, double *sums, int mode, const double *__restrict__ x_alt, const ohp_p2p_dev pd,
+              const ohp_cgcg_epi epi) {
   extern __shared__ double s_prod[];
   if (CG && st->done) return;
-  if (CG && (st->its & 1)) x = x_alt; /* double-buffered search direction */
+  if (CG) x = cg_pick_input(st, epi, x, x_alt); /* double-buffered SpMV input */
   double dot[1] = {0.0};
   for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const int r0 = __ldg(tile_row + t), r1 = __ldg(tile_row + t + 1);
@@ -104,13 +133,7 @@ k_spmv_stream(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ co
     __syncthreads();
   }
   if (CG) {
-    if (grid_sum<1>(dot, partials, ticket)) {
-      if (mode == OHP_MODE_P2P) p2p_allreduce<1>(pd, dot);
-      if (threadIdx.x == 0) {
-        sums[0] = dot[0];
-        if (mode != OHP_MODE_NCCL) cg_fin_spmv(st, dot[0]);
-      }
-    }
+    if (grid_sum<1>(dot, partials, ticket)) cg_spmv_epilogue(st, dot, sums, mode, pd, epi);
   }
 }
 
@@ -133,13 +156,13 @@ __global__ void __launch_bounds__(kTmaConsumers + 32, 1)
 k_spmv_tma(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colidx, const double *__restrict__ vals,
            const double *__restrict__ x, double *__restrict__ y, const int32_t *__restrict__ tile_row, int n_tiles,
            ohp_cg_state *st, double *partials, unsigned *ticket, double *sums, int mode,
-           const double *__restrict__ x_alt, const ohp_p2p_dev pd) {
+           const double *__restrict__ x_alt, const ohp_p2p_dev pd, const ohp_cgcg_epi epi) {
   constexpr int T = kSpmvTile, S = kTmaStages, NC = kTmaConsumers;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   pdl_wait();
   pdl_launch();
   if (CG && st->done) return;
-  if (CG && (st->its & 1)) x = x_alt;
+  if (CG) x = cg_pick_input(st, epi, x, x_alt);
   double *vals_s = reinterpret_cast<double *>(smem_raw);
   IDX *cols_s = reinterpret_cast<IDX *>(vals_s + S * T);
   int32_t *rp_s = reinterpret_cast<int32_t *>(cols_s + S * T);
@@ -205,17 +228,12 @@ k_spmv_tma(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colidx, c
     }
   }
   if (CG) {
-    if (grid_sum<1>(dot, partials, ticket)) {
-      if (mode == OHP_MODE_P2P) p2p_allreduce<1>(pd, dot);
-      if (threadIdx.x == 0) {
-        sums[0] = dot[0];
-        if (mode != OHP_MODE_NCCL) cg_fin_spmv(st, dot[0]);
-      }
-    }
+    if (grid_sum<1>(dot, partials, ticket)) cg_spmv_epilogue(st, dot, sums, mode, pd, epi);
   }
 }
 
 constexpr int kPersistentBelowRows = 400000;
+constexpr int kSingleReductionBelowRows = 1600000;
 static bool spmv_use_tma(ohp_mesh m) { return m->max_tile_rows <= kSpmvRowCap - 1 && m->n_tiles > 0; }
 
 static int spmv_smem_bytes(ohp_mesh m) { return (int)sizeof(double) * (kSpmvTile + std::max(1, m->max_row)); }
@@ -234,7 +252,7 @@ static int spmv_configure(ohp_mesh m) {
 
 template <int S, int NC, class IDX>
 static int spmv_tma_launch_t(ohp_mat A, const IDX *cols, const double *x, double *y, ohp_cg_state *st, double *sums, int mode,
-                             const double *x_alt, const ohp_p2p_dev &pd) {
+                             const double *x_alt, const ohp_p2p_dev &pd, const ohp_cgcg_epi &epi) {
   ohp_mesh m = A->mesh;
   ohp_context ctx = m->ctx;
   constexpr int smem = tma_smem_bytes(S, (int)sizeof(IDX));
@@ -248,25 +266,25 @@ static int spmv_tma_launch_t(ohp_mat A, const IDX *cols, const double *x, double
   if (st) {
     static const char *nopdl = getenv("OHP_NOPDL");
     OHP_CUDA(ohp_launch(k_spmv_tma<true, S, NC, IDX>, dim3(grid), dim3(NC + 32), (size_t)smem, ctx->stream, mode != OHP_MODE_NCCL && !nopdl,
-                        m->rowptr, cols, A->vals, x, y, m->tile_row, m->n_tiles, st, ctx->d_partials, ctx->d_ticket + 1, sums, mode, x_alt, pd));
+                        m->rowptr, cols, A->vals, x, y, m->tile_row, m->n_tiles, st, ctx->d_partials, ctx->d_ticket + 1, sums, mode, x_alt, pd, epi));
   }
   else k_spmv_tma<false, S, NC, IDX><<<grid, NC + 32, smem, ctx->stream>>>(
-      m->rowptr, cols, A->vals, x, y, m->tile_row, m->n_tiles, nullptr, nullptr, nullptr, nullptr, 0, nullptr, pd);
+      m->rowptr, cols, A->vals, x, y, m->tile_row, m->n_tiles, nullptr, nullptr, nullptr, nullptr, 0, nullptr, pd, epi);
   OHP_CHECK_LAUNCH(ctx);
   return 0;
 }
 template <int S, int NC>
 static int spmv_tma_launch(ohp_mat A, const double *x, double *y, ohp_cg_state *st, double *sums, int mode,
-                           const double *x_alt, const ohp_p2p_dev &pd) {
+                           const double *x_alt, const ohp_p2p_dev &pd, const ohp_cgcg_epi &epi) {
   ohp_mesh m = A->mesh;
   static const char *idx = getenv("OHP_IDX"); /* "32" keeps absolute 32-bit column ids (A/B runs) */
-  if (m->col16 && !(idx && idx[0] == '3')) return spmv_tma_launch_t<S, NC, int16_t>(A, m->col16, x, y, st, sums, mode, x_alt, pd);
-  return spmv_tma_launch_t<S, NC, int32_t>(A, m->colidx, x, y, st, sums, mode, x_alt, pd);
+  if (m->col16 && !(idx && idx[0] == '3')) return spmv_tma_launch_t<S, NC, int16_t>(A, m->col16, x, y, st, sums, mode, x_alt, pd, epi);
+  return spmv_tma_launch_t<S, NC, int32_t>(A, m->colidx, x, y, st, sums, mode, x_alt, pd, epi);
 }
 
 /* y = A x on the context stream; with `st` the (x, y) dot and the CG scalar update are fused in */
 static int spmv_enqueue(ohp_mat A, const double *x, double *y, ohp_cg_state *st, double *sums, int mode,
-                        const double *x_alt, const ohp_p2p_dev &pd) {
+                        const double *x_alt, const ohp_p2p_dev &pd, const ohp_cgcg_epi &epi = ohp_cgcg_epi{}) {
   ohp_mesh m = A->mesh;
   ohp_context ctx = m->ctx;
   static const char *force = getenv("OHP_SPMV"); /* "stream" forces the fallback kernel; "0".."5" pick a TMA config (A/B runs) */
@@ -274,18 +292,18 @@ static int spmv_enqueue(ohp_mat A, const double *x, double *y, ohp_cg_state *st,
   if (tma) {
     const int cfg = (force && force[0] >= '0' && force[0] <= '9') ? force[0] - '0' : 0;
     switch (cfg) {
-      case 1: return spmv_tma_launch<3, 384>(A, x, y, st, sums, mode, x_alt, pd);
-      case 2: return spmv_tma_launch<3, 768>(A, x, y, st, sums, mode, x_alt, pd);
-      case 3: return spmv_tma_launch<2, 640>(A, x, y, st, sums, mode, x_alt, pd);
-      default: return spmv_tma_launch<3, 608>(A, x, y, st, sums, mode, x_alt, pd);
+      case 1: return spmv_tma_launch<3, 384>(A, x, y, st, sums, mode, x_alt, pd, epi);
+      case 2: return spmv_tma_launch<3, 768>(A, x, y, st, sums, mode, x_alt, pd, epi);
+      case 3: return spmv_tma_launch<2, 640>(A, x, y, st, sums, mode, x_alt, pd, epi);
+      default: return spmv_tma_launch<3, 608>(A, x, y, st, sums, mode, x_alt, pd, epi);
     }
   }
   OHP_TRY(spmv_configure(m));
   const int grid = std::max(1, std::min(m->n_tiles, kMaxPartials));
   if (st) k_spmv_stream<true><<<grid, kSpmvThreads, spmv_smem_bytes(m), ctx->stream>>>(
-      m->rowptr, m->colidx, A->vals, x, y, m->tile_row, m->n_tiles, st, ctx->d_partials, ctx->d_ticket + 1, sums, mode, x_alt, pd);
+      m->rowptr, m->colidx, A->vals, x, y, m->tile_row, m->n_tiles, st, ctx->d_partials, ctx->d_ticket + 1, sums, mode, x_alt, pd, epi);
   else k_spmv_stream<false><<<grid, kSpmvThreads, spmv_smem_bytes(m), ctx->stream>>>(
-      m->rowptr, m->colidx, A->vals, x, y, m->tile_row, m->n_tiles, nullptr, nullptr, nullptr, nullptr, 0, nullptr, pd);
+      m->rowptr, m->colidx, A->vals, x, y, m->tile_row, m->n_tiles, nullptr, nullptr, nullptr, nullptr, 0, nullptr, pd, epi);
   OHP_CHECK_LAUNCH(ctx);
   return 0;
 }
@@ -420,7 +438,7 @@ extern "C" int ohp_mat_create(ohp_mesh m, ohp_mat *out) {
   if (!m || !m->setup_done) OHP_FAIL(OHP_ERR_ORDER, "ohp_mat_create: mesh not set up");
   OHP_CUDA(cudaSetDevice(m->ctx->device));
   ohp_mat A = new ohp_mat_s();
-  A->mesh = m; A->r = A->z = A->p = A->p1 = A->w = A->dinv = A->hist = A->s = nullptr; A->hist_cap = 0;
+  A->mesh = m; A->r = A->z = A->p = A->p1 = A->w = A->dinv = A->hist = A->s = A->r1 = A->z1 = A->s1 = nullptr; A->hist_cap = 0;
   OHP_CUDA(cudaMalloc(&A->vals, sizeof(double) * ohp_padded_nnz(m->nnz)));
   OHP_CUDA(cudaMemsetAsync(A->vals, 0, sizeof(double) * ohp_padded_nnz(m->nnz), m->ctx->stream));
   *out = A;
@@ -430,7 +448,7 @@ extern "C" int ohp_mat_destroy(ohp_mat A) {
   if (!A) return 0;
   cudaSetDevice(A->mesh->ctx->device);
   cudaStreamSynchronize(A->mesh->ctx->stream);
-  cudaFree(A->vals); cudaFree(A->r); cudaFree(A->z); cudaFree(A->p); cudaFree(A->p1); cudaFree(A->s); cudaFree(A->w); cudaFree(A->dinv); cudaFree(A->hist);
+  cudaFree(A->vals); cudaFree(A->r); cudaFree(A->z); cudaFree(A->p); cudaFree(A->p1); cudaFree(A->s); cudaFree(A->r1); cudaFree(A->z1); cudaFree(A->s1); cudaFree(A->w); cudaFree(A->dinv); cudaFree(A->hist);
   delete A;
   return 0;
 }
@@ -579,6 +597,94 @@ k_cg_update(double *__restrict__ r, double *__restrict__ z, const double *__rest
   }
 }
 
+/* ------------------------------------------------------------------------------------ */
+/* Single-reduction CG (Chronopoulos-Gear) as two launches per iteration:                 */
+/*   k_cgcg_vec : p = u + beta p; s = w + beta s; x += alpha p; r -= alpha s; u = M^-1 r,  */
+/*                partial (r,u), (u,u) per block; halo blocks push the new u to neighbours */
+/*   k_spmv_*   : w = A u, (w,u); its last block adds the partials, all-reduces ONCE and   */
+/*                advances alpha/beta/norm/its.                                           */
+/* r, u and s are double-buffered by iteration parity so that the halo blocks can recompute */
+/* the values they push from buffers nobody writes during the kernel.                     */
+/* ------------------------------------------------------------------------------------ */
+template <int MODE, bool JACOBI>
+__global__ void __launch_bounds__(256)
+k_cgcg_vec(double *R0, double *R1, double *U0, double *U1, double *S0, double *S1, double *__restrict__ p,
+           const double *__restrict__ w, double *__restrict__ x, const double *__restrict__ b,
+           const double *__restrict__ dinv, int n, const ohp_cg_state *st, double *vpart, const ohp_p2p_dev pd,
+           int n_halo_blocks, unsigned *halo_ticket) {
+  pdl_wait();
+  pdl_launch();
+  if (st->done) return;
+  const bool init = (st->x_pending == 0);
+  const int k = init ? 1 : st->its; /* init writes the index-0 buffers, like an iteration of odd parity */
+  const double alpha = st->alpha, beta = st->beta;
+  const double *ro = (k & 1) ? R1 : R0, *uo = (k & 1) ? U1 : U0, *so = (k & 1) ? S1 : S0;
+  double *rn = (k & 1) ? R0 : R1, *un = (k & 1) ? U0 : U1, *sn = (k & 1) ? S0 : S1;
+  int blk = blockIdx.x, nb = gridDim.x;
+  if (MODE == OHP_MODE_P2P) {
+    if (blk < n_halo_blocks) {
+      const int nsend = pd.soff[pd.n_nbr];
+      const int nbuf = (k & 1) ? 0 : 1; /* index of the buffer being written */
+      for (int i = blk * blockDim.x + threadIdx.x; i < nsend; i += n_halo_blocks * blockDim.x) {
+        const int l = pd.send_ldof[i];
+        double val;
+        if (init) val = JACOBI ? dinv[l] * b[l] : b[l];
+        else {
+          const double si = fma(beta, so[l], w[l]);
+          const double ri = fma(-alpha, si, ro[l]);
+          val = JACOBI ? dinv[l] * ri : ri;
+        }
+        int q = 0;
+        while (i >= pd.soff[q + 1]) ++q;
+        pd.p[nbuf][pd.nbr[q]][pd.dst_off[q] + (i - pd.soff[q])] = val;
+      }
+      __threadfence_system();
+      __syncthreads();
+      __shared__ unsigned long long s_seq;
+      __shared__ bool s_last;
+      if (threadIdx.x == 0) {
+        s_last = (atomicInc(halo_ticket, n_halo_blocks - 1) == (unsigned)(n_halo_blocks - 1));
+        if (s_last) { __threadfence(); s_seq = pd.seq[1] + 1; pd.seq[1] = s_seq; }
+      }
+      __syncthreads();
+      if (s_last && threadIdx.x < pd.n_nbr) {
+        const int q = pd.nbr[threadIdx.x];
+        st_release_sys(pd.hflags[q] + pd.rank, s_seq);
+        p2p_wait(pd.hflags[pd.rank] + q, s_seq, pd.seq + 2);
+      }
+      return;
+    }
+    blk -= n_halo_blocks; nb -= n_halo_blocks;
+  }
+  double sums[2] = {0.0, 0.0};
+  if (init) {
+    for (int i = blk * blockDim.x + threadIdx.x; i < n; i += nb * blockDim.x) {
+      const double bi = b[i];
+      x[i] = 0.0; p[i] = 0.0; sn[i] = 0.0;
+      rn[i] = bi;
+      double ui = bi;
+      if (JACOBI) { ui = dinv[i] * bi; un[i] = ui; }
+      sums[0] += bi * ui; sums[1] += ui * ui;
+    }
+  } else {
+    for (int i = blk * blockDim.x + threadIdx.x; i < n; i += nb * blockDim.x) {
+      const double ui = uo[i];
+      const double pi = fma(beta, p[i], ui);
+      const double si = fma(beta, so[i], w[i]);
+      p[i] = pi; sn[i] = si;
+      x[i] = fma(alpha, pi, x[i]);
+      const double ri = fma(-alpha, si, ro[i]);
+      rn[i] = ri;
+      double uu = ri;
+      if (JACOBI) { uu = dinv[i] * ri; un[i] = uu; }
+      sums[0] += ri * uu; sums[1] += uu * uu;
+    }
+  }
+  __shared__ double s_red2[2 * 32];
+  block_sum<2>(sums, s_red2);
+  if (threadIdx.x == 0) { vpart[2 * blk] = sums[0]; vpart[2 * blk + 1] = sums[1]; }
+}
+
 __global__ void k_extract_dinv(const int32_t *rowptr, const int32_t *colidx, const double *vals, int n, double *dinv) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
@@ -597,6 +703,97 @@ int ohp_extract_dinv(ohp_mat A) {
 extern "C" int ohp_ksp_default_options(ohp_ksp_options *o) {
   o->rtol = 1e-5; o->abstol = 1e-50; o->dtol = 1e5; o->max_it = 10000; o->pc = OHP_PC_NONE;
   o->check_every = 0; o->history_cap = 0; o->history = nullptr; o->profile = 0;
+  return 0;
+}
+
+static int cgcg_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o, ohp_ksp_result *res, bool p2p) {
+  ohp_mesh m = A->mesh;
+  ohp_context ctx = m->ctx;
+  cudaStream_t st = ctx->stream;
+  const int n = m->n_owned;
+  const size_t len = (size_t)std::max(1, n + m->n_ghost);
+  const bool jac = (o->pc == OHP_PC_JACOBI);
+  auto need = [&](double **ptr) -> int {
+    if (!*ptr) { OHP_CUDA(cudaMalloc(ptr, sizeof(double) * len)); OHP_CUDA(cudaMemsetAsync(*ptr, 0, sizeof(double) * len, st)); }
+    return 0;
+  };
+  OHP_TRY(need(&A->p)); OHP_TRY(need(&A->w)); OHP_TRY(need(&A->s)); OHP_TRY(need(&A->s1));
+  static const ohp_p2p_dev no_p2p = {};
+  const ohp_p2p_dev &pd = p2p ? m->p2p->dev : no_p2p;
+  double *U0, *U1, *R0, *R1;
+  if (p2p) { U0 = pd.p[0][ctx->rank]; U1 = pd.p[1][ctx->rank]; }
+  else if (jac) { OHP_TRY(need(&A->z)); OHP_TRY(need(&A->z1)); U0 = A->z; U1 = A->z1; }
+  else { OHP_TRY(need(&A->r)); OHP_TRY(need(&A->r1)); U0 = A->r; U1 = A->r1; }
+  if (jac) {
+    OHP_TRY(need(&A->r)); OHP_TRY(need(&A->r1)); OHP_TRY(need(&A->dinv));
+    R0 = A->r; R1 = A->r1;
+    OHP_TRY(ohp_extract_dinv(A));
+  } else { R0 = U0; R1 = U1; }
+  double *hist = nullptr;
+  int hist_cap = 0;
+  if (o->history && o->history_cap > 0) {
+    if (A->hist_cap < o->history_cap) {
+      cudaFree(A->hist);
+      OHP_CUDA(cudaMalloc(&A->hist, sizeof(double) * o->history_cap));
+      A->hist_cap = o->history_cap;
+    }
+    hist = A->hist; hist_cap = o->history_cap;
+    OHP_CUDA(cudaMemsetAsync(hist, 0, sizeof(double) * hist_cap, st));
+  }
+  ohp_cg_state init;
+  memset(&init, 0, sizeof(init));
+  init.rtol = o->rtol; init.abstol = o->abstol; init.dtol = o->dtol; init.maxit = o->max_it;
+  *ctx->h_cg = init;
+  OHP_CUDA(cudaMemcpyAsync(ctx->d_cg, ctx->h_cg, sizeof(init), cudaMemcpyHostToDevice, st));
+  const int mode = p2p ? OHP_MODE_P2P : OHP_MODE_SERIAL;
+  const int vgrid = vec_grid(ctx, n);
+  const int nhalo = p2p ? std::max(1, std::min(16, (pd.soff[pd.n_nbr] + 255) / 256)) : 0;
+  double *vpart = ctx->d_partials + kMaxPartials; /* second half of the scratch: the SpMV uses the first */
+  ohp_cgcg_epi epi;
+  epi.vpart = vpart; epi.nvpart = vgrid; epi.jacobi = jac ? 1 : 0; epi.hist = hist; epi.hist_cap = hist_cap;
+  static const char *nopdl = getenv("OHP_NOPDL");
+  const bool pdl = !nopdl;
+  const int check_every = o->check_every > 0 ? o->check_every : 50;
+  cudaEvent_t ev0, ev1;
+  OHP_CUDA(cudaEventCreate(&ev0)); OHP_CUDA(cudaEventCreate(&ev1));
+  OHP_CUDA(cudaEventRecord(ev0, st));
+  int launched = 0;
+  for (;;) {
+    for (int it = 0; it < check_every; ++it) {
+      if (p2p) {
+        if (jac) OHP_CUDA(ohp_launch(k_cgcg_vec<OHP_MODE_P2P, true>, dim3(vgrid + nhalo), dim3(256), 0, st, pdl, R0, R1, U0, U1, A->s, A->s1, A->p, (const double *)A->w, x->d, (const double *)b->d, (const double *)A->dinv, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, nhalo, ctx->d_ticket + 2));
+        else OHP_CUDA(ohp_launch(k_cgcg_vec<OHP_MODE_P2P, false>, dim3(vgrid + nhalo), dim3(256), 0, st, pdl, R0, R1, U0, U1, A->s, A->s1, A->p, (const double *)A->w, x->d, (const double *)b->d, (const double *)A->dinv, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, nhalo, ctx->d_ticket + 2));
+      } else {
+        if (jac) OHP_CUDA(ohp_launch(k_cgcg_vec<OHP_MODE_SERIAL, true>, dim3(vgrid), dim3(256), 0, st, pdl, R0, R1, U0, U1, A->s, A->s1, A->p, (const double *)A->w, x->d, (const double *)b->d, (const double *)A->dinv, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, 0, (unsigned *)nullptr));
+        else OHP_CUDA(ohp_launch(k_cgcg_vec<OHP_MODE_SERIAL, false>, dim3(vgrid), dim3(256), 0, st, pdl, R0, R1, U0, U1, A->s, A->s1, A->p, (const double *)A->w, x->d, (const double *)b->d, (const double *)A->dinv, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, 0, (unsigned *)nullptr));
+      }
+      ctx->launches++;
+      OHP_TRY(spmv_enqueue(A, U0, A->w, ctx->d_cg, ctx->d_scalars, mode, U1, pd, epi));
+    }
+    launched += check_every;
+    OHP_CUDA(cudaMemcpyAsync(ctx->h_cg, ctx->d_cg, sizeof(ohp_cg_state), cudaMemcpyDeviceToHost, st));
+    OHP_CUDA(cudaStreamSynchronize(st));
+    if (ctx->h_cg->done) break;
+    if (launched > o->max_it + 2 * check_every) OHP_FAIL(OHP_ERR_LIB, "ohp_ksp_cg (single-reduction): iteration control did not terminate");
+  }
+  OHP_CUDA(cudaEventRecord(ev1, st));
+  OHP_CUDA(cudaEventSynchronize(ev1));
+  res->total_ms = 0.f;
+  cudaEventElapsedTime(&res->total_ms, ev0, ev1);
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+  res->its = ctx->h_cg->its; res->reason = ctx->h_cg->reason; res->rnorm = ctx->h_cg->dp; res->rnorm0 = ctx->h_cg->rnorm0;
+  res->spmv_ms = 0.f; res->spmv_samples = 0;
+  if (p2p) {
+    unsigned long long err = 0;
+    OHP_CUDA(cudaMemcpyAsync(&err, pd.seq + 2, sizeof(err), cudaMemcpyDeviceToHost, st));
+    OHP_CUDA(cudaStreamSynchronize(st));
+    if (err) OHP_FAIL(OHP_ERR_LIB, "ohp_ksp_cg (single-reduction): a peer-to-peer wait timed out");
+  }
+  if (hist) {
+    const int ncopy = std::min(hist_cap, res->its + 1);
+    OHP_CUDA(cudaMemcpyAsync(o->history, hist, sizeof(double) * ncopy, cudaMemcpyDeviceToHost, st));
+    OHP_CUDA(cudaStreamSynchronize(st));
+  }
   return 0;
 }
 
@@ -620,9 +817,15 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
     const bool can_p2p = ctx->nranks > 1 && m->p2p && m->p2p->attached && !(force_comm && force_comm[0] == 'n');
     const bool feasible = spmv_use_tma(m) && n > 0 && (ctx->nranks == 1 || can_p2p);
     bool persistent = feasible && ctx->nranks == 1 && n < kPersistentBelowRows; /* measured: see DESIGN.md section 5 */
-    if (force && force[0] == 'c') persistent = false;
+    if (force && force[0] == 'c') persistent = false; /* classic or cgcg */
     if (force && force[0] == 'p') persistent = feasible;
     if (persistent) return ohp_cg_persistent_solve(A, b, x, o, res, can_p2p);
+    /* single-reduction recurrence in two launches: default for partitioned runs over NVLink peer memory (one
+     * all-reduce and one kernel boundary fewer per iteration); OHP_CG=cgcg forces it on one GPU */
+    bool cgcg = can_p2p && n > 0 && n < kSingleReductionBelowRows; /* measured crossover: 0.145 vs 0.141 ms at 4.2 M rows/rank, 0.056 vs 0.068 at 1.05 M */
+    if (force && force[0] == 'c' && force[1] == 'l') cgcg = false;              /* classic */
+    if (force && force[0] == 'c' && force[1] == 'g') cgcg = (ctx->nranks == 1 || can_p2p) && n > 0; /* cgcg */
+    if (cgcg) return cgcg_solve(A, b, x, o, res, can_p2p);
   }
   const size_t len = (size_t)std::max(1, n + m->n_ghost);
   if (!A->r) {
