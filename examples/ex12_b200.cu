@@ -262,6 +262,7 @@ int main(int argc, char **argv)
     ierr = SNESGetLinearSolveIterations(snes, &lits);CHKERRQ(ierr);
     ierr = VecGetSize(u, &N);CHKERRQ(ierr);
     ierr = PetscPrintf(PETSC_COMM_WORLD, "N: %d Newton its: %d CG its: %d L_2 Error: %.6g\n", N, its, lits, (double)error);CHKERRQ(ierr);
+    ierr = VecViewFromOptions(u, NULL, "-vec_view");CHKERRQ(ierr);                             /* ex12.cpp:1618 */
   } else if (user.runType == RUN_PERF) {                                                       /* ex12.cpp:1619-1628 */
     Vec r;
     PetscReal res = 0.0;

@@ -171,6 +171,9 @@ int ohp_mesh_get_info(ohp_mesh mesh, ohp_mesh_info *info);
 int ohp_mesh_p2p_export(ohp_mesh mesh, void *handle64);
 int ohp_mesh_p2p_attach(ohp_mesh mesh, const void *handles /* nranks x 64 bytes */);
 
+/* the DM's copy of the cell list ((dim+1)*n_cells int32) and coordinates (dim*n_verts doubles), for viewers */
+int ohp_mesh_get_cells(ohp_mesh mesh, int32_t *cells);
+int ohp_mesh_get_coords(ohp_mesh mesh, double *coords);
 /* label "marker" (ex12.cpp:1023-1026): bnd[v] in {0,1}, n_verts bytes */
 int ohp_mesh_get_boundary(ohp_mesh mesh, uint8_t *bnd);
 /* global section: gidx[v] = global dof of vertex v, -1 if constrained; n_verts int64 */

@@ -245,7 +245,7 @@ inline PetscErrorCode PetscOptionsGetIntArray(void *, const char *, const char *
   return 0;
 }
 #define PetscPrintf(comm, ...) (printf(__VA_ARGS__), 0)
-inline PetscErrorCode PetscObjectSetName(PetscObject, const char *) { return 0; }
+inline PetscErrorCode PetscObjectSetName(PetscObject, const char *) { return 0; } /* names: see VecSetName */
 
 /* ---- DM: mesh ---- */
 inline PetscErrorCode DMPlexCreateFromCellListPetsc(MPI_Comm, PetscInt dim, PetscInt numCells, PetscInt numVertices,
@@ -376,6 +376,7 @@ inline PetscErrorCode VecDuplicate(Vec v, Vec *w) {
   return 0;
 }
 inline PetscErrorCode VecDestroy(Vec *v) { if (*v) { ohp_vec_destroy((*v)->v); delete *v; *v = nullptr; } return 0; }
+inline PetscErrorCode VecSetName(Vec v, const char *name) { v->name = name; return 0; }
 inline PetscErrorCode VecSet(Vec v, PetscScalar a) { return ohp_vec_set(v->v, a); }
 inline PetscErrorCode VecCopy(Vec x, Vec y) { return ohp_vec_copy(x->v, y->v); }
 inline PetscErrorCode VecAXPY(Vec y, PetscScalar a, Vec x) { return ohp_vec_axpy(y->v, a, x->v); }
@@ -432,6 +433,54 @@ inline PetscErrorCode DMComputeL2Diff(DM dm, PetscReal, PetscSimplePointFunc *, 
   int problem;
   PetscErrorCode ierr = ohp_ds_problem(&dm->ds, &problem); if (ierr) return ierr;
   return ohp_l2_error(dm->mesh, problem < 3 ? problem : 0, u->v, err);
+}
+
+/* ---- viewers: `-vec_view vtk:<file>.vtu` (what every reference CTest writes, CMakeLists.txt:75,81,87,93,100,107) ----
+ * ASCII VTK XML UnstructuredGrid of this rank's mesh with the nodal field: unconstrained vertices from
+ * the vector, "marker" vertices from the Dirichlet function (the values PETSc inserts into the local vector). */
+inline PetscErrorCode VecViewVTU(Vec u, const char *path) {
+  DM dm = u->dm;
+  ohp_mesh_info info;
+  PetscErrorCode ierr = ohp_mesh_get_info(dm->mesh, &info); if (ierr) return ierr;
+  const int dim = info.dim, nc = dim + 1;
+  std::vector<int32_t> cells((size_t)info.n_cells * nc);
+  std::vector<double> X((size_t)info.n_verts * dim), vals;
+  std::vector<int64_t> gidx(info.n_verts);
+  ierr = ohp_mesh_get_cells(dm->mesh, cells.data()); if (ierr) return ierr;
+  ierr = ohp_mesh_get_coords(dm->mesh, X.data()); if (ierr) return ierr;
+  ierr = ohp_mesh_get_numbering(dm->mesh, gidx.data()); if (ierr) return ierr;
+  ierr = VecGetValuesHost(u, vals); if (ierr) return ierr;
+  FILE *f = fopen(path, "w");
+  if (!f) { fprintf(stderr, "[0]PETSC ERROR: cannot open %s\n", path); return OHP_ERR_FILE_OPEN; }
+  fprintf(f, "<?xml version=\"1.0\"?>\n<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n <UnstructuredGrid>\n");
+  fprintf(f, "  <Piece NumberOfPoints=\"%d\" NumberOfCells=\"%d\">\n   <Points>\n    <DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"ascii\">\n", info.n_verts, info.n_cells);
+  for (int v = 0; v < info.n_verts; ++v) fprintf(f, "%.17g %.17g %.17g\n", X[(size_t)v * dim], X[(size_t)v * dim + 1], dim == 3 ? X[(size_t)v * dim + 2] : 0.0);
+  fprintf(f, "    </DataArray>\n   </Points>\n   <Cells>\n    <DataArray type=\"Int32\" Name=\"connectivity\" format=\"ascii\">\n");
+  for (int c = 0; c < info.n_cells; ++c) { for (int j = 0; j < nc; ++j) fprintf(f, "%d ", cells[(size_t)c * nc + j]); fprintf(f, "\n"); }
+  fprintf(f, "    </DataArray>\n    <DataArray type=\"Int32\" Name=\"offsets\" format=\"ascii\">\n");
+  for (int c = 0; c < info.n_cells; ++c) fprintf(f, "%d\n", (c + 1) * nc);
+  fprintf(f, "    </DataArray>\n    <DataArray type=\"UInt8\" Name=\"types\" format=\"ascii\">\n");
+  for (int c = 0; c < info.n_cells; ++c) fprintf(f, "%d\n", dim == 2 ? 5 : 10); /* VTK_TRIANGLE / VTK_TETRA */
+  fprintf(f, "    </DataArray>\n   </Cells>\n   <PointData Scalars=\"%s\">\n    <DataArray type=\"Float64\" Name=\"%s\" format=\"ascii\">\n",
+          u->name.empty() ? "potential" : u->name.c_str(), u->name.empty() ? "potential" : u->name.c_str());
+  for (int v = 0; v < info.n_verts; ++v) {
+    double val = 0.0;
+    const int64_t g = gidx[v] - info.row_start;
+    if (gidx[v] >= 0 && g >= 0 && g < info.n_owned) val = vals[(size_t)g];
+    else if (gidx[v] < 0 && dm->ds.bc) dm->ds.bc(dim, 0.0, &X[(size_t)v * dim], 1, &val, NULL);
+    fprintf(f, "%.17g\n", val);
+  }
+  fprintf(f, "    </DataArray>\n   </PointData>\n  </Piece>\n </UnstructuredGrid>\n</VTKFile>\n");
+  fclose(f);
+  return 0;
+}
+inline PetscErrorCode VecViewFromOptions(Vec u, PetscObject, const char *name) {
+  char buf[1024];
+  PetscBool set;
+  PetscOptionsGetString(NULL, NULL, name, buf, sizeof(buf), &set);
+  if (!set) return 0;
+  if (strncmp(buf, "vtk:", 4)) { fprintf(stderr, "[0]PETSC ERROR: %s %s: only vtk:<file>.vtu is built\n", name, buf); return PETSC_ERR_SUP; }
+  return VecViewVTU(u, buf + 4);
 }
 
 /* ---- SNES ---- */

@@ -206,6 +206,11 @@ int ohp_scan_exclusive_i32(ohp_context ctx, const int32_t *in, int32_t *out, int
 /* ------------------------------------------------------------------------------------ */
 /* DM creation                                                                           */
 /* ------------------------------------------------------------------------------------ */
+__global__ void k_check_cells(const int32_t *cells, int64_t n, int nV, int *flag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && (cells[i] < 0 || cells[i] >= nV)) atomicExch(flag, 1);
+}
+
 extern "C" int ohp_mesh_create(ohp_context ctx, int dim, int32_t nC, int32_t nV, const int32_t *cells,
                                const double *coords, ohp_mesh *out) {
   if (!ctx || !out) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_mesh_create: null argument");
@@ -214,10 +219,6 @@ extern "C" int ohp_mesh_create(ohp_context ctx, int dim, int32_t nC, int32_t nV,
   if ((int64_t)nC * (dim + 1) >= (int64_t)1 << 29) OHP_FAIL(OHP_ERR_ARG_SIZ, "ohp_mesh_create: too many cells for 32-bit incidence ids");
   if ((nC && !cells) || (nV && !coords)) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_mesh_create: null arrays");
   const int nc = dim + 1;
-  for (int64_t i = 0; i < (int64_t)nC * nc; ++i)
-    if (cells[i] < 0 || cells[i] >= nV)
-      OHP_FAIL(OHP_ERR_ARG_OUTOFRANGE, "ohp_mesh_create: cell %lld references vertex %d outside [0,%d)",
-               (long long)(i / nc), cells[i], nV);
   OHP_CUDA(cudaSetDevice(ctx->device));
   ohp_mesh m = new ohp_mesh_s();
   m->ctx = ctx; m->dim = dim; m->nc = nc; m->nC = nC; m->nV = nV;
@@ -229,7 +230,22 @@ extern "C" int ohp_mesh_create(ohp_context ctx, int dim, int32_t nC, int32_t nV,
   OHP_CUDA(cudaMalloc(&m->coords, sizeof(double) * std::max<int64_t>(1, (int64_t)nV * dim)));
   OHP_CUDA(cudaMemcpyAsync(m->cells, cells, sizeof(int32_t) * (int64_t)nC * nc, cudaMemcpyHostToDevice, ctx->stream));
   OHP_CUDA(cudaMemcpyAsync(m->coords, coords, sizeof(double) * (int64_t)nV * dim, cudaMemcpyHostToDevice, ctx->stream));
+  /* range check of the connectivity on the device (a host pass over 50 M ints costs more than the upload) */
+  if (nC) {
+    k_check_cells<<<(unsigned)std::max<int64_t>(1, ((int64_t)nC * nc + 255) / 256), 256, 0, ctx->stream>>>(m->cells, (int64_t)nC * nc, nV, ctx->d_flag);
+    OHP_CHECK_LAUNCH(ctx);
+  }
+  int bad = 0;
+  OHP_CUDA(cudaMemcpyAsync(&bad, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   OHP_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (bad) {
+    cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream);
+    int64_t i = 0;
+    while (i < (int64_t)nC * nc && cells[i] >= 0 && cells[i] < nV) ++i;
+    const int64_t bc = std::min<int64_t>(i, (int64_t)nC * nc - 1);
+    ohp_mesh_destroy(m);
+    OHP_FAIL(OHP_ERR_ARG_OUTOFRANGE, "ohp_mesh_create: cell %lld references vertex %d outside [0,%d)", (long long)(bc / nc), cells[bc], nV);
+  }
   *out = m;
   return 0;
 }
@@ -671,6 +687,21 @@ extern "C" int ohp_mesh_get_info(ohp_mesh m, ohp_mesh_info *info) {
   info->dim = m->dim; info->n_cells = m->nC; info->n_verts = m->nV; info->n_boundary_verts = m->n_bnd;
   info->n_owned = m->n_owned; info->n_ghost = m->n_ghost; info->n_global = m->n_global;
   info->row_start = m->row_start; info->nnz = m->nnz; info->max_row = m->max_row;
+  return 0;
+}
+
+extern "C" int ohp_mesh_get_cells(ohp_mesh m, int32_t *cells) {
+  if (!m || !cells) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_mesh_get_cells: null argument");
+  OHP_CUDA(cudaSetDevice(m->ctx->device));
+  OHP_CUDA(cudaMemcpyAsync(cells, m->cells, sizeof(int32_t) * (size_t)m->nC * m->nc, cudaMemcpyDeviceToHost, m->ctx->stream));
+  OHP_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  return 0;
+}
+extern "C" int ohp_mesh_get_coords(ohp_mesh m, double *coords) {
+  if (!m || !coords) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_mesh_get_coords: null argument");
+  OHP_CUDA(cudaSetDevice(m->ctx->device));
+  OHP_CUDA(cudaMemcpyAsync(coords, m->coords, sizeof(double) * (size_t)m->nV * m->dim, cudaMemcpyDeviceToHost, m->ctx->stream));
+  OHP_CUDA(cudaStreamSynchronize(m->ctx->stream));
   return 0;
 }
 

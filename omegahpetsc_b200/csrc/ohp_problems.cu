@@ -93,10 +93,12 @@ std::vector<ProblemEntry> &registry() {
 /* DMComputeL2Diff [PETSc-internal, reached from ex12.cpp:1611,1637]: sqrt(sum_c sum_q w_q detJ (u_h - u_exact)^2),
  * evaluated with the same quadrature; deterministic two-stage sum */
 template <int DIM>
-__global__ void __launch_bounds__(256) k_l2_diff(const ohp_assembly_view vw, double *partials) {
+__global__ void __launch_bounds__(256) k_l2_diff(const ohp_assembly_view vw, const uint8_t *owned, double *partials) {
   constexpr int NC = DIM + 1;
   double acc = 0.0;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < vw.n_cells; c += gridDim.x * blockDim.x) {
+    /* partitioned meshes overlap by one layer of cells: a cell is integrated by the rank that owns its first corner */
+    if (!owned[vw.cells_dev[(size_t)c * NC]]) continue;
     int cv[NC];
     double X[NC][DIM], ue[NC];
     ohp::load_cell<DIM, QuadraticBC, true>(vw, c, cv, X, ue);
@@ -199,19 +201,25 @@ extern "C" int ohp_project(ohp_mesh m, int problem, int which, ohp_vec u) {
 extern "C" int ohp_l2_error(ohp_mesh m, int problem, ohp_vec u, double *err) {
   NEED(m, "ohp_l2_error");
   (void)problem; /* all built-in problems share the quadratic exact solution (ex12.cpp:1222,1230) */
-  if (m->ctx->nranks > 1) OHP_FAIL(OHP_ERR_SUP, "ohp_l2_error: serial only (owned-cell mask not wired)");
   ohp_context ctx = m->ctx;
+  if (ctx->nranks > 1) OHP_TRY(ohp_halo_exchange(m, u->d));
   ohp_assembly_view vw;
   ohp_assembly_view_make(m, u->d, nullptr, &vw);
   const int grid = std::min(std::max(1, (m->nC + 255) / 256), 1024);
-  if (m->dim == 2) k_l2_diff<2><<<grid, 256, 0, ctx->stream>>>(vw, ctx->d_partials);
-  else k_l2_diff<3><<<grid, 256, 0, ctx->stream>>>(vw, ctx->d_partials);
+  if (m->dim == 2) k_l2_diff<2><<<grid, 256, 0, ctx->stream>>>(vw, m->owned, ctx->d_partials);
+  else k_l2_diff<3><<<grid, 256, 0, ctx->stream>>>(vw, m->owned, ctx->d_partials);
   OHP_CHECK_LAUNCH(ctx);
   std::vector<double> part(grid);
   OHP_CUDA(cudaMemcpyAsync(part.data(), ctx->d_partials, sizeof(double) * grid, cudaMemcpyDeviceToHost, ctx->stream));
   OHP_CUDA(cudaStreamSynchronize(ctx->stream));
   double s = 0.0;
   for (double p : part) s += p;
+  if (ctx->nranks > 1) {
+    OHP_CUDA(cudaMemcpyAsync(ctx->d_scalars, &s, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    OHP_TRY(ohp_allreduce_sum(ctx, ctx->d_scalars, 1));
+    OHP_CUDA(cudaMemcpyAsync(&s, ctx->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    OHP_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   *err = sqrt(s);
   return 0;
 }

@@ -121,6 +121,21 @@ def main():
     assert abs(res["ksp_its"] - ref["ksp_its"]) <= max(2, ref["ksp_its"] // 40), (res["ksp_its"], ref["ksp_its"])
     uref = ref["u"][gidx[dof2vert[start:start + info.n_owned]]]
     assert np.abs(u.to_host() - uref).max() <= 1e-7 * np.abs(ref["u"]).max(), "solution"
+    # DMComputeL2Diff across ranks: every cell integrated once (by the owner of its first corner)
+    xi, wq = oracle.quadrature(coords.shape[1])
+    full = (coords ** 2).sum(axis=1) * (1.0 if coords.shape[1] == 2 else 2.0 / 3.0)
+    full[ser_vert] = ref["u"]
+    if coords.shape[1] == 2:
+        X = coords[cells]
+        Jm = 0.5 * np.stack([X[:, 1] - X[:, 0], X[:, 2] - X[:, 0]], axis=2)
+        detJ = np.abs(Jm[:, 0, 0] * Jm[:, 1, 1] - Jm[:, 0, 1] * Jm[:, 1, 0])
+        e2 = 0.0
+        for q in range(4):
+            phi = np.array([-(xi[q, 0] + xi[q, 1]) / 2, (1 + xi[q, 0]) / 2, (1 + xi[q, 1]) / 2])
+            xq = X[:, 0] + Jm @ (xi[q] + 1.0)
+            e2 += (wq[q] * detJ * (full[cells] @ phi - (xq ** 2).sum(axis=1)) ** 2).sum()
+        l2 = m.l2_error(0, u)
+        assert abs(l2 - np.sqrt(e2)) <= 1e-6 * np.sqrt(e2) + 1e-12, (l2, np.sqrt(e2))
     dist.barrier()
     if rank == 0:
         print("MGPU_OK %s world=%d N=%d ksp_its=%d (oracle %d) ghosts(rank0)=%d" % (

@@ -86,3 +86,29 @@ def test_unsupported_requests_fail_loudly():
     assert p.returncode != 0 and "only cg is built" in p.stderr
     p = subprocess.run([EXE, "-mesh", "/nonexistent.osh"], capture_output=True, text=True, timeout=120)
     assert p.returncode != 0
+
+
+@pytest.mark.gpu
+def test_vec_view_vtu(tmp_path, oracle_mod):
+    """-vec_view vtk:<file>.vtu (ex12.cpp:1618; every reference CTest writes one, CMakeLists.txt:75-109)."""
+    build()
+    out = tmp_path / "sol.vtu"
+    p = subprocess.run([EXE, "-mesh", golden_mesh_path("23elm.osh"), "-ksp_rtol", "1e-12", "-vec_view", "vtk:%s" % out],
+                       capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stdout + p.stderr
+    import xml.etree.ElementTree as ET
+    root = ET.parse(out).getroot()
+    piece = root.find("UnstructuredGrid/Piece")
+    assert (piece.get("NumberOfPoints"), piece.get("NumberOfCells")) == ("19", "23")
+    pts = np.array(piece.find("Points/DataArray").text.split(), float).reshape(-1, 3)
+    conn = np.array(piece.find("Cells/DataArray[@Name='connectivity']").text.split(), int).reshape(-1, 3)
+    vals = np.array(piece.find("PointData/DataArray").text.split(), float)
+    cells, coords, _ = load_osh_oracle("23elm.osh")
+    assert np.array_equal(conn, cells) and np.allclose(pts[:, :2], coords, rtol=0, atol=0)
+    bnd = oracle_mod.mark_boundary(cells, coords.shape[0])
+    gidx, N = oracle_mod.numbering(bnd)
+    rowptr, colidx = oracle_mod.pattern(cells, gidx, N)
+    ref = oracle_mod.newton(0, cells, coords, gidx, N, rowptr, colidx, ksp_rtol=1e-12)
+    full = (coords ** 2).sum(axis=1)
+    full[gidx >= 0] = ref["u"]
+    assert np.abs(vals - full).max() < 1e-9
