@@ -822,9 +822,11 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
     if (persistent) return ohp_cg_persistent_solve(A, b, x, o, res, can_p2p);
     /* single-reduction recurrence in two launches: default for partitioned runs over NVLink peer memory (one
      * all-reduce and one kernel boundary fewer per iteration); OHP_CG=cgcg forces it on one GPU */
-    bool cgcg = can_p2p && n > 0 && n < kSingleReductionBelowRows; /* measured crossover: 0.145 vs 0.141 ms at 4.2 M rows/rank, 0.056 vs 0.068 at 1.05 M */
-    if (force && force[0] == 'c' && force[1] == 'l') cgcg = false;              /* classic */
-    if (force && force[0] == 'c' && force[1] == 'g') cgcg = (ctx->nranks == 1 || can_p2p) && n > 0; /* cgcg */
+    /* every rank must take the same branch: decide on GLOBAL quantities only (a rank may own no rows at all) */
+    const int64_t rows_per_rank = m->n_global / std::max(1, ctx->nranks);
+    bool cgcg = can_p2p && rows_per_rank < kSingleReductionBelowRows; /* measured crossover: 0.145 vs 0.141 ms at 4.2 M rows/rank, 0.056 vs 0.068 at 1.05 M */
+    if (force && force[0] == 'c' && force[1] == 'l') cgcg = false;                          /* classic */
+    if (force && force[0] == 'c' && force[1] == 'g') cgcg = (ctx->nranks == 1 || can_p2p);  /* cgcg */
     if (cgcg) return cgcg_solve(A, b, x, o, res, can_p2p);
   }
   const size_t len = (size_t)std::max(1, n + m->n_ghost);

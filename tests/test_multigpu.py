@@ -31,7 +31,14 @@ def test_two_gpus(mesh, comm):
     run_worker(2, mesh, 29611, comm)
 
 
-@pytest.mark.parametrize("mesh", ["24k_4p", "box2d_40"])
+def test_two_gpus_from_picpart_files():
+    """Each rank reads its own pumipic picpart (23elm 2-part fixture) and extracts its core on the device."""
+    if ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    run_worker(2, "pic:23elm_2p", 29613)
+
+
+@pytest.mark.parametrize("mesh", ["24k_4p", "box2d_40", "pic:24k_4p"])
 def test_four_gpus(mesh):
     if ngpus() < 4:
         pytest.skip("needs 4 GPUs")
