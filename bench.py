@@ -286,8 +286,13 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     phase = {"ms_residual": 0.0, "ms_jacobian": 0.0, "ms_ksp": 0.0, "spmv_ms": [], "ksp_its": 0}
+    step_events = []
     for _ in range(args.steps):
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record(stream)
         res = step()
+        eb.record(stream)
+        step_events.append((ea, eb))
         for k in ("ms_residual", "ms_jacobian", "ms_ksp"):
             phase[k] += res[k]
         phase["ksp_its"] += res["ksp_its"]
@@ -298,6 +303,7 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
     launches = ctx.launch_count() - l0
     ms_total = e0.elapsed_time(e1)
+    ms_each = [a.elapsed_time(b) for a, b in step_events]
     if world > 1:
         t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -352,6 +358,7 @@ def run_ours(args):
     for k in kernels.values():
         k["frac_of_peak"] = k["GBps"] / peak
     kernels["phase_ms_per_step"] = {k: phase[k] / args.steps for k in ("ms_residual", "ms_jacobian", "ms_ksp")}
+    kernels["phase_ms_per_step"]["each_step_ms"] = ms_each
 
     cpu = None
     if args.gpus == 1 and not args.no_cpu:

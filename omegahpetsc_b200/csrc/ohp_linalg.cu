@@ -151,7 +151,7 @@ k_spmv_stream(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ co
 /* A row that straddles a tile boundary is carried in a register by the thread that       */
 /* started it (same thread finishes it in the next tile), so the order stays serial.      */
 /* ------------------------------------------------------------------------------------ */
-template <bool CG, int kTmaStages, int kTmaConsumers, class IDX>
+template <bool CG, int kTmaStages, int kTmaConsumers, class IDX, bool SPLIT>
 __global__ void __launch_bounds__(kTmaConsumers + 32, 1)
 k_spmv_tma(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colidx, const double *__restrict__ vals,
            const double *__restrict__ x, double *__restrict__ y, const int32_t *__restrict__ tile_row, int n_tiles,
@@ -211,11 +211,39 @@ k_spmv_tma(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colidx, c
         carry = row_dot<IDX>(vs, cs, 0, min(end, lim) - base, x, carry, pend);
         if (end <= lim) { y[pend] = carry; if (CG) dot[0] += carry * __ldg(x + pend); pend = -1; }
       }
-      for (int r = rs + tid; r < re; r += NC) {
-        const int a = rp[r - rs], b = rp[r - rs + 1];
-        const double sum = row_dot<IDX>(vs, cs, a - base, min(b, lim) - base, x, 0.0, r);
-        if (b > lim) { carry = sum; pend = r; }
-        else { y[r] = sum; if (CG) dot[0] += sum * __ldg(x + r); }
+      if (!SPLIT) {
+        for (int r = rs + tid; r < re; r += NC) {
+          const int a = rp[r - rs], b = rp[r - rs + 1];
+          const double sum = row_dot<IDX>(vs, cs, a - base, min(b, lim) - base, x, 0.0, r);
+          if (b > lim) { carry = sum; pend = r; }
+          else { y[r] = sum; if (CG) dot[0] += sum * __ldg(x + r); }
+        }
+      } else {
+        /* SPLIT (matrices with long rows, e.g. 15 non-zeros per row in 3-D): when a tile starts few rows, 2 or 4
+         * adjacent lanes share a row so that it still costs one gather latency; their partial sums are combined in
+         * a fixed butterfly order.  The choice depends on the tile only, so results stay reproducible. */
+        const int nrows = re - rs;
+        const int tpr = (nrows * 4 <= NC) ? 4 : (nrows * 2 <= NC) ? 2 : 1;
+        const int sub = tid & (tpr - 1), grp = tid / tpr, ngrp = NC / tpr;
+        for (int rb = rs; rb < re; rb += ngrp) { /* uniform trip count: the shuffles below need the whole warp */
+          const int r = rb + grp;
+          const bool valid = r < re;
+          int a = 0, b = 0;
+          if (valid) { a = rp[r - rs]; b = rp[r - rs + 1]; }
+          const int bl = min(b, lim);
+          int ca = a, cb = bl;
+          if (tpr > 1) {
+            if (b > lim) { if (sub != 0) cb = ca; }          /* a straddling row stays with its leader (serial order) */
+            else { const int chunk = (bl - a + tpr - 1) / tpr; ca = min(a + sub * chunk, bl); cb = min(ca + chunk, bl); }
+          }
+          double part = (valid && cb > ca) ? row_dot<IDX>(vs, cs, ca - base, cb - base, x, 0.0, r) : 0.0;
+          if (tpr > 1) part += __shfl_xor_sync(0xffffffffu, part, 1); /* tpr is uniform over the CTA */
+          if (tpr > 2) part += __shfl_xor_sync(0xffffffffu, part, 2);
+          if (valid && sub == 0) {
+            if (b > lim) { carry = part; pend = r; }
+            else { y[r] = part; if (CG) dot[0] += part * __ldg(x + r); }
+          }
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty0 + 8 * s);
@@ -250,28 +278,36 @@ static int spmv_configure(ohp_mesh m) {
   return 0;
 }
 
-template <int S, int NC, class IDX>
-static int spmv_tma_launch_t(ohp_mat A, const IDX *cols, const double *x, double *y, ohp_cg_state *st, double *sums, int mode,
-                             const double *x_alt, const ohp_p2p_dev &pd, const ohp_cgcg_epi &epi) {
+template <int S, int NC, class IDX, bool SPLIT>
+static int spmv_tma_launch_ts(ohp_mat A, const IDX *cols, const double *x, double *y, ohp_cg_state *st, double *sums, int mode,
+                              const double *x_alt, const ohp_p2p_dev &pd, const ohp_cgcg_epi &epi) {
   ohp_mesh m = A->mesh;
   ohp_context ctx = m->ctx;
   constexpr int smem = tma_smem_bytes(S, (int)sizeof(IDX));
   static bool configured = false;
   if (!configured) {
-    OHP_CUDA(cudaFuncSetAttribute(k_spmv_tma<true, S, NC, IDX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    OHP_CUDA(cudaFuncSetAttribute(k_spmv_tma<false, S, NC, IDX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    OHP_CUDA(cudaFuncSetAttribute(k_spmv_tma<true, S, NC, IDX, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    OHP_CUDA(cudaFuncSetAttribute(k_spmv_tma<false, S, NC, IDX, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   const int grid = std::max(1, std::min(m->n_tiles, ctx->num_sms));
   if (st) {
     static const char *nopdl = getenv("OHP_NOPDL");
-    OHP_CUDA(ohp_launch(k_spmv_tma<true, S, NC, IDX>, dim3(grid), dim3(NC + 32), (size_t)smem, ctx->stream, mode != OHP_MODE_NCCL && !nopdl,
+    OHP_CUDA(ohp_launch(k_spmv_tma<true, S, NC, IDX, SPLIT>, dim3(grid), dim3(NC + 32), (size_t)smem, ctx->stream, mode != OHP_MODE_NCCL && !nopdl,
                         m->rowptr, cols, A->vals, x, y, m->tile_row, m->n_tiles, st, ctx->d_partials, ctx->d_ticket + 1, sums, mode, x_alt, pd, epi));
   }
-  else k_spmv_tma<false, S, NC, IDX><<<grid, NC + 32, smem, ctx->stream>>>(
+  else k_spmv_tma<false, S, NC, IDX, SPLIT><<<grid, NC + 32, smem, ctx->stream>>>(
       m->rowptr, cols, A->vals, x, y, m->tile_row, m->n_tiles, nullptr, nullptr, nullptr, nullptr, 0, nullptr, pd, epi);
   OHP_CHECK_LAUNCH(ctx);
   return 0;
+}
+/* long rows (more than 8 non-zeros on average: 3-D meshes) share a row among 2-4 lanes */
+template <int S, int NC, class IDX>
+static int spmv_tma_launch_t(ohp_mat A, const IDX *cols, const double *x, double *y, ohp_cg_state *st, double *sums, int mode,
+                             const double *x_alt, const ohp_p2p_dev &pd, const ohp_cgcg_epi &epi) {
+  ohp_mesh m = A->mesh;
+  if (m->nnz > (int64_t)8 * std::max(1, m->n_owned)) return spmv_tma_launch_ts<S, NC, IDX, true>(A, cols, x, y, st, sums, mode, x_alt, pd, epi);
+  return spmv_tma_launch_ts<S, NC, IDX, false>(A, cols, x, y, st, sums, mode, x_alt, pd, epi);
 }
 template <int S, int NC>
 static int spmv_tma_launch(ohp_mat A, const double *x, double *y, ohp_cg_state *st, double *sums, int mode,
