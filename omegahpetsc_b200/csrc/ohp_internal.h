@@ -178,6 +178,5 @@ int ohp_cg_persistent_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_optio
 /* ohp_problems.cu */
 int ohp_problem_lookup(int id, ohp_assembly_launcher *res, ohp_assembly_launcher *jac,
                        ohp_assembly_launcher *proj);
-int ohp_l2_error_builtin(ohp_mesh mesh, int problem, const double *u, double *err);
 
 #endif
