@@ -99,12 +99,15 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-/* spin until *flag >= seq; a peer that died must not hang this GPU: after 4 s raise seq[2] and go on */
+/* spin until *flag >= seq.  A peer that died must not hang this GPU: after 2 s the wait gives up and raises
+ * seq[2]; once it is raised every later wait returns at once, so the chunk in flight drains quickly and the
+ * host (which reads seq[2] after the chunk) fails the solve with an error instead of hanging the box. */
 __device__ __forceinline__ void p2p_wait(const unsigned long long *flag, unsigned long long seq, unsigned long long *err) {
   if (ld_acquire_sys(flag) >= seq) return;
+  if (*(volatile unsigned long long *)err) return;
   const unsigned long long t0 = global_ns();
   while (ld_acquire_sys(flag) < seq) {
-    if (global_ns() - t0 > 4000000000ull) { *err = 1ull; return; }
+    if (global_ns() - t0 > 2000000000ull) { *(volatile unsigned long long *)err = 1ull; return; }
   }
 }
 

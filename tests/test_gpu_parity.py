@@ -253,6 +253,37 @@ def test_error_paths(ctx):
     m.destroy()
 
 
+def test_vertex_star_limit_is_reported(ctx):
+    """A vertex with more incident cells than the pattern sort stages (512 candidate columns = 170 triangles)
+    must be refused with PETSC_ERR_SUP, not mis-assembled."""
+    k = 200
+    ang = np.linspace(0.0, 2.0 * np.pi, k, endpoint=False)
+    coords = np.vstack([[0.0, 0.0], np.stack([np.cos(ang), np.sin(ang)], axis=1), 2.0 * np.stack([np.cos(ang), np.sin(ang)], axis=1)])
+    inner = np.stack([np.zeros(k, int), 1 + np.arange(k), 1 + (np.arange(k) + 1) % k], axis=1)
+    a, b = 1 + np.arange(k), 1 + (np.arange(k) + 1) % k
+    outer = np.vstack([np.stack([a, a + k, b], axis=1), np.stack([b, a + k, b + k], axis=1)])
+    m = ohp.Mesh(ctx, np.vstack([inner, outer]).astype(np.int32), coords)
+    with pytest.raises(ohp.OhpError) as e:
+        m.setup()
+    assert e.value.code == 56 and "star too large" in str(e.value)
+    m.destroy()
+    # the same fan with 150 triangles is inside the limit and must match the oracle
+    import oracle
+    k = 150
+    ang = np.linspace(0.0, 2.0 * np.pi, k, endpoint=False)
+    coords = np.vstack([[0.0, 0.0], np.stack([np.cos(ang), np.sin(ang)], axis=1), 2.0 * np.stack([np.cos(ang), np.sin(ang)], axis=1)])
+    a, b = 1 + np.arange(k), 1 + (np.arange(k) + 1) % k
+    cells = np.vstack([np.stack([np.zeros(k, int), a, b], axis=1), np.stack([a, a + k, b], axis=1), np.stack([b, a + k, b + k], axis=1)]).astype(np.int32)
+    bnd, gidx, N, rowptr, colidx = oracle_setup(oracle, cells, coords)
+    m = ohp.Mesh(ctx, cells, coords).setup()
+    rp, ci = m.csr()
+    assert np.array_equal(rp, rowptr) and np.array_equal(ci, colidx) and m.info().max_row == k + 1
+    J, u = m.create_matrix(), m.create_global_vector()
+    vo = oracle.jacobian(0, cells, coords, gidx, N, np.zeros(N), rowptr, colidx)
+    assert rowwise_close(m.jacobian(0, u, J).values(), vo, rowptr, VAL_RTOL)
+    m.destroy()
+
+
 def test_picpart_extract_matches_reference_semantics(ctx, expected):
     """getPicPartCore* (ex12.cpp:584-730) on the 4-part XGC fixture: counts from the survey
     probe, arrays against a numpy restatement."""
