@@ -333,7 +333,11 @@ def run_ours(args):
     h2d = int(lcells.nbytes + lcoords.nbytes)
     d2h = int(info.n_owned * 8)
 
+    if world > 1:
+        dist.barrier()
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     peak, peak_kind = peaks()
     ab = algorithmic_bytes(dim, info.n_cells, info.n_verts, info.n_owned, info.nnz)
@@ -389,7 +393,9 @@ def run_ours(args):
                     "steps": e2e_steps, "includes": "ohp_mesh_create (H2D of cells+coords from pinned host memory), device numbering + CSR build, "
                                                     "Newton step, D2H of the solution"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():

@@ -224,7 +224,7 @@ extern "C" int ohp_mesh_create(ohp_context ctx, int dim, int32_t nC, int32_t nV,
   m->ctx = ctx; m->dim = dim; m->nc = nc; m->nC = nC; m->nV = nV;
   m->cells = nullptr; m->coords = nullptr; m->owned = nullptr; m->setup_done = false;
   m->v2c_ptr = m->v2c = nullptr; m->bnd = nullptr; m->lidx = m->row_vertex = nullptr; m->ldof_gid = nullptr;
-  m->rowptr = m->colidx = nullptr; m->col16 = nullptr; m->slot = nullptr; m->tile_row = nullptr; m->halo = nullptr; m->p2p = nullptr;
+  m->rowptr = m->colidx = nullptr; m->col16 = nullptr; m->slot = nullptr; m->tile_row = nullptr; m->halo = nullptr; m->p2p = nullptr; m->ghost_cta = nullptr;
   m->n_owned = m->n_ghost = m->n_bnd = 0; m->n_global = m->row_start = m->nnz = 0; m->max_row = 0; m->n_tiles = 0; m->max_tile_rows = 0;
   OHP_CUDA(cudaMalloc(&m->cells, sizeof(int32_t) * std::max<int64_t>(1, (int64_t)nC * nc)));
   OHP_CUDA(cudaMalloc(&m->coords, sizeof(double) * std::max<int64_t>(1, (int64_t)nV * dim)));
@@ -259,6 +259,7 @@ extern "C" int ohp_mesh_destroy(ohp_mesh m) {
   cudaFree(m->colidx); cudaFree(m->col16); cudaFree(m->slot); cudaFree(m->tile_row);
   ohp_halo_free(m->halo);
   ohp_p2p_free(m->p2p);
+  cudaFree(m->ghost_cta);
   delete m;
   return 0;
 }
@@ -477,6 +478,16 @@ __global__ void k_col16(const int32_t *rowptr, const int32_t *colidx, int n_rows
   if (bad) atomicExch(overflow, 1);
 }
 
+/* which CTAs of the persistent SpMV (CTA b owns tiles [n_tiles*b/G, n_tiles*(b+1)/G)) touch ghost columns */
+__global__ void k_ghost_cta(const int32_t *colidx, int64_t nnz, int n_owned, int n_tiles, int tile, uint8_t *flag) {
+  const int64_t k0 = (int64_t)(((int64_t)n_tiles * blockIdx.x) / gridDim.x) * tile;
+  const int64_t k1 = std::min<int64_t>(nnz, (int64_t)(((int64_t)n_tiles * (blockIdx.x + 1)) / gridDim.x) * tile + 8192);
+  int any = 0; /* + 8192: a row started in the last tile may run on into the next CTA's first tile */
+  for (int64_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) any |= (colidx[k] >= n_owned);
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) flag[blockIdx.x] = any ? 1 : 0;
+}
+
 __global__ void k_max_rowlen(const int32_t *rowptr, int n_rows, int32_t *out) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   int len = r < n_rows ? rowptr[r + 1] - rowptr[r] : 0;
@@ -661,6 +672,12 @@ extern "C" int ohp_mesh_setup(ohp_mesh m) {
   if (m->n_tiles == 0 && N > 0) m->n_tiles = 1;
   OHP_CUDA(cudaMalloc(&m->tile_row, sizeof(int32_t) * (m->n_tiles + 1)));
   k_tile_rows<<<nblk(m->n_tiles + 1, BS), BS, 0, st>>>(m->rowptr, N, kSpmvTile, m->n_tiles, m->tile_row); OHP_CHECK_LAUNCH(ctx);
+  if (ctx->nranks > 1 && m->n_tiles > 0) {
+    const int G = std::max(1, std::min(m->n_tiles, ctx->num_sms));
+    OHP_CUDA(cudaMalloc(&m->ghost_cta, ctx->num_sms));
+    OHP_CUDA(cudaMemsetAsync(m->ghost_cta, 1, ctx->num_sms, st));
+    k_ghost_cta<<<G, 256, 0, st>>>(m->colidx, m->nnz, m->n_owned, m->n_tiles, kSpmvTile, m->ghost_cta); OHP_CHECK_LAUNCH(ctx);
+  }
   {
     std::vector<int32_t> tr(m->n_tiles + 1);
     OHP_CUDA(cudaMemcpyAsync(tr.data(), m->tile_row, sizeof(int32_t) * (m->n_tiles + 1), cudaMemcpyDeviceToHost, st));

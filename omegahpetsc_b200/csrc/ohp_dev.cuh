@@ -238,6 +238,7 @@ struct ohp_cgcg_epi {
   const double *vpart; /* nvpart x 2, NULL = classic recurrence */
   int nvpart, jacobi, hist_cap;
   double *hist;
+  const uint8_t *ghost_cta; /* non-NULL: the SpMV itself waits for the halo, and only in the CTAs flagged here */
 };
 
 #endif

@@ -134,6 +134,7 @@ struct ohp_mesh_s {
   int32_t max_tile_rows; /* most rows starting inside one tile */
   ohp_halo *halo;    /* dof-level halo plan (NULL when serial) */
   ohp_p2p *p2p;      /* NVLink peer mapping (NULL until ohp_mesh_p2p_attach) */
+  uint8_t *ghost_cta; /* per persistent-SpMV CTA: 1 if its tiles reference ghost columns (NULL when serial) */
 };
 
 struct ohp_vec_s {

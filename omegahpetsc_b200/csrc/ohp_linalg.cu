@@ -174,6 +174,10 @@ k_spmv_tma(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colidx, c
     for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 33); mbar_init(empty0 + 8 * s, NC / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  /* halo/compute overlap: the vector kernel only PUSHED its halo; the neighbours' values are awaited here, and
+   * only by the CTAs whose tiles reference ghost columns (the strips' first and last CTAs): interior CTAs start at once */
+  if (CG && mode == OHP_MODE_P2P && epi.ghost_cta && epi.ghost_cta[blockIdx.x] && tid < pd.n_nbr)
+    p2p_wait(pd.hflags[pd.rank] + pd.nbr[tid], pd.seq[1], pd.seq + 2);
   __syncthreads();
   const int t0 = (int)(((int64_t)n_tiles * blockIdx.x) / gridDim.x);
   const int t1 = (int)(((int64_t)n_tiles * (blockIdx.x + 1)) / gridDim.x);
@@ -544,7 +548,7 @@ k_cg_init(const double *__restrict__ b, double *__restrict__ x, double *__restri
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_cg_pupdate(double *__restrict__ p0, double *__restrict__ p1, const double *__restrict__ z, double *__restrict__ x,
-             int n, const ohp_cg_state *st, const ohp_p2p_dev pd, int n_halo_blocks, unsigned *halo_ticket) {
+             int n, const ohp_cg_state *st, const ohp_p2p_dev pd, int n_halo_blocks, unsigned *halo_ticket, int wait_here) {
   pdl_wait();
   pdl_launch();
   if (st->done) return;
@@ -577,7 +581,7 @@ k_cg_pupdate(double *__restrict__ p0, double *__restrict__ p1, const double *__r
       if (s_last && threadIdx.x < pd.n_nbr) { /* every push of this rank has landed: publish, then wait for the neighbours */
         const int q = pd.nbr[threadIdx.x];
         st_release_sys(pd.hflags[q] + pd.rank, s_seq);
-        p2p_wait(pd.hflags[pd.rank] + q, s_seq, pd.seq + 2);
+        if (wait_here) p2p_wait(pd.hflags[pd.rank] + q, s_seq, pd.seq + 2);
       }
       return;
     }
@@ -647,7 +651,7 @@ __global__ void __launch_bounds__(256)
 k_cgcg_vec(double *R0, double *R1, double *U0, double *U1, double *S0, double *S1, double *__restrict__ p,
            const double *__restrict__ w, double *__restrict__ x, const double *__restrict__ b,
            const double *__restrict__ dinv, int n, const ohp_cg_state *st, double *vpart, const ohp_p2p_dev pd,
-           int n_halo_blocks, unsigned *halo_ticket) {
+           int n_halo_blocks, unsigned *halo_ticket, int wait_here) {
   pdl_wait();
   pdl_launch();
   if (st->done) return;
@@ -686,7 +690,7 @@ k_cgcg_vec(double *R0, double *R1, double *U0, double *U1, double *S0, double *S
       if (s_last && threadIdx.x < pd.n_nbr) {
         const int q = pd.nbr[threadIdx.x];
         st_release_sys(pd.hflags[q] + pd.rank, s_seq);
-        p2p_wait(pd.hflags[pd.rank] + q, s_seq, pd.seq + 2);
+        if (wait_here) p2p_wait(pd.hflags[pd.rank] + q, s_seq, pd.seq + 2);
       }
       return;
     }
@@ -787,6 +791,10 @@ static int cgcg_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o,
   double *vpart = ctx->d_partials + kMaxPartials; /* second half of the scratch: the SpMV uses the first */
   ohp_cgcg_epi epi;
   epi.vpart = vpart; epi.nvpart = vgrid; epi.jacobi = jac ? 1 : 0; epi.hist = hist; epi.hist_cap = hist_cap;
+  static const char *nooverlap = getenv("OHP_NOOVERLAP");
+  const bool overlap = p2p && spmv_use_tma(m) && m->ghost_cta && !nooverlap && !getenv("OHP_SPMV");
+  const int wait_in_vec = overlap ? 0 : 1;
+  epi.ghost_cta = overlap ? m->ghost_cta : nullptr;
   static const char *nopdl = getenv("OHP_NOPDL");
   const bool pdl = !nopdl;
   const int check_every = o->check_every > 0 ? o->check_every : 50;
@@ -797,11 +805,11 @@ static int cgcg_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o,
   for (;;) {
     for (int it = 0; it < check_every; ++it) {
       if (p2p) {
-        if (jac) OHP_CUDA(ohp_launch(k_cgcg_vec<OHP_MODE_P2P, true>, dim3(vgrid + nhalo), dim3(256), 0, st, pdl, R0, R1, U0, U1, A->s, A->s1, A->p, (const double *)A->w, x->d, (const double *)b->d, (const double *)A->dinv, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, nhalo, ctx->d_ticket + 2));
-        else OHP_CUDA(ohp_launch(k_cgcg_vec<OHP_MODE_P2P, false>, dim3(vgrid + nhalo), dim3(256), 0, st, pdl, R0, R1, U0, U1, A->s, A->s1, A->p, (const double *)A->w, x->d, (const double *)b->d, (const double *)A->dinv, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, nhalo, ctx->d_ticket + 2));
+        if (jac) OHP_CUDA(ohp_launch(k_cgcg_vec<OHP_MODE_P2P, true>, dim3(vgrid + nhalo), dim3(256), 0, st, pdl, R0, R1, U0, U1, A->s, A->s1, A->p, (const double *)A->w, x->d, (const double *)b->d, (const double *)A->dinv, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, nhalo, ctx->d_ticket + 2, wait_in_vec));
+        else OHP_CUDA(ohp_launch(k_cgcg_vec<OHP_MODE_P2P, false>, dim3(vgrid + nhalo), dim3(256), 0, st, pdl, R0, R1, U0, U1, A->s, A->s1, A->p, (const double *)A->w, x->d, (const double *)b->d, (const double *)A->dinv, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, nhalo, ctx->d_ticket + 2, wait_in_vec));
       } else {
-        if (jac) OHP_CUDA(ohp_launch(k_cgcg_vec<OHP_MODE_SERIAL, true>, dim3(vgrid), dim3(256), 0, st, pdl, R0, R1, U0, U1, A->s, A->s1, A->p, (const double *)A->w, x->d, (const double *)b->d, (const double *)A->dinv, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, 0, (unsigned *)nullptr));
-        else OHP_CUDA(ohp_launch(k_cgcg_vec<OHP_MODE_SERIAL, false>, dim3(vgrid), dim3(256), 0, st, pdl, R0, R1, U0, U1, A->s, A->s1, A->p, (const double *)A->w, x->d, (const double *)b->d, (const double *)A->dinv, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, 0, (unsigned *)nullptr));
+        if (jac) OHP_CUDA(ohp_launch(k_cgcg_vec<OHP_MODE_SERIAL, true>, dim3(vgrid), dim3(256), 0, st, pdl, R0, R1, U0, U1, A->s, A->s1, A->p, (const double *)A->w, x->d, (const double *)b->d, (const double *)A->dinv, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, 0, (unsigned *)nullptr, 1));
+        else OHP_CUDA(ohp_launch(k_cgcg_vec<OHP_MODE_SERIAL, false>, dim3(vgrid), dim3(256), 0, st, pdl, R0, R1, U0, U1, A->s, A->s1, A->p, (const double *)A->w, x->d, (const double *)b->d, (const double *)A->dinv, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, 0, (unsigned *)nullptr, 1));
       }
       ctx->launches++;
       OHP_TRY(spmv_enqueue(A, U0, A->w, ctx->d_cg, ctx->d_scalars, mode, U1, pd, epi));
@@ -908,6 +916,12 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
   const bool nccl = (mode == OHP_MODE_NCCL);
   static const char *nopdl = getenv("OHP_NOPDL"); /* A/B switch for programmatic dependent launch */
   const bool pdl = !nccl && !nopdl;
+  /* with the persistent TMA SpMV the halo wait moves into the SpMV's boundary CTAs (overlap); otherwise it stays here */
+  static const char *nooverlap = getenv("OHP_NOOVERLAP");
+  const bool overlap = p2p && spmv_use_tma(m) && m->ghost_cta && !nooverlap && !getenv("OHP_SPMV");
+  const int wait_in_vec = overlap ? 0 : 1;
+  ohp_cgcg_epi cepi = {};
+  cepi.ghost_cta = overlap ? m->ghost_cta : nullptr;
   const int nhalo = p2p ? std::max(1, std::min(16, (pd.soff[pd.n_nbr] + 255) / 256)) : 0;
   const int vgrid = vec_grid(ctx, n);
   double *sums = ctx->d_scalars;
@@ -934,8 +948,8 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
     if (ctx->h_cg->done) break;
     if (launched > o->max_it + check_every) OHP_FAIL(OHP_ERR_LIB, "ohp_ksp_cg: device-side iteration control did not terminate");
     for (int it = 0; it < check_every; ++it) {
-      if (p2p) OHP_CUDA(ohp_launch(k_cg_pupdate<OHP_MODE_P2P>, dim3(vgrid + nhalo), dim3(256), 0, st, pdl, P0, P1, z, x->d, n, ctx->d_cg, pd, nhalo, ctx->d_ticket + 2));
-      else OHP_CUDA(ohp_launch(k_cg_pupdate<OHP_MODE_SERIAL>, dim3(vgrid), dim3(256), 0, st, pdl, P0, P1, z, x->d, n, ctx->d_cg, pd, 0, (unsigned *)nullptr));
+      if (p2p) OHP_CUDA(ohp_launch(k_cg_pupdate<OHP_MODE_P2P>, dim3(vgrid + nhalo), dim3(256), 0, st, pdl, P0, P1, z, x->d, n, ctx->d_cg, pd, nhalo, ctx->d_ticket + 2, wait_in_vec));
+      else OHP_CUDA(ohp_launch(k_cg_pupdate<OHP_MODE_SERIAL>, dim3(vgrid), dim3(256), 0, st, pdl, P0, P1, z, x->d, n, ctx->d_cg, pd, 0, (unsigned *)nullptr, 1));
       OHP_CHECK_LAUNCH(ctx);
       if (nccl) {
         /* the host does not know the iteration parity on the device: exchange both buffers' tails is
@@ -944,7 +958,7 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
       }
       const bool timed = (int)prof.size() < 2 * nprof && (launched > 0 || o->max_it <= check_every);
       if (timed) { cudaEvent_t e; OHP_CUDA(cudaEventCreate(&e)); OHP_CUDA(cudaEventRecord(e, st)); prof.push_back(e); }
-      OHP_TRY(spmv_enqueue(A, P0, A->w, ctx->d_cg, sums, mode, P1, pd));
+      OHP_TRY(spmv_enqueue(A, P0, A->w, ctx->d_cg, sums, mode, P1, pd, cepi));
       if (timed) { cudaEvent_t e; OHP_CUDA(cudaEventCreate(&e)); OHP_CUDA(cudaEventRecord(e, st)); prof.push_back(e); }
       if (nccl) {
         OHP_TRY(ohp_allreduce_sum(ctx, sums, 1));
