@@ -22,7 +22,7 @@ def test_example_builds_with_user_callbacks_inlined():
     build()
     out = subprocess.run(["cuobjdump", "-elf", "-lelf", EXE], capture_output=True, text=True).stdout
     assert "sm_100a" in out
-    sym = subprocess.run("cuobjdump -symbols %s | grep -c ohp_problem_coeff_none" % EXE, shell=True, capture_output=True, text=True).stdout
+    sym = subprocess.run("cuobjdump -symbols %s | grep -c ohp_problem_constant" % EXE, shell=True, capture_output=True, text=True).stdout
     assert int(sym.strip() or 0) >= 2, "assembly kernels must be instantiated on the user's callback set"
 
 
