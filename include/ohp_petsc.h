@@ -251,7 +251,10 @@ inline PetscErrorCode PetscObjectSetName(PetscObject, const char *) { return 0; 
 inline PetscErrorCode DMPlexCreateFromCellListPetsc(MPI_Comm, PetscInt dim, PetscInt numCells, PetscInt numVertices,
                                                     PetscInt numCorners, PetscBool /*interpolate*/, const PetscInt cells[],
                                                     PetscInt spaceDim, const PetscReal vertexCoords[], DM *dm) {
-  if (numCorners != dim + 1 || spaceDim != dim) { ohp_last_error(); return PETSC_ERR_SUP; }
+  if (numCorners != dim + 1 || spaceDim != dim) {
+    fprintf(stderr, "[0]PETSC ERROR: DMPlexCreateFromCellListPetsc: only simplices with spaceDim == dim are built\n");
+    return PETSC_ERR_SUP;
+  }
   DM d = new _p_DM();
   d->dim = dim;
   d->sf.dm = d;
