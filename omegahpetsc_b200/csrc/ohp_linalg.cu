@@ -151,8 +151,8 @@ k_spmv_stream(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ co
 /* A row that straddles a tile boundary is carried in a register by the thread that       */
 /* started it (same thread finishes it in the next tile), so the order stays serial.      */
 /* ------------------------------------------------------------------------------------ */
-template <bool CG, int kTmaStages, int kTmaConsumers, class IDX, bool SPLIT>
-__global__ void __launch_bounds__(kTmaConsumers + 32, 1)
+template <bool CG, int kTmaStages, int kTmaConsumers, class IDX, bool SPLIT, int MINB = 1>
+__global__ void __launch_bounds__(kTmaConsumers + 32, MINB)
 k_spmv_tma(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colidx, const double *__restrict__ vals,
            const double *__restrict__ x, double *__restrict__ y, const int32_t *__restrict__ tile_row, int n_tiles,
            ohp_cg_state *st, double *partials, unsigned *ticket, double *sums, int mode,
@@ -282,7 +282,7 @@ static int spmv_configure(ohp_mesh m) {
   return 0;
 }
 
-template <int S, int NC, class IDX, bool SPLIT>
+template <int S, int NC, class IDX, bool SPLIT, int MINB = 1>
 static int spmv_tma_launch_ts(ohp_mat A, const IDX *cols, const double *x, double *y, ohp_cg_state *st, double *sums, int mode,
                               const double *x_alt, const ohp_p2p_dev &pd, const ohp_cgcg_epi &epi) {
   ohp_mesh m = A->mesh;
@@ -290,17 +290,17 @@ static int spmv_tma_launch_ts(ohp_mat A, const IDX *cols, const double *x, doubl
   constexpr int smem = tma_smem_bytes(S, (int)sizeof(IDX));
   static bool configured = false;
   if (!configured) {
-    OHP_CUDA(cudaFuncSetAttribute(k_spmv_tma<true, S, NC, IDX, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    OHP_CUDA(cudaFuncSetAttribute(k_spmv_tma<false, S, NC, IDX, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    OHP_CUDA(cudaFuncSetAttribute(k_spmv_tma<true, S, NC, IDX, SPLIT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    OHP_CUDA(cudaFuncSetAttribute(k_spmv_tma<false, S, NC, IDX, SPLIT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  const int grid = std::max(1, std::min(m->n_tiles, ctx->num_sms));
+  const int grid = std::max(1, std::min(m->n_tiles, ctx->num_sms * MINB));
   if (st) {
     static const char *nopdl = getenv("OHP_NOPDL");
-    OHP_CUDA(ohp_launch(k_spmv_tma<true, S, NC, IDX, SPLIT>, dim3(grid), dim3(NC + 32), (size_t)smem, ctx->stream, mode != OHP_MODE_NCCL && !nopdl,
+    OHP_CUDA(ohp_launch(k_spmv_tma<true, S, NC, IDX, SPLIT, MINB>, dim3(grid), dim3(NC + 32), (size_t)smem, ctx->stream, mode != OHP_MODE_NCCL && !nopdl,
                         m->rowptr, cols, A->vals, x, y, m->tile_row, m->n_tiles, st, ctx->d_partials, ctx->d_ticket + 1, sums, mode, x_alt, pd, epi));
   }
-  else k_spmv_tma<false, S, NC, IDX, SPLIT><<<grid, NC + 32, smem, ctx->stream>>>(
+  else k_spmv_tma<false, S, NC, IDX, SPLIT, MINB><<<grid, NC + 32, smem, ctx->stream>>>(
       m->rowptr, cols, A->vals, x, y, m->tile_row, m->n_tiles, nullptr, nullptr, nullptr, nullptr, 0, nullptr, pd, epi);
   OHP_CHECK_LAUNCH(ctx);
   return 0;
@@ -332,6 +332,9 @@ static int spmv_enqueue(ohp_mat A, const double *x, double *y, ohp_cg_state *st,
   if (tma) {
     const int cfg = (force && force[0] >= '0' && force[0] <= '9') ? force[0] - '0' : 0;
     switch (cfg) {
+      /* 4, 5: two CTAs per SM with two stages -- measured slower (0.151 / 0.177 ms vs 0.146 on the 16 M box), kept for A/B */
+      case 4: if (m->col16 && ctx->nranks == 1) return spmv_tma_launch_ts<2, 352, int16_t, false, 2>(A, m->col16, x, y, st, sums, mode, x_alt, pd, epi); break;
+      case 5: if (m->col16 && ctx->nranks == 1) return spmv_tma_launch_ts<2, 288, int16_t, false, 2>(A, m->col16, x, y, st, sums, mode, x_alt, pd, epi); break;
       case 1: return spmv_tma_launch<3, 384>(A, x, y, st, sums, mode, x_alt, pd, epi);
       case 2: return spmv_tma_launch<3, 768>(A, x, y, st, sums, mode, x_alt, pd, epi);
       case 3: return spmv_tma_launch<2, 640>(A, x, y, st, sums, mode, x_alt, pd, epi);
