@@ -207,18 +207,61 @@ def edges_from_tris(tris):
     return ev, te, codes
 
 
+def faces_from_tets(tets):
+    """Build tri->vert (stored faces), tet->tri and alignment codes for tetrahedra so that the reader's
+    derivation (faces 0 = (0,2,1), 1 = (0,1,3), 2 = (1,2,3), 3 = (2,0,3) of the simplex down template;
+    code bit 0 = flip, bits 1-2 = rotation) reproduces `tets` exactly.  A face is stored with the vertex
+    order of its first use; every later use gets the (rotation, flip) that maps the stored triple onto it."""
+    tets = np.asarray(tets, dtype=np.int64)
+    template = ((0, 2, 1), (0, 1, 3), (1, 2, 3), (2, 0, 3))
+    faces, index = [], {}
+    tt = np.empty((tets.shape[0], 4), dtype=np.int32)
+    cc = np.empty((tets.shape[0], 4), dtype=np.int8)
+    for t, tet in enumerate(tets):
+        for f, tpl in enumerate(template):
+            used = tuple(int(tet[i]) for i in tpl)
+            key = tuple(sorted(used))
+            if key not in index:
+                index[key] = len(faces)
+                faces.append(used)
+            fid = index[key]
+            stored = faces[fid]
+            code = None
+            for flip in (0, 1):
+                for r in range(3):
+                    out = [stored[(k + 3 - r) % 3] for k in range(3)]
+                    if flip:
+                        out[1], out[2] = out[2], out[1]
+                    if tuple(out) == used:
+                        code = (r << 1) | flip
+                        break
+                if code is not None:
+                    break
+            assert code is not None
+            tt[t, f] = fid
+            cc[t, f] = code
+    return np.asarray(faces, dtype=np.int32), tt, cc
+
+
 def write_osh(path, dim, coords_arr, elems, tags=None, rank=0, nparts=1):
-    """Write a serial `.osh` directory (version 9) for a triangle mesh (dim=2).
+    """Write a serial `.osh` directory (version 9) for a triangle (dim=2) or tetrahedron (dim=3) mesh.
     `tags` = {d: {name: (ncomps, array)}} adds extra tags."""
-    if dim != 2:
-        raise NotImplementedError("oracle writer covers triangles; 3-D inputs go through cell lists")
+    if dim not in (2, 3):
+        raise NotImplementedError("oracle writer covers triangles and tetrahedra")
     os.makedirs(path, exist_ok=True)
-    ev, te, codes = edges_from_tris(elems)
+    tt = cc = None
+    tris = elems
+    if dim == 3:
+        tris, tt, cc = faces_from_tets(elems)
+    ev, te, codes = edges_from_tris(tris)
     nverts = int(np.asarray(coords_arr).reshape(-1, dim).shape[0])
     out = [MAGIC, struct.pack("<bbbiibib", 1, 0, dim, 1, 0, 0, 0, 0), struct.pack("<i", nverts)]
     _w_array(out, ev.reshape(-1), "<i4")
     _w_array(out, te.reshape(-1), "<i4")
     _w_array(out, codes.reshape(-1), "<i1")
+    if dim == 3:
+        _w_array(out, tt.reshape(-1), "<i4")
+        _w_array(out, cc.reshape(-1), "<i1")
     tags = tags or {}
     for d in range(dim + 1):
         dt = dict(tags.get(d, {}))
