@@ -124,7 +124,7 @@ int ohp_picpart_extract(ohp_context ctx, int dim, int rank, int with_overlap, in
 /* ------------------------------------------------------------------------------------ */
 int ohp_mesh_create(ohp_context ctx, int dim, int32_t n_cells, int32_t n_verts,
                     const int32_t *cells, const double *coords, ohp_mesh *mesh);
-int ohp_mesh_destroy(ohp_mesh mesh);
+int ohp_mesh_destroy(ohp_mesh mesh); /* collective once ohp_mesh_p2p_attach was called (DMDestroy of a parallel DM) */
 
 /* PetscSFSetGraph on the DM's point SF (ex12.cpp:873-876, 937-939): leaf i = local vertex
  * ghost_vertex[i] (0-based VERTEX index, i.e. Plex point minus nC), root = vertex

@@ -353,10 +353,19 @@ int ohp_halo_build(ohp_mesh m) {
 /* ------------------------------------------------------------------------------------ */
 /* NVLink peer-to-peer mapping (CUDA IPC between the per-GPU processes)                  */
 /* ------------------------------------------------------------------------------------ */
-void ohp_p2p_free(ohp_p2p *p) {
+/* Collective when the heap was attached: an exporter must not free memory a peer still maps (CUDA IPC),
+ * so every rank first closes its mappings, then all ranks meet (a 1-element all-reduce as the barrier), then
+ * each frees its own heap.  ohp_mesh_destroy therefore has to be called by all ranks, like DMDestroy on a
+ * parallel DM. */
+void ohp_p2p_free(ohp_context ctx, ohp_p2p *p) {
   if (!p) return;
   for (int q = 0; q < kMaxRanks; ++q)
     if (p->peer[q] && p->peer[q] != p->heap) cudaIpcCloseMemHandle(p->peer[q]);
+  if (p->attached && ctx->comm && ctx->nranks > 1) {
+    cudaMemsetAsync(ctx->d_scalars + 8, 0, sizeof(double), ctx->stream);
+    g_nccl.AllReduce(ctx->d_scalars + 8, ctx->d_scalars + 8, 1, ncclFloat64, ncclSum, (ncclComm_t)ctx->comm, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+  }
   cudaFree(p->heap);
   delete p;
 }

@@ -258,7 +258,7 @@ extern "C" int ohp_mesh_destroy(ohp_mesh m) {
   cudaFree(m->bnd); cudaFree(m->lidx); cudaFree(m->row_vertex); cudaFree(m->ldof_gid); cudaFree(m->rowptr);
   cudaFree(m->colidx); cudaFree(m->col16); cudaFree(m->slot); cudaFree(m->tile_row);
   ohp_halo_free(m->halo);
-  ohp_p2p_free(m->p2p);
+  ohp_p2p_free(m->ctx, m->p2p);
   cudaFree(m->ghost_cta);
   delete m;
   return 0;

@@ -167,7 +167,7 @@ int ohp_allreduce_sum(ohp_context ctx, double *d_vals, int n);
 int ohp_vertex_halo_i32(ohp_mesh mesh, int32_t *vertex_data_dev);
 int ohp_allgather_i64(ohp_context ctx, int64_t mine, std::vector<int64_t> &all);
 void ohp_comm_destroy(ohp_context ctx);
-void ohp_p2p_free(ohp_p2p *p);
+void ohp_p2p_free(ohp_context ctx, ohp_p2p *p);
 
 /* ohp_linalg.cu */
 int ohp_spmv_launch(ohp_mat A, const double *x, double *y);
