@@ -397,6 +397,13 @@ class Mesh:
         overt = np.ascontiguousarray(owner_vertex, dtype=np.int32)
         _chk(lib().ohp_mesh_set_ghosts(self.h, gv.size, _ptr(gv, _i32p), _ptr(orank, _i32p), _ptr(overt, _i32p)))
 
+    def set_point_sf(self, leaf_point, root_rank, root_point):
+        """The same graph in Plex POINT numbers, exactly as ex12 passes it (ex12.cpp:867-871,924-926)."""
+        lp = np.ascontiguousarray(leaf_point, dtype=np.int32)
+        rr = np.ascontiguousarray(root_rank, dtype=np.int32)
+        rp = np.ascontiguousarray(root_point, dtype=np.int32)
+        _chk(lib().ohp_mesh_set_point_sf(self.h, lp.size, _ptr(lp, _i32p), _ptr(rr, _i32p), _ptr(rp, _i32p)))
+
     def setup(self):
         _chk(lib().ohp_mesh_setup(self.h))
         self._info = None

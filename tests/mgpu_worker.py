@@ -80,8 +80,15 @@ def main():
         cells, coords, eo, vo = load(name, world)
         part = partition.local_part(cells, coords, eo, vo, rank)
         m = ohp.Mesh(ctx, part["cells"], part["coords"])
-        m.set_ghosts(part["ghost_local"], part["ghost_owner"],
-                     partition.resolve_ghost_roots(part, vo, rank, world, dist.all_gather_object))
+        roots = partition.resolve_ghost_roots(part, vo, rank, world, dist.all_gather_object)
+        if name.startswith("box3d"):
+            # the Plex-point form of the SF, as ex12 builds it: leaf = nCells + vertex, root = owner's nCells + its vertex
+            ncs = [None] * world
+            dist.all_gather_object(ncs, int(part["cells"].shape[0]))
+            m.set_point_sf(part["cells"].shape[0] + part["ghost_local"], part["ghost_owner"],
+                           np.asarray(ncs)[part["ghost_owner"]] + roots)
+        else:
+            m.set_ghosts(part["ghost_local"], part["ghost_owner"], roots)
     m.setup()
     if os.environ.get("OHP_COMM", "p2p") != "nccl":
         m.p2p_enable(dist.all_gather_object, world)
