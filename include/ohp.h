@@ -178,7 +178,9 @@ int ohp_mesh_get_coords(ohp_mesh mesh, double *coords);
 int ohp_mesh_get_boundary(ohp_mesh mesh, uint8_t *bnd);
 /* global section: gidx[v] = global dof of vertex v, -1 if constrained; n_verts int64 */
 int ohp_mesh_get_numbering(ohp_mesh mesh, int64_t *gidx);
-/* CSR pattern: rowptr[n_owned+1]; colidx[nnz] in GLOBAL dof numbers, ascending per row */
+/* CSR pattern: rowptr[n_owned+1]; colidx[nnz] in GLOBAL dof numbers.  Serial: ascending per row (PETSc's AIJ
+ * order).  Partitioned: per row the owned (diagonal-block) columns ascending, then the ghost (off-diagonal-block)
+ * columns ascending, the MPIAIJ layout. */
 int ohp_mesh_get_csr(ohp_mesh mesh, int32_t *rowptr, int64_t *colidx);
 
 /* ------------------------------------------------------------------------------------ */
