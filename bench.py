@@ -349,7 +349,7 @@ def run_ours(args):
                 "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                 "bytes_per_launch": ab["spmv"], "ms_per_launch": spmv_ms, "launches_timed": int(res["spmv_samples"])}
         tr = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tr):
+        if os.path.exists(tr) and world == 1 and not args.n:  # the ncu capture is of the full matrix on one GPU
             with open(tr) as f:
                 roof["traffic"] = json.load(f).get("%s:spmv" % args.workload)
     its_step = phase["ksp_its"] / args.steps
