@@ -71,6 +71,20 @@ int ohp_comm_unique_id(void *unique_id128);
 int ohp_comm_init(ohp_context ctx, int nranks, int rank, const void *unique_id128);
 int ohp_comm_rank_size(ohp_context ctx, int *rank, int *nranks);
 
+/* MPI-free start-up (this image has no MPI; PetscInitialize -> MPI_Init, ex12.cpp:1485).  ohp_boot_env reads rank,
+ * size and local rank from the launcher's environment (RANK / WORLD_SIZE / LOCAL_RANK of torch.distributed.run;
+ * OMPI_*, PMI_*, SLURM_* as fall-backs).  ohp_boot_bcast sends `bytes` bytes from rank 0 to every rank over TCP
+ * at MASTER_ADDR, port OHP_BOOT_PORT (default MASTER_PORT + 307): the one exchange needed before NCCL exists.
+ * ohp_comm_init_from_env = both, applied to the ncclUniqueId, then ohp_comm_init. */
+int ohp_boot_env(int *rank, int *nranks, int *local_rank);
+int ohp_boot_bcast(int rank, int nranks, void *buf, int bytes);
+int ohp_comm_init_from_env(ohp_context ctx);
+/* MPI_Barrier (ex12.cpp:573,575,814,953,978), MPI_Allgather of one count per rank (the element counts that
+ * getNeighborElmCounts exchanges, ex12.cpp:528-577), MPI_Allreduce(SUM) of integers (ex12.cpp:844) */
+int ohp_comm_barrier(ohp_context ctx);
+int ohp_comm_allgather_i64(ohp_context ctx, int64_t mine, int64_t *all /* nranks */);
+int ohp_comm_allreduce_sum_i64(ohp_context ctx, int64_t *vals, int n);
+
 /* ------------------------------------------------------------------------------------ */
 /* `.osh` loading -- Omega_h::binary::read (ex12.cpp:813,818) + Mesh::ask_elem_verts     */
 /* (ex12.cpp:591,634,784) + mesh.coords() / get_array<>(dim,name) (ex12.cpp:593-594,     */
@@ -117,6 +131,17 @@ int ohp_picpart_extract(ohp_context ctx, int dim, int rank, int with_overlap, in
                         int32_t *ghost_owner /* n_verts cap */,
                         int64_t *core_gid /* n_verts cap */);
 
+/* The rest of getPicPartCoreVtxOwnerIdx (ex12.cpp:731-777): for every ghost vertex, the index it has in
+ * its OWNER's vertex array.  Restates the gid round trip of the reference -- ghosts' gids to the owners
+ * (Dist::exch, :740), findIdxOfGid on the owner (K6, :748-761, here a hash join on the device instead of the
+ * O(n_verts x n_ghosts) search), indices back (distInv.exch, :765) -- over the NCCL communicator.
+ * `core_gid[n_core]` are the global ids of THIS rank's vertex array (the one given to ohp_mesh_create),
+ * `core_owned[n_core]` flags the vertices this rank owns (NULL = all of them are entered in the join table).  roots[i] = index of ghost i in rank ghost_owner[i]'s array; add the owner's cell count
+ * to get the Plex point ex12 stores (:757) or hand the indices to ohp_mesh_set_ghosts as they are.
+ * Collective; every rank returns the same error code when any rank finds an inconsistency. */
+int ohp_ghost_roots_from_gids(ohp_context ctx, int32_t n_ghost, const int64_t *ghost_gid, const int32_t *ghost_owner,
+                              int32_t n_core, const int64_t *core_gid, const uint8_t *core_owned, int32_t *roots);
+
 /* ------------------------------------------------------------------------------------ */
 /* DM.  ohp_mesh_create = DMPlexCreateFromCellListPetsc(comm,dim,nC,nV,nCorners,interp,  */
 /* cells,spaceDim,coords,&dm) (ex12.cpp:859,933): cells and coords are COPIED (to HBM).  */
@@ -150,6 +175,20 @@ int ohp_mesh_set_point_sf(ohp_mesh mesh, int32_t n_leaves, const int32_t *leaf_p
  * Collective when a communicator is attached. */
 int ohp_mesh_setup(ohp_mesh mesh);
 
+/* Plex queries for callers that walk the interpolated mesh themselves, as CreateQuadMesh does between
+ * DMPlexInterpolate and the solve (ex12.cpp:958-1033).  Facets are the points DMPlexInterpolate creates between
+ * cells and vertices: edges in 2-D (Plex points [nC+nV, nC+nV+nF)), triangles in 3-D.  Built on the device on first
+ * use (support counted inside vertex stars), numbered by creating cell and local facet like PETSc's interpolation.
+ *   facet_verts[(dim)*nF]      cone of each facet as 0-based vertex indices      (DMPlexGetCone,        ex12.cpp:1006)
+ *   support[nF]                number of cells on each facet                      (DMPlexGetSupportSize, ex12.cpp:990)
+ *   cell_facets[(dim+1)*nC]    cone of each cell as 0-based facet indices         (may be NULL)
+ * ohp_mesh_set_label = the caller's DMSetLabelValue(dm,"marker",nC+v,1) loop (ex12.cpp:1023-1026): when given,
+ * the library uses this label for the vertices the rank owns instead of detecting the boundary itself (ghost
+ * vertices still take the label from their owner, so an incomplete local star cannot mislabel them). */
+int ohp_mesh_build_facets(ohp_mesh mesh, int32_t *n_facets);
+int ohp_mesh_get_facets(ohp_mesh mesh, int32_t *facet_verts, int32_t *support, int32_t *cell_facets);
+int ohp_mesh_set_label(ohp_mesh mesh, int32_t n, const int32_t *vertices);
+
 typedef struct {
   int32_t dim, n_cells, n_verts;
   int32_t n_boundary_verts; /* vertices labelled "marker"=1                              */
@@ -170,6 +209,8 @@ int ohp_mesh_get_info(ohp_mesh mesh, ohp_mesh_info *info);
  * Plays the role PETSc's PetscSF/VecScatter + MPI_Allreduce play under SNESSolve (ex12.cpp:1609). */
 int ohp_mesh_p2p_export(ohp_mesh mesh, void *handle64);
 int ohp_mesh_p2p_attach(ohp_mesh mesh, const void *handles /* nranks x 64 bytes */);
+/* the same in one collective call: the handles are all-gathered over the communicator itself */
+int ohp_mesh_p2p_enable(ohp_mesh mesh);
 
 /* the DM's copy of the cell list ((dim+1)*n_cells int32) and coordinates (dim*n_verts doubles), for viewers */
 int ohp_mesh_get_cells(ohp_mesh mesh, int32_t *cells);
@@ -189,11 +230,16 @@ int ohp_mesh_get_csr(ohp_mesh mesh, int32_t *rowptr, int64_t *colidx);
 /*   OHP_PROBLEM_COEFF_NONE : f0_u, f1_u, g3_uu            (ex12.cpp:147,198,209)          */
 /*   OHP_PROBLEM_ANALYTIC   : f0/f1/g3_analytic_u          (ex12.cpp:283,292,313)          */
 /*   OHP_PROBLEM_NONLINEAR  : f0/f1/g3_analytic_nonlinear_u (ex12.cpp:341,350,369)         */
-/* Dirichlet / exact data: quadratic_u_2d / quadratic_u_3d (ex12.cpp:113,408).           */
+/*   OHP_PROBLEM_CIRCLE/CROSS : f0_circle_u / f0_cross_u, -bc_type dirichlet with           */
+/*                              -variable_coefficient circle|cross (ex12.cpp:155-177,1185-1204) */
+/* Dirichlet / exact data: quadratic_u_2d / quadratic_u_3d (ex12.cpp:113,408); circle_u_2d /  */
+/* cross_u_2d for the last two (ex12.cpp:127-145,1222-1225).                                */
 /* User callbacks compiled by nvcc are registered through ohp_problem_register (see      */
 /* include/ohp_petsc.h, which turns PetscDSSetResidual/Jacobian into this call).         */
 /* ------------------------------------------------------------------------------------ */
-enum { OHP_PROBLEM_COEFF_NONE = 0, OHP_PROBLEM_ANALYTIC = 1, OHP_PROBLEM_NONLINEAR = 2 };
+enum { OHP_PROBLEM_COEFF_NONE = 0, OHP_PROBLEM_ANALYTIC = 1, OHP_PROBLEM_NONLINEAR = 2,
+       OHP_PROBLEM_CIRCLE = 3,   /* f0_circle_u (ex12.cpp:155-166) with f1_u, g3_uu; Dirichlet/exact circle_u_2d (:127-136) */
+       OHP_PROBLEM_CROSS = 4 };  /* f0_cross_u (ex12.cpp:168-177) with f1_u, g3_uu; Dirichlet/exact cross_u_2d (:138-145) */
 
 /* device view handed to registered assembly launchers (all pointers are DEVICE pointers) */
 typedef struct {
@@ -207,13 +253,18 @@ typedef struct {
   const uint8_t *slot_dev;     /* (dim+1) per v2c entry: column slot within the row, 255 = constrained */
   const int32_t *rowptr_dev;   /* n_rows+1                                              */
   const double *u_dev;         /* local solution: n_rows owned + ghost dofs             */
-  double *out_dev;             /* residual: F[n_rows]; Jacobian: vals[nnz]              */
+  double *out_dev;             /* residual: F[n_rows]; Jacobian: vals[nnz]; projection: u[n_rows]; L2 diff: partial sums */
   void *stream;                /* cudaStream_t                                          */
+  const uint8_t *owned_dev;    /* n_verts: 1 if this rank owns the vertex               */
+  int32_t n_partials;          /* L2 diff: out_dev receives this many per-block partial sums of the squared error */
 } ohp_assembly_view;
 
 typedef int (*ohp_assembly_launcher)(const ohp_assembly_view *view);
+/* `project_exact` and `l2_diff` may be NULL (the problem then has no exact solution to project / compare with) */
 int ohp_problem_register(ohp_assembly_launcher residual, ohp_assembly_launcher jacobian,
-                         ohp_assembly_launcher project_exact, int *problem_id);
+                         ohp_assembly_launcher project_exact, ohp_assembly_launcher l2_diff, int *problem_id);
+/* DMProjectFunction of an arbitrary point function compiled for the device (ohp::launch_project_fn<F>) */
+int ohp_project_function(ohp_mesh mesh, ohp_assembly_launcher project, ohp_vec u);
 
 /* ------------------------------------------------------------------------------------ */
 /* Vec (VecCreate via DMCreateGlobalVector ex12.cpp:1505; VecSet/AXPY/Norm/Chop/Duplicate */
@@ -284,10 +335,17 @@ int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *opts, ohp
 /* SNES newtonls + bt (PETSc-internal SNESSolve_NEWTONLS reached from SNESSolve          */
 /* ex12.cpp:1609)                                                                        */
 /* ------------------------------------------------------------------------------------ */
+/* -snes_monitor / -ksp_monitor (CMakeLists.txt:56-57): called on the host, after Newton iteration `it` produced
+ * ||F|| = fnorm, and after the linear solve of Newton iteration `it` with the n+1 monitored norms of its CG run */
+typedef void (*ohp_snes_monitor_fn)(void *ctx, int32_t it, double fnorm);
+typedef void (*ohp_ksp_monitor_fn)(void *ctx, int32_t newton_it, int32_t n, const double *rnorm, int32_t reason);
 typedef struct {
   double rtol, abstol, stol; /* -snes_rtol 1e-8 -snes_atol 1e-50 -snes_stol 1e-8 */
   int32_t max_it;            /* -snes_max_it 50 */
   ohp_ksp_options ksp;
+  ohp_snes_monitor_fn snes_monitor; /* may be NULL */
+  ohp_ksp_monitor_fn ksp_monitor;   /* may be NULL; when set the CG history is recorded on the device and copied back per solve */
+  void *monitor_ctx;
 } ohp_snes_options;
 typedef struct {
   int32_t its;          /* Newton iterations */

@@ -366,6 +366,58 @@ template <int DIM, class P> __global__ void k_project_exact(const ohp_assembly_v
   vw.out_dev[r] = val;
 }
 
+/* DMProjectFunction of any point function F::eval(dim, time, x, Nc, u, ctx) compiled for the device */
+template <int DIM, class F> __global__ void k_project_fn(const ohp_assembly_view vw) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= vw.n_rows) return;
+  const int v = __ldg(vw.row_vertex_dev + r);
+  double x[DIM], val = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) x[d] = __ldg(vw.coords_dev + (size_t)v * DIM + d);
+  F::eval(DIM, 0.0, x, 1, &val, nullptr);
+  vw.out_dev[r] = val;
+}
+
+/* DMComputeL2Diff [PETSc-internal, reached from ex12.cpp:1611,1637]: sum_c sum_q w_q |detJ| (u_h - u_exact)^2 with the
+ * problem's own exact solution and the assembly quadrature; one partial sum per block, added in block order by the
+ * host (deterministic).  Partitioned meshes overlap by one layer of cells: a cell is integrated by the rank that
+ * owns its first corner. */
+template <int DIM, class P>
+__global__ void __launch_bounds__(256) k_l2_diff(const ohp_assembly_view vw) {
+  constexpr int NC = DIM + 1;
+  double acc = 0.0;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < vw.n_cells; c += gridDim.x * blockDim.x) {
+    if (!vw.owned_dev[vw.cells_dev[(size_t)c * NC]]) continue;
+    int cv[NC];
+    double X[NC][DIM], ue[NC];
+    load_cell<DIM, P, true>(vw, c, cv, X, ue);
+    CellGeom<DIM> g;
+    cell_geometry<DIM>(X, g);
+    for (int q = 0; q < Quadrature<DIM>::NQ; ++q) {
+      double phi[NC], xq[DIM], uq = 0.0, ex = 0.0;
+      p1_basis<DIM>(q, phi);
+      for (int d = 0; d < DIM; ++d) {
+        double s = g.v0[d];
+        for (int f = 0; f < DIM; ++f) s += g.J[d * DIM + f] * (Quadrature<DIM>::xi(q, f) + 1.0);
+        xq[d] = s;
+      }
+      for (int j = 0; j < NC; ++j) uq += phi[j] * ue[j];
+      P::exact(DIM, 0.0, xq, 1, &ex, nullptr);
+      acc += Quadrature<DIM>::w(q) * fabs(g.detJ) * (uq - ex) * (uq - ex);
+    }
+  }
+  __shared__ double red[8];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    vw.out_dev[blockIdx.x] = t;
+  }
+}
+
 template <int DIM, class P> int launch_residual(const ohp_assembly_view *vw) {
   if (vw->n_rows <= 0) return 0;
   const int bs = 128;
@@ -382,6 +434,23 @@ template <int DIM, class P> int launch_project_exact(const ohp_assembly_view *vw
   if (vw->n_rows <= 0) return 0;
   const int bs = 256;
   k_project_exact<DIM, P><<<(vw->n_rows + bs - 1) / bs, bs, 0, (cudaStream_t)vw->stream>>>(*vw);
+  return cudaGetLastError() == cudaSuccess ? 0 : OHP_ERR_LIB;
+}
+
+template <int DIM, class P> int launch_l2_diff(const ohp_assembly_view *vw) {
+  if (vw->n_partials <= 0) return OHP_ERR_ARG_SIZ;
+  k_l2_diff<DIM, P><<<vw->n_partials, 256, 0, (cudaStream_t)vw->stream>>>(*vw);
+  return cudaGetLastError() == cudaSuccess ? 0 : OHP_ERR_LIB;
+}
+template <class P> int launch_l2_diff_any(const ohp_assembly_view *vw) {
+  return vw->dim == 2 ? launch_l2_diff<2, P>(vw) : vw->dim == 3 ? launch_l2_diff<3, P>(vw) : OHP_ERR_SUP;
+}
+template <class F> int launch_project_fn(const ohp_assembly_view *vw) {
+  if (vw->n_rows <= 0) return 0;
+  const int bs = 256, grid = (vw->n_rows + bs - 1) / bs;
+  if (vw->dim == 2) k_project_fn<2, F><<<grid, bs, 0, (cudaStream_t)vw->stream>>>(*vw);
+  else if (vw->dim == 3) k_project_fn<3, F><<<grid, bs, 0, (cudaStream_t)vw->stream>>>(*vw);
+  else return OHP_ERR_SUP;
   return cudaGetLastError() == cudaSuccess ? 0 : OHP_ERR_LIB;
 }
 

@@ -53,6 +53,14 @@ typedef enum { PETSC_FALSE, PETSC_TRUE } PetscBool;
 typedef int MPI_Comm;
 #define PETSC_COMM_WORLD 0
 #define PETSC_COMM_SELF 1
+#ifndef MPI_COMM_WORLD
+#define MPI_COMM_WORLD PETSC_COMM_WORLD
+#define MPI_COMM_SELF PETSC_COMM_SELF
+typedef int MPI_Datatype;
+typedef int MPI_Op;
+#define MPI_INT 1
+#define MPI_SUM 1
+#endif
 #define PETSC_DEFAULT (-2)
 #define PETSC_ERR_SUP OHP_ERR_SUP
 #define PETSC_ERR_ARG_WRONG OHP_ERR_ARG_WRONG
@@ -109,10 +117,14 @@ struct ProblemKey {
 struct ProblemRecord { int id; void *exact; };
 inline std::map<ProblemKey, ProblemRecord> &problem_registry() { static std::map<ProblemKey, ProblemRecord> r; return r; }
 
+/* point functions compiled for the device so that DMProjectFunction can evaluate them at the vertices */
+inline std::map<void *, ohp_assembly_launcher> &function_registry() { static std::map<void *, ohp_assembly_launcher> r; return r; }
+
 #ifdef __CUDACC__
+template <class F> int register_function(void *fn) { function_registry()[fn] = launch_project_fn<F>; return 0; }
 template <class P> int register_problem(void *f0, void *f1, void *g3, void *bc, void *exact) {
   int id = -1;
-  if (ohp_problem_register(launch_residual_any<P>, launch_jacobian_any<P>, launch_project_exact_any<P>, &id)) return -1;
+  if (ohp_problem_register(launch_residual_any<P>, launch_jacobian_any<P>, launch_project_exact_any<P>, launch_l2_diff_any<P>, &id)) return -1;
   problem_registry()[ProblemKey{f0, f1, g3, bc}] = ProblemRecord{id, exact};
   return id;
 }
@@ -144,6 +156,15 @@ template <class P> int register_problem(void *f0, void *f1, void *g3, void *bc, 
       (void *)(PetscPointFunc)F0, (void *)(PetscPointFunc)F1, (void *)(PetscPointJac)G3,                        \
       (void *)(PetscSimplePointFunc)BC, (void *)(PetscSimplePointFunc)EXACT);
 
+/* Makes a PetscSimplePointFunc (initial guess, any function handed to DMProjectFunction) available on the device */
+#define OHP_DEFINE_FUNCTION(name, FN)                                                                           \
+  struct ohp_function_##name {                                                                                  \
+    OHP_HD static int eval(int dim, double time, const double x[], int Nc, double *u, void *ctx) {              \
+      return FN(dim, time, x, Nc, u, ctx);                                                                      \
+    }                                                                                                           \
+  };                                                                                                            \
+  static const int ohp_function_id_##name = ohp::register_function<ohp_function_##name>((void *)(PetscSimplePointFunc)FN);
+
 /* ------------------------------------------------------------------------------------------------ */
 /* objects                                                                                          */
 /* ------------------------------------------------------------------------------------------------ */
@@ -163,6 +184,14 @@ struct _p_DM {
   ohp_mesh mesh = nullptr;
   int refs = 1;
   bool set_up = false;
+  PetscInt nC = 0, nV = 0;
+  /* Plex queries (ex12.cpp:966-1010): host copies of the facets, fetched once */
+  bool facets = false;
+  PetscInt nF = 0;
+  std::vector<PetscInt> facet_cone, facet_support, cell_cone; /* cones as Plex POINT numbers */
+  /* DMSetLabelValue("marker", vertex point, 1) calls (ex12.cpp:1023-1026) */
+  bool label_by_caller = false;
+  std::vector<PetscInt> label_verts;
   void *app_ctx = nullptr;
   _p_PetscSF sf;
   _p_PetscDS ds;
@@ -180,6 +209,7 @@ struct _p_SNES {
   ohp_snes_result last;
   bool monitor = false, ksp_monitor = false, converged_reason = false, ksp_converged_reason = false;
   std::string ksp_type = "cg";
+  int last_ksp_reason = 0, last_ksp_its = 0;
 };
 typedef _p_DM *DM;
 typedef _p_Vec *Vec;
@@ -192,7 +222,32 @@ typedef _p_DMLabel *DMLabel;
 typedef void *PetscObject;
 typedef struct _p_MatNullSpace *MatNullSpace;
 
+/* ---- the few MPI calls of the adapter (ex12.cpp:573-575,800-801,814,844,953,978), over the library's communicator ---- */
+inline int MPI_Comm_rank(MPI_Comm comm, int *rank) {
+  int r = 0, n = 1;
+  if (comm == PETSC_COMM_WORLD && ohp::global_context()) ohp_comm_rank_size(ohp::global_context(), &r, &n);
+  *rank = r;
+  return 0;
+}
+inline int MPI_Comm_size(MPI_Comm comm, int *size) {
+  int r = 0, n = 1;
+  if (comm == PETSC_COMM_WORLD && ohp::global_context()) ohp_comm_rank_size(ohp::global_context(), &r, &n);
+  *size = n;
+  return 0;
+}
+inline int MPI_Barrier(MPI_Comm comm) { return comm == PETSC_COMM_WORLD ? ohp_comm_barrier(ohp::global_context()) : 0; }
+inline int MPI_Allreduce(const void *sendbuf, void *recvbuf, int count, MPI_Datatype type, MPI_Op op, MPI_Comm comm) {
+  if (type != MPI_INT || op != MPI_SUM) return PETSC_ERR_SUP;
+  std::vector<int64_t> v(count);
+  for (int i = 0; i < count; ++i) v[i] = ((const int *)sendbuf)[i];
+  const int rc = comm == PETSC_COMM_WORLD ? ohp_comm_allreduce_sum_i64(ohp::global_context(), v.data(), count) : 0;
+  for (int i = 0; i < count; ++i) ((int *)recvbuf)[i] = (int)v[i];
+  return rc;
+}
+
 /* ---- init / options ---- */
+/* One process per GPU.  Launched by torch.distributed.run (or anything that exports RANK / WORLD_SIZE / LOCAL_RANK /
+ * MASTER_ADDR / MASTER_PORT) the ranks form the NCCL communicator here, the way PetscInitialize calls MPI_Init. */
 inline PetscErrorCode PetscInitialize(int *argc, char ***argv, const char *, const char *) {
   for (int i = 1; i < *argc; ++i) {
     const char *a = (*argv)[i];
@@ -202,10 +257,13 @@ inline PetscErrorCode PetscInitialize(int *argc, char ***argv, const char *, con
       ohp::options_db()[key] = val;
     }
   }
-  int device = 0;
-  const char *lr = getenv("LOCAL_RANK");
-  if (lr) device = atoi(lr);
-  return ohp_init(device, &ohp::global_context());
+  int rank = 0, nranks = 1, device = 0;
+  PetscErrorCode ierr = ohp_boot_env(&rank, &nranks, &device);
+  if (ierr) return ierr;
+  ierr = ohp_init(device, &ohp::global_context());
+  if (ierr) return ierr;
+  if (nranks > 1) ierr = ohp_comm_init_from_env(ohp::global_context());
+  return ierr;
 }
 inline PetscErrorCode PetscFinalize(void) {
   PetscErrorCode ierr = ohp_finalize(ohp::global_context());
@@ -244,7 +302,12 @@ inline PetscErrorCode PetscOptionsGetIntArray(void *, const char *, const char *
   *n = k;
   return 0;
 }
-#define PetscPrintf(comm, ...) (printf(__VA_ARGS__), 0)
+inline bool ohp_prints(MPI_Comm comm) { /* PETSC_COMM_WORLD prints on rank 0 only */
+  int r = 0;
+  if (comm == PETSC_COMM_WORLD) MPI_Comm_rank(comm, &r);
+  return r == 0;
+}
+#define PetscPrintf(comm, ...) (ohp_prints(comm) ? (printf(__VA_ARGS__), fflush(stdout), 0) : 0)
 inline PetscErrorCode PetscObjectSetName(PetscObject, const char *) { return 0; } /* names: see VecSetName */
 
 /* ---- DM: mesh ---- */
@@ -257,6 +320,7 @@ inline PetscErrorCode DMPlexCreateFromCellListPetsc(MPI_Comm, PetscInt dim, Pets
   }
   DM d = new _p_DM();
   d->dim = dim;
+  d->nC = numCells; d->nV = numVertices;
   d->sf.dm = d;
   PetscErrorCode ierr = ohp_mesh_create(ohp::global_context(), dim, numCells, numVertices, cells, vertexCoords, &d->mesh);
   if (ierr) { delete d; return ierr; }
@@ -285,9 +349,91 @@ inline PetscErrorCode DMHasLabel(DM dm, const char *, PetscBool *has) { *has = d
 
 inline PetscErrorCode ohp_dm_setup(DM dm) {
   if (dm->set_up) return 0;
-  PetscErrorCode ierr = ohp_mesh_setup(dm->mesh);
+  PetscErrorCode ierr = 0;
+  if (dm->label_by_caller) ierr = ohp_mesh_set_label(dm->mesh, (PetscInt)dm->label_verts.size(), dm->label_verts.data());
+  if (!ierr) ierr = ohp_mesh_setup(dm->mesh);
+  /* partitioned run: NVLink peer mapping for the fused halo / all-reduce kernels (OHP_COMM=nccl keeps plain NCCL) */
+  if (!ierr) {
+    int r = 0, n = 1;
+    ohp_comm_rank_size(ohp::global_context(), &r, &n);
+    const char *c = getenv("OHP_COMM");
+    if (n > 1 && !(c && c[0] == 'n')) ierr = ohp_mesh_p2p_enable(dm->mesh);
+  }
   if (!ierr) dm->set_up = true;
   return ierr;
+}
+
+/* ---- Plex queries used by CreateQuadMesh after DMPlexInterpolate (ex12.cpp:966-1033).  Point numbering as in the
+ * reference: cells [0,nC), vertices [nC,nC+nV), then the facets DMPlexInterpolate creates (edges in 2-D). ---- */
+inline PetscErrorCode ohp_dm_facets(DM dm) {
+  if (dm->facets) return 0;
+  PetscErrorCode ierr = ohp_mesh_build_facets(dm->mesh, &dm->nF); if (ierr) return ierr;
+  const PetscInt nc = dm->dim + 1, fv = dm->dim;
+  dm->facet_cone.resize((size_t)dm->nF * fv); dm->facet_support.resize(dm->nF); dm->cell_cone.resize((size_t)dm->nC * nc);
+  ierr = ohp_mesh_get_facets(dm->mesh, dm->facet_cone.data(), dm->facet_support.data(), dm->cell_cone.data()); if (ierr) return ierr;
+  for (auto &p : dm->facet_cone) p += dm->nC;             /* vertex index -> Plex point */
+  for (auto &p : dm->cell_cone) p += dm->nC + dm->nV;     /* facet index  -> Plex point */
+  dm->facets = true;
+  return 0;
+}
+inline PetscErrorCode DMPlexGetHeightStratum(DM dm, PetscInt height, PetscInt *start, PetscInt *end) {
+  if (height == 0) { *start = 0; *end = dm->nC; return 0; }
+  if (height == dm->dim) { *start = dm->nC; *end = dm->nC + dm->nV; return 0; }
+  if (height == 1) {
+    PetscErrorCode ierr = ohp_dm_facets(dm); if (ierr) return ierr;
+    *start = dm->nC + dm->nV; *end = dm->nC + dm->nV + dm->nF;
+    return 0;
+  }
+  fprintf(stderr, "[0]PETSC ERROR: DMPlexGetHeightStratum: height %d of a %d-D mesh is not built (cells, facets, vertices only)\n", (int)height, (int)dm->dim);
+  return PETSC_ERR_SUP;
+}
+inline PetscErrorCode DMPlexGetDepthStratum(DM dm, PetscInt depth, PetscInt *start, PetscInt *end) {
+  return DMPlexGetHeightStratum(dm, dm->dim - depth, start, end);
+}
+inline PetscErrorCode DMPlexGetSupportSize(DM dm, PetscInt p, PetscInt *size) {
+  PetscErrorCode ierr = ohp_dm_facets(dm); if (ierr) return ierr;
+  const PetscInt f0 = dm->nC + dm->nV;
+  if (p < f0 || p >= f0 + dm->nF) { fprintf(stderr, "[0]PETSC ERROR: DMPlexGetSupportSize: point %d is not a facet\n", (int)p); return PETSC_ERR_ARG_OUTOFRANGE; }
+  *size = dm->facet_support[p - f0];
+  return 0;
+}
+inline PetscErrorCode DMPlexGetConeSize(DM dm, PetscInt p, PetscInt *size) {
+  const PetscInt f0 = dm->nC + dm->nV;
+  *size = p < dm->nC ? dm->dim + 1 : p >= f0 ? dm->dim : 0;
+  return 0;
+}
+inline PetscErrorCode DMPlexGetCone(DM dm, PetscInt p, const PetscInt **cone) {
+  PetscErrorCode ierr = ohp_dm_facets(dm); if (ierr) return ierr;
+  const PetscInt f0 = dm->nC + dm->nV;
+  if (p >= 0 && p < dm->nC) { *cone = dm->cell_cone.data() + (size_t)p * (dm->dim + 1); return 0; }
+  if (p >= f0 && p < f0 + dm->nF) { *cone = dm->facet_cone.data() + (size_t)(p - f0) * dm->dim; return 0; }
+  fprintf(stderr, "[0]PETSC ERROR: DMPlexGetCone: point %d has no cone\n", (int)p);
+  return PETSC_ERR_ARG_OUTOFRANGE;
+}
+/* the reference labels the boundary vertices (and edges) one point at a time (ex12.cpp:1023-1033): vertex points are
+ * collected and handed to the library at set-up; edge points carry no P1 dof and are accepted and ignored */
+inline PetscErrorCode DMSetLabelValue(DM dm, const char *name, PetscInt point, PetscInt value) {
+  if (strcmp(name, "marker") || value != 1) { fprintf(stderr, "[0]PETSC ERROR: DMSetLabelValue: only label \"marker\" = 1 is built\n"); return PETSC_ERR_SUP; }
+  if (dm->set_up) return PETSC_ERR_ORDER;
+  dm->label_by_caller = true; dm->has_marker = true;
+  if (point >= dm->nC && point < dm->nC + dm->nV) dm->label_verts.push_back(point - dm->nC);
+  else if (point < dm->nC) return PETSC_ERR_ARG_OUTOFRANGE;
+  return 0;
+}
+inline PetscErrorCode DMPlexUninterpolate(DM dm, DM *udm) { dm->refs++; *udm = dm; return 0; }
+inline PetscErrorCode DMPlexCopyCoordinates(DM, DM) { return 0; }
+inline PetscErrorCode DMSetFromOptions(DM) { return 0; }
+inline PetscErrorCode PetscSFView(PetscSF, void *) { return 0; }
+/* -dm_view (CMakeLists.txt:44-62 pass it through -dm_view in the TEST block, ex12.cpp:881,962): PETSc's one-line-per-stratum summary */
+inline PetscErrorCode DMViewFromOptions(DM dm, PetscObject, const char *name) {
+  PetscBool set;
+  PetscOptionsHasName(NULL, NULL, name, &set);
+  if (!set) return 0;
+  int64_t tot[3] = {dm->nV, dm->facets ? dm->nF : -1, dm->nC};
+  PetscPrintf(PETSC_COMM_WORLD, "DM Object: Mesh in %d dimensions (this rank):\n  0-cells: %lld\n", (int)dm->dim, (long long)tot[0]);
+  if (tot[1] >= 0) PetscPrintf(PETSC_COMM_WORLD, "  %d-cells: %lld\n", (int)dm->dim - 1, (long long)tot[1]);
+  PetscPrintf(PETSC_COMM_WORLD, "  %d-cells: %lld\nLabels:\n  marker: %s\n", (int)dm->dim, (long long)tot[2], dm->has_marker ? "1 strata (boundary)" : "not set");
+  return 0;
 }
 /* CreateBCLabel (ex12.cpp:515-526): faces with one supporting cell, completed to their vertices */
 inline PetscErrorCode DMPlexMarkBoundaryFaces(DM dm, PetscInt value, DMLabel) {
@@ -425,17 +571,16 @@ inline PetscErrorCode DMProjectFunction(DM dm, PetscReal, PetscSimplePointFunc *
   PetscErrorCode ierr = ohp_dm_setup(dm); if (ierr) return ierr;
   ierr = ohp_ds_problem(&dm->ds, &problem); if (ierr) return ierr;
   if (funcs[0] == dm->ds.exact) return ohp_project(dm->mesh, problem, 1, u->v);
-  /* the only other function ex12 projects is zero() (ex12.cpp:76-80,1598-1602): recognised by value */
-  PetscScalar val = 1.0; const PetscReal x0[3] = {0.3, 0.7, 0.2};
-  funcs[0](dm->dim, 0.0, x0, 1, &val, NULL);
-  if (val == 0.0) return ohp_project(dm->mesh, problem, 0, u->v);
-  fprintf(stderr, "[0]PETSC ERROR: DMProjectFunction: only the registered exact solution and zero are built\n");
+  auto it = ohp::function_registry().find((void *)funcs[0]);
+  if (it != ohp::function_registry().end()) return ohp_project_function(dm->mesh, it->second, u->v); /* OHP_DEFINE_FUNCTION */
+  fprintf(stderr, "[0]PETSC ERROR: DMProjectFunction: this function has no device instantiation: declare it with "
+                  "OHP_DEFINE_FUNCTION(name, fn) next to its definition (the exact solution of the DS needs no declaration)\n");
   return PETSC_ERR_SUP;
 }
 inline PetscErrorCode DMComputeL2Diff(DM dm, PetscReal, PetscSimplePointFunc *, void **, Vec u, PetscReal *err) {
   int problem;
   PetscErrorCode ierr = ohp_ds_problem(&dm->ds, &problem); if (ierr) return ierr;
-  return ohp_l2_error(dm->mesh, problem < 3 ? problem : 0, u->v, err);
+  return ohp_l2_error(dm->mesh, problem, u->v, err); /* the registered problem's own exact solution */
 }
 
 /* ---- viewers: `-vec_view vtk:<file>.vtu` (what every reference CTest writes, CMakeLists.txt:75,81,87,93,100,107) ----
@@ -528,6 +673,8 @@ inline PetscErrorCode SNESSetFromOptions(SNES snes) {
   PetscBool b;
   PetscOptionsHasName(NULL, NULL, "-snes_monitor_short", &b); snes->monitor = b;
   PetscOptionsHasName(NULL, NULL, "-snes_monitor", &b); snes->monitor = snes->monitor || b;
+  PetscOptionsHasName(NULL, NULL, "-ksp_monitor_short", &b); snes->ksp_monitor = b;
+  PetscOptionsHasName(NULL, NULL, "-ksp_monitor", &b); snes->ksp_monitor = snes->ksp_monitor || b;
   PetscOptionsHasName(NULL, NULL, "-snes_converged_reason", &b); snes->converged_reason = b;
   PetscOptionsHasName(NULL, NULL, "-ksp_converged_reason", &b); snes->ksp_converged_reason = b;
   return 0;
@@ -548,20 +695,38 @@ inline const char *ohp_snes_reason_name(int r) {
     case -3: return "DIVERGED_LINEAR_SOLVE"; case -5: return "DIVERGED_MAX_IT"; default: return "UNKNOWN";
   }
 }
+inline const char *ohp_ksp_reason_name(int r) {
+  switch (r) {
+    case 2: return "CONVERGED_RTOL"; case 3: return "CONVERGED_ATOL"; case -3: return "DIVERGED_ITS"; case -4: return "DIVERGED_DTOL";
+    case -8: return "DIVERGED_INDEFINITE_MAT"; case -9: return "DIVERGED_NANORINF"; default: return "UNKNOWN";
+  }
+}
+/* -snes_monitor_short / -ksp_monitor_short / -ksp_converged_reason (CMakeLists.txt:56-59), in PETSc's wording and
+ * indentation (the KSP is nested one level inside the SNES) */
+inline void ohp_snes_monitor_print(void *ctx, int32_t it, double fnorm) {
+  SNES snes = (SNES)ctx;
+  if (snes->monitor) PetscPrintf(PETSC_COMM_WORLD, "  %d SNES Function norm %g \n", (int)it, fnorm);
+}
+inline void ohp_ksp_monitor_print(void *ctx, int32_t, int32_t n, const double *rnorm, int32_t reason) {
+  SNES snes = (SNES)ctx;
+  if (snes->ksp_monitor && rnorm)
+    for (int k = 0; k <= n; ++k) PetscPrintf(PETSC_COMM_WORLD, "    %d KSP Residual norm %g \n", k, rnorm[k] < 1e-11 ? 0.0 : rnorm[k]);
+  if (snes->ksp_converged_reason)
+    PetscPrintf(PETSC_COMM_WORLD, "    Linear solve %s due to %s iterations %d\n", reason > 0 ? "converged" : "did not converge", ohp_ksp_reason_name(reason), (int)n);
+}
 inline PetscErrorCode SNESSolve(SNES snes, Vec b, Vec u) {
   if (b) return PETSC_ERR_SUP;
   if (!snes->J) return PETSC_ERR_ORDER;
   int problem;
   PetscErrorCode ierr = ohp_ds_problem(&snes->dm->ds, &problem); if (ierr) return ierr;
+  snes->opts.monitor_ctx = snes;
+  snes->opts.snes_monitor = snes->monitor ? ohp_snes_monitor_print : nullptr;
+  snes->opts.ksp_monitor = (snes->ksp_monitor || snes->ksp_converged_reason) ? ohp_ksp_monitor_print : nullptr;
+  if (snes->ksp_converged_reason && !snes->ksp_monitor) { snes->opts.ksp.history = nullptr; snes->opts.ksp.history_cap = 0; }
   ierr = ohp_snes_solve(snes->dm->mesh, problem, snes->J->m, u->v, &snes->opts, &snes->last); if (ierr) return ierr;
-  if (snes->monitor) {
-    printf("  0 SNES Function norm %g\n", snes->last.fnorm0);
-    printf("  %d SNES Function norm %g\n", snes->last.its, snes->last.fnorm);
-  }
-  if (snes->ksp_converged_reason) printf("  Linear solve %s: total iterations %d\n", snes->last.reason == -3 ? "did not converge" : "converged", snes->last.ksp_its);
   if (snes->converged_reason)
-    printf("Nonlinear solve %s due to %s iterations %d\n", snes->last.reason > 0 ? "converged" : "did not converge",
-           ohp_snes_reason_name(snes->last.reason), snes->last.its);
+    PetscPrintf(PETSC_COMM_WORLD, "Nonlinear solve %s due to %s iterations %d\n", snes->last.reason > 0 ? "converged" : "did not converge",
+                ohp_snes_reason_name(snes->last.reason), snes->last.its);
   snes->sol = u; /* borrowed reference, as SNESGetSolution returns (ex12.cpp:1610) */
   return 0;
 }

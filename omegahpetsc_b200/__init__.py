@@ -13,9 +13,9 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libohp.so")
+LIB_PATH = os.environ.get("OHP_LIB") or os.path.join(_HERE, "lib", "libohp.so")  # OHP_LIB: A/B builds of the same ABI
 
-PROBLEM_COEFF_NONE, PROBLEM_ANALYTIC, PROBLEM_NONLINEAR = 0, 1, 2
+PROBLEM_COEFF_NONE, PROBLEM_ANALYTIC, PROBLEM_NONLINEAR, PROBLEM_CIRCLE, PROBLEM_CROSS = 0, 1, 2, 3, 4
 PC_NONE, PC_JACOBI = 0, 1
 
 _i32p = ctypes.POINTER(ctypes.c_int32)
@@ -55,9 +55,14 @@ class KspResult(ctypes.Structure):
                 ("total_ms", ctypes.c_float)]
 
 
+SNES_MONITOR_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int32, ctypes.c_double)
+KSP_MONITOR_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, _f64p, ctypes.c_int32)
+
+
 class SnesOptions(ctypes.Structure):
     _fields_ = [("rtol", ctypes.c_double), ("abstol", ctypes.c_double), ("stol", ctypes.c_double),
-                ("max_it", ctypes.c_int32), ("ksp", KspOptions)]
+                ("max_it", ctypes.c_int32), ("ksp", KspOptions),
+                ("snes_monitor", SNES_MONITOR_FN), ("ksp_monitor", KSP_MONITOR_FN), ("monitor_ctx", ctypes.c_void_p)]
 
 
 class SnesResult(ctypes.Structure):
@@ -144,10 +149,41 @@ class Context:
         buf = (ctypes.c_uint8 * 128).from_buffer_copy(unique_id)
         _chk(lib().ohp_comm_init(self.h, int(nranks), int(rank), buf))
 
+    def comm_init_from_env(self):
+        """PetscInitialize for a multi-rank launch without MPI: rank/size from the launcher's environment, the NCCL id
+        from rank 0 over TCP next to MASTER_PORT (ohp_boot_env + ohp_boot_bcast + ohp_comm_init)."""
+        _chk(lib().ohp_comm_init_from_env(self.h))
+
+    def barrier(self):
+        _chk(lib().ohp_comm_barrier(self.h))
+
+    def allgather_i64(self, mine):
+        n = self.rank_size()[1]
+        out = np.zeros(n, dtype=np.int64)
+        _chk(lib().ohp_comm_allgather_i64(self.h, ctypes.c_int64(int(mine)), _ptr(out, _i64p)))
+        return out
+
+    def allreduce_sum_i64(self, vals):
+        v = np.ascontiguousarray(vals, dtype=np.int64).copy()
+        _chk(lib().ohp_comm_allreduce_sum_i64(self.h, _ptr(v, _i64p), v.size))
+        return v
+
     def rank_size(self):
         r, n = ctypes.c_int(), ctypes.c_int()
         _chk(lib().ohp_comm_rank_size(self.h, ctypes.byref(r), ctypes.byref(n)))
         return r.value, n.value
+
+    def ghost_roots_from_gids(self, ghost_gid, ghost_owner, core_gid, core_owned=None):
+        """getPicPartCoreVtxOwnerIdx's gid round trip (ex12.cpp:731-777) on the device: index of every ghost in
+        its owner's vertex array.  Collective."""
+        gg = np.ascontiguousarray(ghost_gid, dtype=np.int64)
+        go = np.ascontiguousarray(ghost_owner, dtype=np.int32)
+        cg = np.ascontiguousarray(core_gid, dtype=np.int64)
+        co = None if core_owned is None else np.ascontiguousarray(core_owned, dtype=np.uint8)
+        roots = np.empty(max(gg.size, 1), dtype=np.int32)
+        _chk(lib().ohp_ghost_roots_from_gids(self.h, gg.size, _ptr(gg, _i64p), _ptr(go, _i32p), cg.size, _ptr(cg, _i64p),
+                                             _ptr(co, _u8p) if co is not None else None, _ptr(roots, _i32p)))
+        return roots[:gg.size]
 
     def picpart_extract(self, dim, rank, elem_verts, coords, elem_owner, vert_owner, vert_gid=None, with_overlap=False):
         """getPicPartCoreVtxCoords / CoreElmToVtxArray / ghost list (ex12.cpp:584-730) on the device."""
@@ -176,6 +212,22 @@ class Context:
                     core_coords=cX[:cnt.n_core_verts].copy(), part2core=p2c[:nV].copy(),
                     ghost_core_idx=gci[:cnt.n_ghost_verts].copy(), ghost_gid=ggid[:cnt.n_ghost_verts].copy(),
                     ghost_owner=gown[:cnt.n_ghost_verts].copy(), core_gid=cgid[:cnt.n_core_verts].copy())
+
+
+def boot_env():
+    """(rank, nranks, local_rank) from the launcher's environment (ohp_boot_env); needs no GPU."""
+    r, n, l = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _chk(lib().ohp_boot_env(ctypes.byref(r), ctypes.byref(n), ctypes.byref(l)))
+    return r.value, n.value, l.value
+
+
+def boot_bcast(rank, nranks, payload, nbytes):
+    """Rank 0's `payload` (bytes) to every rank over TCP (ohp_boot_bcast); needs no GPU."""
+    buf = (ctypes.c_uint8 * nbytes)()
+    if rank == 0:
+        buf[:] = payload[:nbytes]
+    _chk(lib().ohp_boot_bcast(int(rank), int(nranks), buf, int(nbytes)))
+    return bytes(buf)
 
 
 class Osh:
@@ -372,6 +424,7 @@ class Mesh:
         if cells.shape[1] != self.dim + 1:
             raise OhpError(60, "Mesh: %d corners for dim %d" % (cells.shape[1], self.dim))
         self.h = _vp()
+        self._nC = cells.shape[0]
         _chk(lib().ohp_mesh_create(ctx.h, self.dim, cells.shape[0], coords.shape[0], _ptr(cells, _i32p),
                                    _ptr(coords, _f64p), ctypes.byref(self.h)))
         self._info = None
@@ -397,6 +450,14 @@ class Mesh:
         overt = np.ascontiguousarray(owner_vertex, dtype=np.int32)
         _chk(lib().ohp_mesh_set_ghosts(self.h, gv.size, _ptr(gv, _i32p), _ptr(orank, _i32p), _ptr(overt, _i32p)))
 
+    def set_ghosts_from_gids(self, ghost_vertex, owner_rank, vertex_gid, vertex_owned):
+        """Point SF from global vertex ids: the roots are resolved on the device (ohp_ghost_roots_from_gids)."""
+        gv = np.ascontiguousarray(ghost_vertex, dtype=np.int32)
+        gid = np.ascontiguousarray(vertex_gid, dtype=np.int64)
+        roots = self.ctx.ghost_roots_from_gids(gid[gv], owner_rank, gid, vertex_owned)
+        self.set_ghosts(gv, owner_rank, roots)
+        return roots
+
     def set_point_sf(self, leaf_point, root_rank, root_point):
         """The same graph in Plex POINT numbers, exactly as ex12 passes it (ex12.cpp:867-871,924-926)."""
         lp = np.ascontiguousarray(leaf_point, dtype=np.int32)
@@ -408,6 +469,27 @@ class Mesh:
         _chk(lib().ohp_mesh_setup(self.h))
         self._info = None
         return self
+
+    def p2p_enable_native(self):
+        """ohp_mesh_p2p_enable: the IPC handles travel over the library's own communicator."""
+        _chk(lib().ohp_mesh_p2p_enable(self.h))
+
+    def facets(self):
+        """What DMPlexInterpolate adds between cells and vertices (edges in 2-D, faces in 3-D): (facet_verts [nF, dim],
+        support [nF], cell_facets [nC, dim+1]) as 0-based indices (DMPlexGetCone / GetSupportSize, ex12.cpp:990,1006)."""
+        n = ctypes.c_int32()
+        _chk(lib().ohp_mesh_build_facets(self.h, ctypes.byref(n)))
+        nF, nC = n.value, self._nC
+        fv = np.empty((max(nF, 1), self.dim), dtype=np.int32)
+        sup = np.empty(max(nF, 1), dtype=np.int32)
+        cf = np.empty((max(nC, 1), self.dim + 1), dtype=np.int32)
+        _chk(lib().ohp_mesh_get_facets(self.h, _ptr(fv, _i32p), _ptr(sup, _i32p), _ptr(cf, _i32p)))
+        return fv[:nF], sup[:nF], cf[:nC]
+
+    def set_label(self, vertices):
+        """DMSetLabelValue(dm, "marker", nC + v, 1) for every v (ex12.cpp:1023-1026)."""
+        v = np.ascontiguousarray(vertices, dtype=np.int32)
+        _chk(lib().ohp_mesh_set_label(self.h, v.size, _ptr(v, _i32p)))
 
     def p2p_enable(self, all_gather_object, world):
         """ohp_mesh_p2p_export + all-gather of the CUDA IPC handles + ohp_mesh_p2p_attach."""
@@ -467,13 +549,23 @@ class Mesh:
         _chk(lib().ohp_l2_error(self.h, int(problem), u.h, ctypes.byref(e)))
         return e.value
 
-    def snes_solve(self, problem, J, u, snes_rtol=1e-8, snes_atol=1e-50, snes_stol=1e-8, snes_max_it=50, ksp=None):
-        """SNESSolve (ex12.cpp:1609): newtonls + bt over CG."""
+    def snes_solve(self, problem, J, u, snes_rtol=1e-8, snes_atol=1e-50, snes_stol=1e-8, snes_max_it=50, ksp=None, monitor=None):
+        """SNESSolve (ex12.cpp:1609): newtonls + bt over CG.  `monitor` (a dict) receives the -snes_monitor norms under
+        "snes" and one array of -ksp_monitor norms per Newton iteration under "ksp"."""
         o = SnesOptions()
         _chk(lib().ohp_snes_default_options(ctypes.byref(o)))
         o.rtol, o.abstol, o.stol, o.max_it = snes_rtol, snes_atol, snes_stol, int(snes_max_it)
         if ksp is not None:
             o.ksp = ksp
+        keep = []
+        if monitor is not None:
+            monitor.setdefault("snes", []); monitor.setdefault("ksp", []); monitor.setdefault("ksp_reason", [])
+            sm = SNES_MONITOR_FN(lambda ctx, it, fnorm: monitor["snes"].append((it, fnorm)))
+            km = KSP_MONITOR_FN(lambda ctx, nit, n, rn, reason: (monitor["ksp"].append(np.array([rn[k] for k in range(n + 1)])),
+                                                                  monitor["ksp_reason"].append(reason)) and None)
+            keep = [sm, km]
+            o.snes_monitor, o.ksp_monitor = sm, km
         r = SnesResult()
         _chk(lib().ohp_snes_solve(self.h, int(problem), J.h, u.h, ctypes.byref(o), ctypes.byref(r)))
+        del keep
         return {f[0]: getattr(r, f[0]) for f in SnesResult._fields_}

@@ -52,11 +52,6 @@ struct PcgArgs {
 };
 
 __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PNC) : "memory"); }
-__device__ __forceinline__ double ld_weak(const double *p) {
-  double v;
-  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -258,7 +253,7 @@ __global__ void __launch_bounds__(PNC + 32, 1) k_cg_persistent(const PcgArgs a) 
         if (tid < pd.n_nbr) {
           const int q = pd.nbr[tid];
           st_release_sys(pd.hflags[q] + pd.rank, s_seq);
-          p2p_wait(pd.hflags[pd.rank] + q, s_seq, pd.seq + 2);
+          p2p_wait(pd.hflags[pd.rank] + q, s_seq, pd.seq + 2, pd.timeout_ns);
         }
       }
       gbar_release(a.sync + 1, bar_k);
@@ -331,20 +326,16 @@ int ohp_cg_persistent_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_optio
   const size_t len = (size_t)std::max(1, n + m->n_ghost);
   const bool jac = (o->pc == OHP_PC_JACOBI);
   if (!A->r) {
-    OHP_CUDA(cudaMalloc(&A->r, sizeof(double) * len));
-    OHP_CUDA(cudaMalloc(&A->p, sizeof(double) * len));
-    OHP_CUDA(cudaMalloc(&A->p1, sizeof(double) * len));
-    OHP_CUDA(cudaMalloc(&A->w, sizeof(double) * len));
+    OHP_CUDA(OHP_MALLOC(ctx, &A->r, sizeof(double) * len));
+    OHP_CUDA(OHP_MALLOC(ctx, &A->p, sizeof(double) * len));
+    OHP_CUDA(OHP_MALLOC(ctx, &A->p1, sizeof(double) * len));
+    OHP_CUDA(OHP_MALLOC(ctx, &A->w, sizeof(double) * len));
   }
-  if (!A->s) OHP_CUDA(cudaMalloc(&A->s, sizeof(double) * len));
-  if (jac && !A->z) { OHP_CUDA(cudaMalloc(&A->z, sizeof(double) * len)); OHP_CUDA(cudaMalloc(&A->dinv, sizeof(double) * len)); }
+  if (!A->s) OHP_CUDA(OHP_MALLOC(ctx, &A->s, sizeof(double) * len));
+  if (jac && !A->z) { OHP_CUDA(OHP_MALLOC(ctx, &A->z, sizeof(double) * len)); OHP_CUDA(OHP_MALLOC(ctx, &A->dinv, sizeof(double) * len)); }
   if (jac) OHP_TRY(ohp_extract_dinv(A));
-  static bool configured = false;
   const int smem = tma_smem_bytes(PS);
-  if (!configured) {
-    OHP_CUDA(cudaFuncSetAttribute(k_cg_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  OHP_CUDA(cudaFuncSetAttribute(k_cg_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); /* per device */
   static const ohp_p2p_dev no_p2p = {};
   PcgArgs a;
   memset(&a, 0, sizeof(a));
@@ -361,8 +352,8 @@ int ohp_cg_persistent_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_optio
   double *hist = nullptr;
   if (o->history && o->history_cap > 0) {
     if (A->hist_cap < o->history_cap) {
-      cudaFree(A->hist);
-      OHP_CUDA(cudaMalloc(&A->hist, sizeof(double) * o->history_cap));
+      OHP_FREE(ctx, A->hist);
+      OHP_CUDA(OHP_MALLOC(ctx, &A->hist, sizeof(double) * o->history_cap));
       A->hist_cap = o->history_cap;
     }
     hist = A->hist;
@@ -376,8 +367,10 @@ int ohp_cg_persistent_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_optio
   OHP_CUDA(cudaMemcpyAsync(ctx->d_cg, ctx->h_cg, sizeof(init), cudaMemcpyHostToDevice, st));
   const int grid = std::min(ctx->num_sms, PNC);
   a.chunk_iters = o->check_every > 0 ? o->check_every : 200;
-  cudaEvent_t ev0, ev1;
-  OHP_CUDA(cudaEventCreate(&ev0)); OHP_CUDA(cudaEventCreate(&ev1));
+  if (p2p) OHP_TRY(ohp_p2p_entry_barrier(m));
+  struct Ev { cudaEvent_t e = nullptr; ~Ev() { if (e) cudaEventDestroy(e); } } e0, e1;
+  OHP_CUDA(cudaEventCreate(&e0.e)); OHP_CUDA(cudaEventCreate(&e1.e));
+  cudaEvent_t ev0 = e0.e, ev1 = e1.e;
   OHP_CUDA(cudaEventRecord(ev0, st));
   int launched = 0;
   for (;;) {
@@ -395,15 +388,9 @@ int ohp_cg_persistent_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_optio
   OHP_CUDA(cudaEventSynchronize(ev1));
   res->total_ms = 0.f;
   cudaEventElapsedTime(&res->total_ms, ev0, ev1);
-  cudaEventDestroy(ev0); cudaEventDestroy(ev1);
   res->its = ctx->h_cg->its; res->reason = ctx->h_cg->reason; res->rnorm = ctx->h_cg->dp; res->rnorm0 = ctx->h_cg->rnorm0;
   res->spmv_ms = 0.f; res->spmv_samples = 0;
-  if (p2p) {
-    unsigned long long err = 0;
-    OHP_CUDA(cudaMemcpyAsync(&err, a.pd.seq + 2, sizeof(err), cudaMemcpyDeviceToHost, st));
-    OHP_CUDA(cudaStreamSynchronize(st));
-    if (err) OHP_FAIL(OHP_ERR_LIB, "ohp_ksp_cg (persistent): a peer-to-peer wait timed out");
-  }
+  if (p2p) OHP_TRY(ohp_p2p_check(m, "ohp_ksp_cg (persistent)"));
   if (hist) {
     const int ncopy = std::min(o->history_cap, res->its + 1);
     OHP_CUDA(cudaMemcpyAsync(o->history, hist, sizeof(double) * ncopy, cudaMemcpyDeviceToHost, st));

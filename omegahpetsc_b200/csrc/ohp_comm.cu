@@ -14,6 +14,7 @@
  */
 #include <dlfcn.h>
 #include <nccl.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -109,12 +110,48 @@ int ohp_allgather_i64(ohp_context ctx, int64_t mine, std::vector<int64_t> &all) 
   all.assign(ctx->nranks, mine);
   if (ctx->nranks == 1) return 0;
   int64_t *d;
-  OHP_CUDA(cudaMalloc(&d, sizeof(int64_t) * (ctx->nranks + 1)));
+  OHP_CUDA(OHP_MALLOC(ctx, &d, sizeof(int64_t) * (ctx->nranks + 1)));
   OHP_CUDA(cudaMemcpyAsync(d + ctx->nranks, &mine, sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
   OHP_NCCL(g_nccl.AllGather(d + ctx->nranks, d, 1, ncclInt64, (ncclComm_t)ctx->comm, ctx->stream));
   OHP_CUDA(cudaMemcpyAsync(all.data(), d, sizeof(int64_t) * ctx->nranks, cudaMemcpyDeviceToHost, ctx->stream));
   OHP_CUDA(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d);
+  OHP_FREE(ctx, d);
+  return 0;
+}
+
+/* MPI_Barrier / MPI_Allgather / MPI_Allreduce as the adapter uses them (ex12.cpp:573-575,814,844,953) */
+extern "C" int ohp_comm_barrier(ohp_context ctx) {
+  if (!ctx) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_comm_barrier: null context");
+  OHP_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->nranks > 1) {
+    OHP_CUDA(cudaMemsetAsync(ctx->d_scalars + 11, 0, sizeof(double), ctx->stream));
+    OHP_NCCL(g_nccl.AllReduce(ctx->d_scalars + 11, ctx->d_scalars + 11, 1, ncclFloat64, ncclSum, (ncclComm_t)ctx->comm, ctx->stream));
+  }
+  OHP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+extern "C" int ohp_comm_allgather_i64(ohp_context ctx, int64_t mine, int64_t *all) {
+  if (!ctx || !all) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_comm_allgather_i64: null argument");
+  OHP_CUDA(cudaSetDevice(ctx->device));
+  std::vector<int64_t> v;
+  OHP_TRY(ohp_allgather_i64(ctx, mine, v));
+  std::copy(v.begin(), v.end(), all);
+  return 0;
+}
+extern "C" int ohp_comm_allreduce_sum_i64(ohp_context ctx, int64_t *vals, int n) {
+  if (!ctx || (n > 0 && !vals)) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_comm_allreduce_sum_i64: null argument");
+  if (ctx->nranks == 1 || n <= 0) return 0;
+  OHP_CUDA(cudaSetDevice(ctx->device));
+  int64_t *d;
+  OHP_CUDA(OHP_MALLOC(ctx, &d, sizeof(int64_t) * n));
+  OHP_CUDA(cudaMemcpyAsync(d, vals, sizeof(int64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+  ncclResult_t r = g_nccl.AllReduce(d, d, (size_t)n, ncclInt64, ncclSum, (ncclComm_t)ctx->comm, ctx->stream);
+  if (r == ncclSuccess) {
+    cudaMemcpyAsync(vals, d, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  OHP_FREE(ctx, d);
+  OHP_NCCL(r);
   return 0;
 }
 
@@ -128,20 +165,20 @@ static int exchange_lists(ohp_context ctx, const std::vector<std::vector<int32_t
   cudaStream_t st = ctx->stream;
   std::vector<int64_t> counts(P), matrix((size_t)P * P);
   int64_t *d_counts;
-  OHP_CUDA(cudaMalloc(&d_counts, sizeof(int64_t) * ((size_t)P * P + P)));
+  OHP_CUDA(OHP_MALLOC(ctx, &d_counts, sizeof(int64_t) * ((size_t)P * P + P)));
   for (int q = 0; q < P; ++q) counts[q] = (int64_t)send[q].size();
   OHP_CUDA(cudaMemcpyAsync(d_counts + (size_t)P * P, counts.data(), sizeof(int64_t) * P, cudaMemcpyHostToDevice, st));
   OHP_NCCL(g_nccl.AllGather(d_counts + (size_t)P * P, d_counts, P, ncclInt64, (ncclComm_t)ctx->comm, st));
   OHP_CUDA(cudaMemcpyAsync(matrix.data(), d_counts, sizeof(int64_t) * P * P, cudaMemcpyDeviceToHost, st));
   OHP_CUDA(cudaStreamSynchronize(st));
-  cudaFree(d_counts);
+  OHP_FREE(ctx, d_counts);
   int64_t ns = 0, nr = 0;
   std::vector<int64_t> soff(P + 1, 0), roff(P + 1, 0);
   for (int q = 0; q < P; ++q) { soff[q + 1] = soff[q] + matrix[(size_t)ctx->rank * P + q]; roff[q + 1] = roff[q] + matrix[(size_t)q * P + ctx->rank]; }
   ns = soff[P]; nr = roff[P];
   int32_t *d_s, *d_r;
-  OHP_CUDA(cudaMalloc(&d_s, sizeof(int32_t) * std::max<int64_t>(1, ns)));
-  OHP_CUDA(cudaMalloc(&d_r, sizeof(int32_t) * std::max<int64_t>(1, nr)));
+  OHP_CUDA(OHP_MALLOC(ctx, &d_s, sizeof(int32_t) * std::max<int64_t>(1, ns)));
+  OHP_CUDA(OHP_MALLOC(ctx, &d_r, sizeof(int32_t) * std::max<int64_t>(1, nr)));
   std::vector<int32_t> flat((size_t)ns);
   for (int q = 0; q < P; ++q) std::copy(send[q].begin(), send[q].end(), flat.begin() + soff[q]);
   OHP_CUDA(cudaMemcpyAsync(d_s, flat.data(), sizeof(int32_t) * ns, cudaMemcpyHostToDevice, st));
@@ -155,9 +192,54 @@ static int exchange_lists(ohp_context ctx, const std::vector<std::vector<int32_t
   std::vector<int32_t> rflat((size_t)nr);
   OHP_CUDA(cudaMemcpyAsync(rflat.data(), d_r, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, st));
   OHP_CUDA(cudaStreamSynchronize(st));
-  cudaFree(d_s); cudaFree(d_r);
+  OHP_FREE(ctx, d_s); OHP_FREE(ctx, d_r);
   recv.assign(P, {});
   for (int q = 0; q < P; ++q) recv[q].assign(rflat.begin() + roff[q], rflat.begin() + roff[q + 1]);
+  return 0;
+}
+
+/* The same exchange on DEVICE buffers of `elem_bytes`-sized items: d_send holds the items grouped by
+ * destination rank (scount[q] items for rank q, rank order); *d_recv is allocated here (cudaFree it) and holds
+ * what the ranks sent to me, grouped by source rank (rcount[q] items from q).  Collective. */
+int ohp_sparse_exchange(ohp_context ctx, int elem_bytes, const void *d_send, const std::vector<int64_t> &scount,
+                        void **d_recv, std::vector<int64_t> &rcount) {
+  const int P = ctx->nranks;
+  cudaStream_t st = ctx->stream;
+  std::vector<int64_t> matrix((size_t)P * P);
+  int64_t *d_counts;
+  OHP_CUDA(OHP_MALLOC(ctx, &d_counts, sizeof(int64_t) * ((size_t)P * P + P)));
+  OHP_CUDA(cudaMemcpyAsync(d_counts + (size_t)P * P, scount.data(), sizeof(int64_t) * P, cudaMemcpyHostToDevice, st));
+  ncclResult_t r = g_nccl.AllGather(d_counts + (size_t)P * P, d_counts, P, ncclInt64, (ncclComm_t)ctx->comm, st);
+  if (r == ncclSuccess) {
+    cudaMemcpyAsync(matrix.data(), d_counts, sizeof(int64_t) * P * P, cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+  }
+  OHP_FREE(ctx, d_counts);
+  OHP_NCCL(r);
+  rcount.assign(P, 0);
+  std::vector<int64_t> soff(P + 1, 0), roff(P + 1, 0);
+  for (int q = 0; q < P; ++q) {
+    rcount[q] = matrix[(size_t)q * P + ctx->rank];
+    soff[q + 1] = soff[q] + scount[q];
+    roff[q + 1] = roff[q] + rcount[q];
+  }
+  char *recv = nullptr;
+  OHP_CUDA(OHP_MALLOC(ctx, &recv, (size_t)std::max<int64_t>(1, roff[P]) * elem_bytes));
+  *d_recv = recv;
+  const char *send = (const char *)d_send;
+  ncclResult_t first = ncclSuccess;
+  g_nccl.GroupStart();
+  for (int q = 0; q < P; ++q) {
+    if (q == ctx->rank) {
+      if (scount[q]) cudaMemcpyAsync(recv + roff[q] * elem_bytes, send + soff[q] * elem_bytes, (size_t)scount[q] * elem_bytes, cudaMemcpyDeviceToDevice, st);
+      continue;
+    }
+    if (scount[q]) { r = g_nccl.Send(send + soff[q] * elem_bytes, (size_t)scount[q] * elem_bytes, ncclChar, q, (ncclComm_t)ctx->comm, st); if (r != ncclSuccess && first == ncclSuccess) first = r; }
+    if (rcount[q]) { r = g_nccl.Recv(recv + roff[q] * elem_bytes, (size_t)rcount[q] * elem_bytes, ncclChar, q, (ncclComm_t)ctx->comm, st); if (r != ncclSuccess && first == ncclSuccess) first = r; }
+  }
+  r = g_nccl.GroupEnd(); /* always closed, whatever happened inside */
+  if (first == ncclSuccess) first = r;
+  OHP_NCCL(first);
   return 0;
 }
 
@@ -181,10 +263,10 @@ struct ohp_halo {
   std::vector<int64_t> d_dst_off;            /* per neighbour: first index of my block in ITS vector */
 };
 
-void ohp_halo_free(ohp_halo *h) {
+void ohp_halo_free(ohp_context ctx, ohp_halo *h) {
   if (!h) return;
-  cudaFree(h->d_v_send_idx); cudaFree(h->d_v_recv_idx); cudaFree(h->d_v_sbuf); cudaFree(h->d_v_rbuf);
-  cudaFree(h->d_send_ldof); cudaFree(h->d_sbuf);
+  OHP_FREE(ctx, h->d_v_send_idx); OHP_FREE(ctx, h->d_v_recv_idx); OHP_FREE(ctx, h->d_v_sbuf); OHP_FREE(ctx, h->d_v_rbuf);
+  OHP_FREE(ctx, h->d_send_ldof); OHP_FREE(ctx, h->d_sbuf);
   delete h;
 }
 
@@ -220,10 +302,10 @@ static int vertex_plan_build(ohp_mesh m) {
     h->v_roff.push_back(h->v_roff.back() + (int64_t)req[q].size());
   }
   h->v_ns = (int64_t)send_idx.size(); h->v_nr = (int64_t)recv_idx.size();
-  OHP_CUDA(cudaMalloc(&h->d_v_send_idx, sizeof(int32_t) * std::max<int64_t>(1, h->v_ns)));
-  OHP_CUDA(cudaMalloc(&h->d_v_recv_idx, sizeof(int32_t) * std::max<int64_t>(1, h->v_nr)));
-  OHP_CUDA(cudaMalloc(&h->d_v_sbuf, sizeof(int32_t) * std::max<int64_t>(1, h->v_ns)));
-  OHP_CUDA(cudaMalloc(&h->d_v_rbuf, sizeof(int32_t) * std::max<int64_t>(1, h->v_nr)));
+  OHP_CUDA(OHP_MALLOC(ctx, &h->d_v_send_idx, sizeof(int32_t) * std::max<int64_t>(1, h->v_ns)));
+  OHP_CUDA(OHP_MALLOC(ctx, &h->d_v_recv_idx, sizeof(int32_t) * std::max<int64_t>(1, h->v_nr)));
+  OHP_CUDA(OHP_MALLOC(ctx, &h->d_v_sbuf, sizeof(int32_t) * std::max<int64_t>(1, h->v_ns)));
+  OHP_CUDA(OHP_MALLOC(ctx, &h->d_v_rbuf, sizeof(int32_t) * std::max<int64_t>(1, h->v_nr)));
   OHP_CUDA(cudaMemcpyAsync(h->d_v_send_idx, send_idx.data(), sizeof(int32_t) * h->v_ns, cudaMemcpyHostToDevice, ctx->stream));
   OHP_CUDA(cudaMemcpyAsync(h->d_v_recv_idx, recv_idx.data(), sizeof(int32_t) * h->v_nr, cudaMemcpyHostToDevice, ctx->stream));
   OHP_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -284,14 +366,14 @@ int ohp_halo_build(ohp_mesh m) {
   m->row_start = start[ctx->rank]; m->n_global = start[P];
   /* owners' local dof numbers for my ghost vertices */
   int32_t *d_tmp;
-  OHP_CUDA(cudaMalloc(&d_tmp, sizeof(int32_t) * std::max(1, m->nV)));
+  OHP_CUDA(OHP_MALLOC(ctx, &d_tmp, sizeof(int32_t) * std::max(1, m->nV)));
   OHP_CUDA(cudaMemcpyAsync(d_tmp, m->lidx, sizeof(int32_t) * m->nV, cudaMemcpyDeviceToDevice, st));
   OHP_TRY(ohp_vertex_halo_i32(m, d_tmp));
   const int nleaf = (int)m->ghost_vertex.size();
   std::vector<int32_t> owner_ldof_all(m->nV);
   OHP_CUDA(cudaMemcpyAsync(owner_ldof_all.data(), d_tmp, sizeof(int32_t) * m->nV, cudaMemcpyDeviceToHost, st));
   OHP_CUDA(cudaStreamSynchronize(st));
-  cudaFree(d_tmp);
+  OHP_FREE(ctx, d_tmp);
   /* unconstrained ghosts, ordered by (owner rank, owner dof): contiguous receive ranges */
   struct G { int rank; int32_t ldof; int32_t vertex; };
   std::vector<G> gh;
@@ -313,13 +395,13 @@ int ohp_halo_build(ohp_mesh m) {
   }
   OHP_CUDA(cudaMemcpyAsync(m->lidx, lidx.data(), sizeof(int32_t) * m->nV, cudaMemcpyHostToDevice, st));
   int64_t *d_ggid;
-  OHP_CUDA(cudaMalloc(&d_ggid, sizeof(int64_t) * std::max<size_t>(1, gh.size())));
+  OHP_CUDA(OHP_MALLOC(ctx, &d_ggid, sizeof(int64_t) * std::max<size_t>(1, gh.size())));
   OHP_CUDA(cudaMemcpyAsync(d_ggid, ghost_gid.data(), sizeof(int64_t) * gh.size(), cudaMemcpyHostToDevice, st));
-  OHP_CUDA(cudaMalloc(&m->ldof_gid, sizeof(int64_t) * std::max(1, m->n_owned + m->n_ghost)));
+  OHP_CUDA(OHP_MALLOC(ctx, &m->ldof_gid, sizeof(int64_t) * std::max(1, m->n_owned + m->n_ghost)));
   k_ldof_gid<<<nblk(m->n_owned + m->n_ghost, 256), 256, 0, st>>>(m->ldof_gid, m->n_owned, m->row_start, d_ggid, m->n_ghost);
   OHP_CHECK_LAUNCH(ctx);
   OHP_CUDA(cudaStreamSynchronize(st));
-  cudaFree(d_ggid);
+  OHP_FREE(ctx, d_ggid);
   /* who needs which of my dofs */
   OHP_TRY(exchange_lists(ctx, req, serve));
   std::vector<int32_t> send_ldof;
@@ -335,8 +417,8 @@ int ohp_halo_build(ohp_mesh m) {
     h->d_roff.push_back(h->d_roff.back() + (int64_t)req[q].size());
   }
   h->d_ns = (int64_t)send_ldof.size(); h->d_nr = m->n_ghost;
-  OHP_CUDA(cudaMalloc(&h->d_send_ldof, sizeof(int32_t) * std::max<int64_t>(1, h->d_ns)));
-  OHP_CUDA(cudaMalloc(&h->d_sbuf, sizeof(double) * std::max<int64_t>(1, h->d_ns)));
+  OHP_CUDA(OHP_MALLOC(ctx, &h->d_send_ldof, sizeof(int32_t) * std::max<int64_t>(1, h->d_ns)));
+  OHP_CUDA(OHP_MALLOC(ctx, &h->d_sbuf, sizeof(double) * std::max<int64_t>(1, h->d_ns)));
   OHP_CUDA(cudaMemcpyAsync(h->d_send_ldof, send_ldof.data(), sizeof(int32_t) * h->d_ns, cudaMemcpyHostToDevice, st));
   OHP_CUDA(cudaStreamSynchronize(st));
   /* tell every rank that serves me where its block starts in my vector (used by the P2P push) */
@@ -431,8 +513,61 @@ extern "C" int ohp_mesh_p2p_attach(ohp_mesh m, const void *handles) {
     d.p[1][q] = (double *)(base + p->off_p1);
   }
   d.seq = (unsigned long long *)((char *)p->heap + p->bytes - 256);
+  {
+    const char *t = getenv("OHP_P2P_TIMEOUT_S");
+    double sec = t ? atof(t) : 60.0;
+    if (!(sec > 0.0)) sec = 60.0;
+    d.timeout_ns = (unsigned long long)(sec * 1e9);
+  }
   p->attached = true;
   return 0;
+}
+
+int ohp_p2p_entry_barrier(ohp_mesh m) {
+  ohp_context ctx = m->ctx;
+  if (ctx->nranks < 2 || !ctx->comm) return 0;
+  OHP_CUDA(cudaMemsetAsync(ctx->d_scalars + 10, 0, sizeof(double), ctx->stream));
+  OHP_NCCL(g_nccl.AllReduce(ctx->d_scalars + 10, ctx->d_scalars + 10, 1, ncclFloat64, ncclSum, (ncclComm_t)ctx->comm, ctx->stream));
+  return 0;
+}
+
+int ohp_p2p_check(ohp_mesh m, const char *what) {
+  if (!m->p2p || !m->p2p->attached) return 0;
+  ohp_context ctx = m->ctx;
+  unsigned long long err = 0;
+  unsigned long long *flag = m->p2p->dev.seq + 2;
+  OHP_CUDA(cudaMemcpyAsync(&err, flag, sizeof(err), cudaMemcpyDeviceToHost, ctx->stream));
+  OHP_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (err) {
+    cudaMemsetAsync(flag, 0, sizeof(err), ctx->stream); /* reported once; the next solve starts clean */
+    OHP_FAIL(OHP_ERR_LIB, "%s: a peer-to-peer wait timed out after %.0f s (a neighbouring rank stopped responding; OHP_P2P_TIMEOUT_S raises the limit)",
+             what, m->p2p->dev.timeout_ns * 1e-9);
+  }
+  return 0;
+}
+
+/* export + all-gather of the handles over the communicator + attach, in one collective call (what a C/C++ host
+ * uses; the two-step form exists for launchers that carry the handles themselves) */
+extern "C" int ohp_mesh_p2p_enable(ohp_mesh m) {
+  if (!m || !m->setup_done) OHP_FAIL(OHP_ERR_ORDER, "ohp_mesh_p2p_enable: mesh not set up");
+  ohp_context ctx = m->ctx;
+  if (ctx->nranks < 2) return 0;
+  if (m->p2p && m->p2p->attached) return 0;
+  unsigned char mine[64];
+  OHP_TRY(ohp_mesh_p2p_export(m, mine));
+  const int P = ctx->nranks;
+  unsigned char *d;
+  OHP_CUDA(OHP_MALLOC(ctx, &d, 64 * (size_t)(P + 1)));
+  OHP_CUDA(cudaMemcpyAsync(d + 64 * (size_t)P, mine, 64, cudaMemcpyHostToDevice, ctx->stream));
+  ncclResult_t r = g_nccl.AllGather(d + 64 * (size_t)P, d, 64, ncclChar, (ncclComm_t)ctx->comm, ctx->stream);
+  std::vector<unsigned char> all(64 * (size_t)P);
+  if (r == ncclSuccess) {
+    cudaMemcpyAsync(all.data(), d, all.size(), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  OHP_FREE(ctx, d);
+  OHP_NCCL(r);
+  return ohp_mesh_p2p_attach(m, all.data());
 }
 
 /* DMGlobalToLocal / MatMult scatter: x[n_owned + k] <- owner's value of ghost dof k */

@@ -52,14 +52,21 @@ extern "C" int ohp_init(int device, ohp_context *out) {
   OHP_CUDA(cudaGetDeviceProperties(&prop, device));
   c->num_sms = prop.multiProcessorCount;
   OHP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  OHP_CUDA(cudaMalloc(&c->d_partials, sizeof(double) * kMaxPartials * 2));
-  OHP_CUDA(cudaMalloc(&c->d_ticket, sizeof(unsigned) * 8));
+  {
+    /* keep freed blocks in the device's pool instead of returning them to the driver (see OHP_MALLOC) */
+    cudaMemPool_t pool;
+    OHP_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = UINT64_MAX;
+    OHP_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
+  OHP_CUDA(OHP_MALLOC(c, &c->d_partials, sizeof(double) * kMaxPartials * 2));
+  OHP_CUDA(OHP_MALLOC(c, &c->d_ticket, sizeof(unsigned) * 8));
   OHP_CUDA(cudaMemset(c->d_ticket, 0, sizeof(unsigned) * 8));
-  OHP_CUDA(cudaMalloc(&c->d_scalars, sizeof(double) * 16));
+  OHP_CUDA(OHP_MALLOC(c, &c->d_scalars, sizeof(double) * 16));
   OHP_CUDA(cudaMallocHost(&c->h_scalars, sizeof(double) * 16));
-  OHP_CUDA(cudaMalloc(&c->d_cg, sizeof(ohp_cg_state)));
+  OHP_CUDA(OHP_MALLOC(c, &c->d_cg, sizeof(ohp_cg_state)));
   OHP_CUDA(cudaMallocHost(&c->h_cg, sizeof(ohp_cg_state)));
-  OHP_CUDA(cudaMalloc(&c->d_flag, sizeof(int)));
+  OHP_CUDA(OHP_MALLOC(c, &c->d_flag, sizeof(int)));
   OHP_CUDA(cudaMemset(c->d_flag, 0, sizeof(int)));
   *out = c;
   return 0;
@@ -70,8 +77,9 @@ extern "C" int ohp_finalize(ohp_context c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   ohp_comm_destroy(c);
-  cudaFree(c->d_partials); cudaFree(c->d_ticket); cudaFree(c->d_scalars);
-  cudaFreeHost(c->h_scalars); cudaFree(c->d_cg); cudaFreeHost(c->h_cg); cudaFree(c->d_flag);
+  OHP_FREE(c, c->trace.buf); OHP_FREE(c, c->trace.count);
+  OHP_FREE(c, c->d_partials); OHP_FREE(c, c->d_ticket); OHP_FREE(c, c->d_scalars);
+  cudaFreeHost(c->h_scalars); OHP_FREE(c, c->d_cg); cudaFreeHost(c->h_cg); OHP_FREE(c, c->d_flag);
   cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -173,7 +181,7 @@ static int scan_rec(ohp_context ctx, const int32_t *in, int32_t *out, int64_t n)
     return 0;
   }
   int32_t *sums = nullptr;
-  OHP_CUDA(cudaMalloc(&sums, sizeof(int32_t) * (nt + 1)));
+  OHP_CUDA(OHP_MALLOC(ctx, &sums, sizeof(int32_t) * (nt + 1)));
   k_scan_tile_sums<<<(unsigned)nt, SCAN_T, 0, ctx->stream>>>(in, n, sums);
   OHP_CHECK_LAUNCH(ctx);
   int rc = scan_rec(ctx, sums, sums, nt);
@@ -183,7 +191,7 @@ static int scan_rec(ohp_context ctx, const int32_t *in, int32_t *out, int64_t n)
     if (cudaGetLastError() != cudaSuccess) rc = OHP_ERR_LIB;
   }
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(sums);
+  OHP_FREE(ctx, sums);
   return rc;
 }
 
@@ -226,8 +234,8 @@ extern "C" int ohp_mesh_create(ohp_context ctx, int dim, int32_t nC, int32_t nV,
   m->v2c_ptr = m->v2c = nullptr; m->bnd = nullptr; m->lidx = m->row_vertex = nullptr; m->ldof_gid = nullptr;
   m->rowptr = m->colidx = nullptr; m->col16 = nullptr; m->slot = nullptr; m->tile_row = nullptr; m->halo = nullptr; m->p2p = nullptr; m->ghost_cta = nullptr;
   m->n_owned = m->n_ghost = m->n_bnd = 0; m->n_global = m->row_start = m->nnz = 0; m->max_row = 0; m->n_tiles = 0; m->max_tile_rows = 0;
-  OHP_CUDA(cudaMalloc(&m->cells, sizeof(int32_t) * std::max<int64_t>(1, (int64_t)nC * nc)));
-  OHP_CUDA(cudaMalloc(&m->coords, sizeof(double) * std::max<int64_t>(1, (int64_t)nV * dim)));
+  OHP_CUDA(OHP_MALLOC(ctx, &m->cells, sizeof(int32_t) * std::max<int64_t>(1, (int64_t)nC * nc)));
+  OHP_CUDA(OHP_MALLOC(ctx, &m->coords, sizeof(double) * std::max<int64_t>(1, (int64_t)nV * dim)));
   OHP_CUDA(cudaMemcpyAsync(m->cells, cells, sizeof(int32_t) * (int64_t)nC * nc, cudaMemcpyHostToDevice, ctx->stream));
   OHP_CUDA(cudaMemcpyAsync(m->coords, coords, sizeof(double) * (int64_t)nV * dim, cudaMemcpyHostToDevice, ctx->stream));
   /* range check of the connectivity on the device (a host pass over 50 M ints costs more than the upload) */
@@ -254,12 +262,13 @@ extern "C" int ohp_mesh_destroy(ohp_mesh m) {
   if (!m) return 0;
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
-  cudaFree(m->cells); cudaFree(m->coords); cudaFree(m->owned); cudaFree(m->v2c_ptr); cudaFree(m->v2c);
-  cudaFree(m->bnd); cudaFree(m->lidx); cudaFree(m->row_vertex); cudaFree(m->ldof_gid); cudaFree(m->rowptr);
-  cudaFree(m->colidx); cudaFree(m->col16); cudaFree(m->slot); cudaFree(m->tile_row);
-  ohp_halo_free(m->halo);
+  OHP_FREE(m->ctx, m->cells); OHP_FREE(m->ctx, m->coords); OHP_FREE(m->ctx, m->owned); OHP_FREE(m->ctx, m->v2c_ptr); OHP_FREE(m->ctx, m->v2c);
+  OHP_FREE(m->ctx, m->bnd); OHP_FREE(m->ctx, m->lidx); OHP_FREE(m->ctx, m->row_vertex); OHP_FREE(m->ctx, m->ldof_gid); OHP_FREE(m->ctx, m->rowptr);
+  OHP_FREE(m->ctx, m->colidx); OHP_FREE(m->ctx, m->col16); OHP_FREE(m->ctx, m->slot); OHP_FREE(m->ctx, m->tile_row);
+  OHP_FREE(m->ctx, m->facet_verts); OHP_FREE(m->ctx, m->facet_support); OHP_FREE(m->ctx, m->cell_facets);
+  ohp_halo_free(m->ctx, m->halo);
   ohp_p2p_free(m->ctx, m->p2p);
-  cudaFree(m->ghost_cta);
+  OHP_FREE(m->ctx, m->ghost_cta);
   delete m;
   return 0;
 }
@@ -545,6 +554,179 @@ static int check_flag(ohp_context ctx, const char *what) {
   return 0;
 }
 
+__global__ void k_set_label(uint8_t *bnd, const int32_t *verts, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) bnd[verts[i]] = 1;
+}
+
+/* vertex -> cell stars (count, scan, fill, sort); idempotent */
+static int mesh_build_stars(ohp_mesh m) {
+  if (m->v2c_ptr) return 0;
+  ohp_context ctx = m->ctx;
+  cudaStream_t st = ctx->stream;
+  const int nc = m->nc, nV = m->nV, BS = 256;
+  const int64_t ninc = (int64_t)m->nC * nc;
+  int32_t *deg;
+  OHP_CUDA(OHP_MALLOC(ctx, &deg, sizeof(int32_t) * (nV + 1)));
+  OHP_CUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nV + 1), st));
+  OHP_CUDA(OHP_MALLOC(ctx, &m->v2c_ptr, sizeof(int32_t) * (nV + 1)));
+  OHP_CUDA(OHP_MALLOC(ctx, &m->v2c, sizeof(int32_t) * std::max<int64_t>(1, ninc)));
+  if (ninc) { k_count_incidence<<<nblk(ninc, BS), BS, 0, st>>>(m->cells, ninc, deg); OHP_CHECK_LAUNCH(ctx); }
+  OHP_TRY(ohp_scan_exclusive_i32(ctx, deg, m->v2c_ptr, nV, nullptr));
+  OHP_CUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nV + 1), st));
+  if (ninc) { k_fill_v2c<<<nblk(ninc, BS), BS, 0, st>>>(m->cells, nc, ninc, m->v2c_ptr, deg, m->v2c); OHP_CHECK_LAUNCH(ctx); }
+  k_sort_v2c<<<nblk(nV, BS), BS, 0, st>>>(m->v2c_ptr, m->v2c, nV); OHP_CHECK_LAUNCH(ctx);
+  OHP_CUDA(cudaStreamSynchronize(st));
+  OHP_FREE(ctx, deg);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Facets = what DMPlexInterpolate creates between cells and vertices (ex12.cpp:958): edges in 2-D, */
+/* triangles in 3-D.  A facet is created by the first cell (lowest index) that contains it, in that  */
+/* cell's local facet order -- the order of PETSc's interpolation loop [PETSc-internal, unverified    */
+/* here] -- so the numbering is deterministic.  Needed only by callers that walk the Plex themselves  */
+/* (DMPlexGetHeightStratum / GetSupportSize / GetCone, ex12.cpp:966-1010).                          */
+/* ------------------------------------------------------------------------------------ */
+template <int NC> struct FacetTable;
+template <> struct FacetTable<3> { /* triangle edges: (v0,v1) (v1,v2) (v2,v0) */
+  __host__ __device__ static int v(int f, int k) { return (f + k) % 3; }
+};
+template <> struct FacetTable<4> { /* tetrahedron faces: (0,1,2) (0,3,1) (0,2,3) (2,1,3) */
+  __host__ __device__ static int v(int f, int k) {
+    constexpr int F[4][3] = {{0, 1, 2}, {0, 3, 1}, {0, 2, 3}, {2, 1, 3}};
+    return F[f][k];
+  }
+};
+
+template <int NC>
+__global__ void k_facet_first(const int32_t *cells, int nC, const int32_t *ptr, const int32_t *v2c, int32_t *is_first,
+                              int32_t *mincell, int32_t *support) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)nC * NC) return;
+  const int c = (int)(i / NC), f = (int)(i % NC);
+  int fv[NC - 1];
+#pragma unroll
+  for (int k = 0; k < NC - 1; ++k) fv[k] = cells[(size_t)c * NC + FacetTable<NC>::v(f, k)];
+  int sup = 0, mc = c;
+  for (int k = ptr[fv[0]]; k < ptr[fv[0] + 1]; ++k) {
+    const int oc = v2c[k] >> 2;
+    bool all = true;
+#pragma unroll
+    for (int a = 1; a < NC - 1; ++a) {
+      bool found = false;
+#pragma unroll
+      for (int j = 0; j < NC; ++j) found |= (cells[(size_t)oc * NC + j] == fv[a]);
+      all &= found;
+    }
+    if (all) { sup++; mc = min(mc, oc); }
+  }
+  is_first[i] = (mc == c) ? 1 : 0;
+  mincell[i] = mc;
+  support[i] = sup;
+}
+
+template <int NC>
+__global__ void k_facet_fill(const int32_t *cells, int nC, const int32_t *is_first, const int32_t *scan, const int32_t *mincell,
+                             const int32_t *support, int32_t *facet_verts, int32_t *facet_support, int32_t *cell_facets) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)nC * NC) return;
+  const int c = (int)(i / NC), f = (int)(i % NC);
+  int fv[NC - 1];
+#pragma unroll
+  for (int k = 0; k < NC - 1; ++k) fv[k] = cells[(size_t)c * NC + FacetTable<NC>::v(f, k)];
+  int fid;
+  if (is_first[i]) {
+    fid = scan[i];
+#pragma unroll
+    for (int k = 0; k < NC - 1; ++k) facet_verts[(size_t)fid * (NC - 1) + k] = fv[k];
+    facet_support[fid] = support[i];
+  } else {
+    /* the same facet seen from the cell that created it: find its local number there */
+    const int oc = mincell[i];
+    fid = -1;
+#pragma unroll
+    for (int g = 0; g < NC; ++g) {
+      bool same = true;
+#pragma unroll
+      for (int k = 0; k < NC - 1; ++k) {
+        const int w = cells[(size_t)oc * NC + FacetTable<NC>::v(g, k)];
+        bool found = false;
+#pragma unroll
+        for (int a = 0; a < NC - 1; ++a) found |= (w == fv[a]);
+        same &= found;
+      }
+      if (same) fid = scan[(size_t)oc * NC + g];
+    }
+  }
+  cell_facets[i] = fid;
+}
+
+static int mesh_build_facets(ohp_mesh m) {
+  if (m->facets_built) return 0;
+  ohp_context ctx = m->ctx;
+  OHP_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  OHP_TRY(mesh_build_stars(m));
+  const int nc = m->nc, nC = m->nC, BS = 256;
+  const int64_t ninc = (int64_t)nC * nc;
+  int32_t *is_first, *scan, *mincell, *support;
+  OHP_CUDA(OHP_MALLOC(ctx, &is_first, sizeof(int32_t) * (ninc + 1)));
+  OHP_CUDA(OHP_MALLOC(ctx, &scan, sizeof(int32_t) * (ninc + 1)));
+  OHP_CUDA(OHP_MALLOC(ctx, &mincell, sizeof(int32_t) * (ninc + 1)));
+  OHP_CUDA(OHP_MALLOC(ctx, &support, sizeof(int32_t) * (ninc + 1)));
+  if (ninc) {
+    if (nc == 3) k_facet_first<3><<<nblk(ninc, BS), BS, 0, st>>>(m->cells, nC, m->v2c_ptr, m->v2c, is_first, mincell, support);
+    else k_facet_first<4><<<nblk(ninc, BS), BS, 0, st>>>(m->cells, nC, m->v2c_ptr, m->v2c, is_first, mincell, support);
+    OHP_CHECK_LAUNCH(ctx);
+  }
+  int64_t nF = 0;
+  OHP_TRY(ohp_scan_exclusive_i32(ctx, is_first, scan, ninc, &nF));
+  m->n_facets = (int32_t)nF;
+  OHP_CUDA(OHP_MALLOC(ctx, &m->facet_verts, sizeof(int32_t) * std::max<int64_t>(1, nF * (nc - 1))));
+  OHP_CUDA(OHP_MALLOC(ctx, &m->facet_support, sizeof(int32_t) * std::max<int64_t>(1, nF)));
+  OHP_CUDA(OHP_MALLOC(ctx, &m->cell_facets, sizeof(int32_t) * std::max<int64_t>(1, ninc)));
+  if (ninc) {
+    if (nc == 3) k_facet_fill<3><<<nblk(ninc, BS), BS, 0, st>>>(m->cells, nC, is_first, scan, mincell, support, m->facet_verts, m->facet_support, m->cell_facets);
+    else k_facet_fill<4><<<nblk(ninc, BS), BS, 0, st>>>(m->cells, nC, is_first, scan, mincell, support, m->facet_verts, m->facet_support, m->cell_facets);
+    OHP_CHECK_LAUNCH(ctx);
+  }
+  OHP_CUDA(cudaStreamSynchronize(st));
+  OHP_FREE(ctx, is_first); OHP_FREE(ctx, scan); OHP_FREE(ctx, mincell); OHP_FREE(ctx, support);
+  m->facets_built = true;
+  return 0;
+}
+
+extern "C" int ohp_mesh_build_facets(ohp_mesh m, int32_t *n_facets) {
+  if (!m) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_mesh_build_facets: null mesh");
+  OHP_TRY(mesh_build_facets(m));
+  if (n_facets) *n_facets = m->n_facets;
+  return 0;
+}
+
+extern "C" int ohp_mesh_get_facets(ohp_mesh m, int32_t *facet_verts, int32_t *support, int32_t *cell_facets) {
+  if (!m) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_mesh_get_facets: null mesh");
+  OHP_TRY(mesh_build_facets(m));
+  cudaStream_t st = m->ctx->stream;
+  if (facet_verts) OHP_CUDA(cudaMemcpyAsync(facet_verts, m->facet_verts, sizeof(int32_t) * (size_t)m->n_facets * (m->nc - 1), cudaMemcpyDeviceToHost, st));
+  if (support) OHP_CUDA(cudaMemcpyAsync(support, m->facet_support, sizeof(int32_t) * (size_t)m->n_facets, cudaMemcpyDeviceToHost, st));
+  if (cell_facets) OHP_CUDA(cudaMemcpyAsync(cell_facets, m->cell_facets, sizeof(int32_t) * (size_t)m->nC * m->nc, cudaMemcpyDeviceToHost, st));
+  OHP_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+/* DMSetLabelValue(dm, "marker", point, 1) for vertex points, collected (ex12.cpp:1023-1026): replaces the
+ * library's own boundary detection for the vertices this rank owns; ghost vertices still take their owner's label */
+extern "C" int ohp_mesh_set_label(ohp_mesh m, int32_t n, const int32_t *vertices) {
+  if (!m || (n > 0 && !vertices)) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_mesh_set_label: null argument");
+  if (m->setup_done) OHP_FAIL(OHP_ERR_ORDER, "ohp_mesh_set_label: called after ohp_mesh_setup");
+  for (int i = 0; i < n; ++i)
+    if (vertices[i] < 0 || vertices[i] >= m->nV) OHP_FAIL(OHP_ERR_ARG_OUTOFRANGE, "ohp_mesh_set_label: vertex %d outside [0,%d)", vertices[i], m->nV);
+  m->user_label.assign(vertices, vertices + n);
+  m->has_user_label = true;
+  return 0;
+}
+
 extern "C" int ohp_mesh_setup(ohp_mesh m) {
   if (!m) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_mesh_setup: null mesh");
   if (m->setup_done) return 0;
@@ -556,41 +738,45 @@ extern "C" int ohp_mesh_setup(ohp_mesh m) {
   const int BS = 256;
 
   /* ownership: every vertex that is not an SF leaf */
-  OHP_CUDA(cudaMalloc(&m->owned, std::max(1, nV)));
+  OHP_CUDA(OHP_MALLOC(ctx, &m->owned, std::max(1, nV)));
   k_fill_u8<<<nblk(nV, BS), BS, 0, st>>>(m->owned, nV, 1); OHP_CHECK_LAUNCH(ctx);
   const int nleaf = (int)m->ghost_vertex.size();
   if (nleaf) {
     int32_t *d_gv;
-    OHP_CUDA(cudaMalloc(&d_gv, sizeof(int32_t) * nleaf));
+    OHP_CUDA(OHP_MALLOC(ctx, &d_gv, sizeof(int32_t) * nleaf));
     OHP_CUDA(cudaMemcpyAsync(d_gv, m->ghost_vertex.data(), sizeof(int32_t) * nleaf, cudaMemcpyHostToDevice, st));
     k_clear_owned<<<nblk(nleaf, BS), BS, 0, st>>>(m->owned, d_gv, nleaf); OHP_CHECK_LAUNCH(ctx);
     OHP_CUDA(cudaStreamSynchronize(st));
-    cudaFree(d_gv);
+    OHP_FREE(ctx, d_gv);
   }
 
   /* vertex -> cell stars */
+  OHP_TRY(mesh_build_stars(m));
   int32_t *deg;
-  OHP_CUDA(cudaMalloc(&deg, sizeof(int32_t) * (nV + 1)));
-  OHP_CUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nV + 1), st));
-  OHP_CUDA(cudaMalloc(&m->v2c_ptr, sizeof(int32_t) * (nV + 1)));
-  OHP_CUDA(cudaMalloc(&m->v2c, sizeof(int32_t) * std::max<int64_t>(1, ninc)));
-  if (ninc) { k_count_incidence<<<nblk(ninc, BS), BS, 0, st>>>(m->cells, ninc, deg); OHP_CHECK_LAUNCH(ctx); }
-  OHP_TRY(ohp_scan_exclusive_i32(ctx, deg, m->v2c_ptr, nV, nullptr));
-  OHP_CUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nV + 1), st));
-  if (ninc) { k_fill_v2c<<<nblk(ninc, BS), BS, 0, st>>>(m->cells, nc, ninc, m->v2c_ptr, deg, m->v2c); OHP_CHECK_LAUNCH(ctx); }
-  k_sort_v2c<<<nblk(nV, BS), BS, 0, st>>>(m->v2c_ptr, m->v2c, nV); OHP_CHECK_LAUNCH(ctx);
+  OHP_CUDA(OHP_MALLOC(ctx, &deg, sizeof(int32_t) * (nV + 1)));
 
-  /* boundary label */
-  OHP_CUDA(cudaMalloc(&m->bnd, std::max(1, nV)));
+  /* boundary label: facets with one supporting cell (ex12.cpp:986-1010), or the label the caller set point by
+   * point with DMSetLabelValue (ex12.cpp:1023-1026) */
+  OHP_CUDA(OHP_MALLOC(ctx, &m->bnd, std::max(1, nV)));
   OHP_CUDA(cudaMemsetAsync(m->bnd, 0, std::max(1, nV), st));
-  if (nC) {
+  if (m->has_user_label) {
+    const int nl = (int)m->user_label.size();
+    if (nl) {
+      int32_t *d_lab;
+      OHP_CUDA(OHP_MALLOC(ctx, &d_lab, sizeof(int32_t) * nl));
+      OHP_CUDA(cudaMemcpyAsync(d_lab, m->user_label.data(), sizeof(int32_t) * nl, cudaMemcpyHostToDevice, st));
+      k_set_label<<<nblk(nl, BS), BS, 0, st>>>(m->bnd, d_lab, nl); OHP_CHECK_LAUNCH(ctx);
+      OHP_CUDA(cudaStreamSynchronize(st));
+      OHP_FREE(ctx, d_lab);
+    }
+  } else if (nC) {
     if (nc == 3) k_mark_boundary<3><<<nblk(nC, BS), BS, 0, st>>>(m->cells, nC, m->v2c_ptr, m->v2c, m->bnd);
     else k_mark_boundary<4><<<nblk(nC, BS), BS, 0, st>>>(m->cells, nC, m->v2c_ptr, m->v2c, m->bnd);
     OHP_CHECK_LAUNCH(ctx);
   }
   int32_t *tmp_a, *tmp_b;
-  OHP_CUDA(cudaMalloc(&tmp_a, sizeof(int32_t) * (nV + 1)));
-  OHP_CUDA(cudaMalloc(&tmp_b, sizeof(int32_t) * (nV + 1)));
+  OHP_CUDA(OHP_MALLOC(ctx, &tmp_a, sizeof(int32_t) * (nV + 1)));
+  OHP_CUDA(OHP_MALLOC(ctx, &tmp_b, sizeof(int32_t) * (nV + 1)));
   if (ctx->nranks > 1) {
     /* a ghost vertex's star is incomplete here: take its label from the owner (hazard H2) */
     k_u8_to_i32<<<nblk(nV, BS), BS, 0, st>>>(m->bnd, tmp_a, nV); OHP_CHECK_LAUNCH(ctx);
@@ -604,25 +790,25 @@ extern "C" int ohp_mesh_setup(ohp_mesh m) {
   OHP_TRY(ohp_scan_exclusive_i32(ctx, tmp_b, deg, nV, &n_bnd));
   OHP_TRY(ohp_scan_exclusive_i32(ctx, tmp_a, deg, nV, &n_owned));
   m->n_owned = (int32_t)n_owned; m->n_bnd = (int32_t)n_bnd;
-  OHP_CUDA(cudaMalloc(&m->lidx, sizeof(int32_t) * std::max(1, nV)));
-  OHP_CUDA(cudaMalloc(&m->row_vertex, sizeof(int32_t) * std::max(1, m->n_owned)));
+  OHP_CUDA(OHP_MALLOC(ctx, &m->lidx, sizeof(int32_t) * std::max(1, nV)));
+  OHP_CUDA(OHP_MALLOC(ctx, &m->row_vertex, sizeof(int32_t) * std::max(1, m->n_owned)));
   k_assign_rows<<<nblk(nV, BS), BS, 0, st>>>(tmp_a, deg, nV, m->lidx, m->row_vertex); OHP_CHECK_LAUNCH(ctx);
   OHP_CUDA(cudaStreamSynchronize(st));
-  cudaFree(tmp_a); cudaFree(tmp_b); cudaFree(deg);
+  OHP_FREE(ctx, tmp_a); OHP_FREE(ctx, tmp_b); OHP_FREE(ctx, deg);
 
   /* global numbering: ranks concatenated in rank order; ghost dofs + halo plan */
   m->row_start = 0; m->n_global = m->n_owned; m->n_ghost = 0;
   if (ctx->nranks > 1) OHP_TRY(ohp_halo_build(m)); /* sets row_start, n_global, n_ghost, ghost lidx, ldof_gid */
   else {
-    OHP_CUDA(cudaMalloc(&m->ldof_gid, sizeof(int64_t) * std::max(1, m->n_owned)));
+    OHP_CUDA(OHP_MALLOC(ctx, &m->ldof_gid, sizeof(int64_t) * std::max(1, m->n_owned)));
     k_owned_gid<<<nblk(m->n_owned, BS), BS, 0, st>>>(m->ldof_gid, m->n_owned, 0); OHP_CHECK_LAUNCH(ctx);
   }
 
   /* CSR pattern: count, scan, fill */
   const int N = m->n_owned;
   int32_t *rowlen;
-  OHP_CUDA(cudaMalloc(&rowlen, sizeof(int32_t) * (N + 1)));
-  OHP_CUDA(cudaMalloc(&m->rowptr, sizeof(int32_t) * (N + 1)));
+  OHP_CUDA(OHP_MALLOC(ctx, &rowlen, sizeof(int32_t) * (N + 1)));
+  OHP_CUDA(OHP_MALLOC(ctx, &m->rowptr, sizeof(int32_t) * (N + 1)));
   if (N) {
     if (nc == 3) k_row_pattern<3><<<nblk(N, PAT_WARPS), PAT_WARPS * 32, 0, st>>>(m->cells, m->v2c_ptr, m->v2c, m->lidx, m->row_vertex, N, 0, rowlen, nullptr, nullptr, ctx->d_flag);
     else k_row_pattern<4><<<nblk(N, PAT_WARPS), PAT_WARPS * 32, 0, st>>>(m->cells, m->v2c_ptr, m->v2c, m->lidx, m->row_vertex, N, 0, rowlen, nullptr, nullptr, ctx->d_flag);
@@ -630,10 +816,10 @@ extern "C" int ohp_mesh_setup(ohp_mesh m) {
   }
   OHP_TRY(check_flag(ctx, "ohp_mesh_setup (pattern count)"));
   OHP_TRY(ohp_scan_exclusive_i32(ctx, rowlen, m->rowptr, N, &m->nnz));
-  cudaFree(rowlen);
-  OHP_CUDA(cudaMalloc(&m->colidx, sizeof(int32_t) * ohp_padded_nnz(m->nnz)));
+  OHP_FREE(ctx, rowlen);
+  OHP_CUDA(OHP_MALLOC(ctx, &m->colidx, sizeof(int32_t) * ohp_padded_nnz(m->nnz)));
   OHP_CUDA(cudaMemsetAsync(m->colidx, 0, sizeof(int32_t) * ohp_padded_nnz(m->nnz), st));
-  OHP_CUDA(cudaMalloc(&m->slot, std::max<int64_t>(1, ninc * nc)));
+  OHP_CUDA(OHP_MALLOC(ctx, &m->slot, std::max<int64_t>(1, ninc * nc)));
   OHP_CUDA(cudaMemsetAsync(m->slot, 0xff, std::max<int64_t>(1, ninc * nc), st));
   if (N) {
     if (nc == 3) k_row_pattern<3><<<nblk(N, PAT_WARPS), PAT_WARPS * 32, 0, st>>>(m->cells, m->v2c_ptr, m->v2c, m->lidx, m->row_vertex, N, 1, nullptr, m->rowptr, m->colidx, ctx->d_flag);
@@ -647,34 +833,34 @@ extern "C" int ohp_mesh_setup(ohp_mesh m) {
 
   /* 16-bit column offsets (2 B/nnz less SpMV traffic) when the ordering keeps every row's columns within +-32767 */
   if (N) {
-    OHP_CUDA(cudaMalloc(&m->col16, sizeof(int16_t) * ohp_padded_nnz(m->nnz)));
+    OHP_CUDA(OHP_MALLOC(ctx, &m->col16, sizeof(int16_t) * ohp_padded_nnz(m->nnz)));
     OHP_CUDA(cudaMemsetAsync(m->col16, 0, sizeof(int16_t) * ohp_padded_nnz(m->nnz), st));
     k_col16<<<nblk(N, BS), BS, 0, st>>>(m->rowptr, m->colidx, N, m->col16, ctx->d_flag); OHP_CHECK_LAUNCH(ctx);
     int overflow = 0;
     OHP_CUDA(cudaMemcpyAsync(&overflow, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     OHP_CUDA(cudaStreamSynchronize(st));
-    if (overflow) {
+    if (overflow) { /* e.g. a space-filling-curve ordering: the 32-bit stream costs 6 % (measured), see ohp_dev.cuh */
       OHP_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), st));
-      cudaFree(m->col16);
+      OHP_FREE(ctx, m->col16);
       m->col16 = nullptr;
     }
   }
 
   /* longest row + SpMV tiles */
   int32_t *d_max;
-  OHP_CUDA(cudaMalloc(&d_max, sizeof(int32_t)));
+  OHP_CUDA(OHP_MALLOC(ctx, &d_max, sizeof(int32_t)));
   OHP_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int32_t), st));
   if (N) { k_max_rowlen<<<nblk(N, BS), BS, 0, st>>>(m->rowptr, N, d_max); OHP_CHECK_LAUNCH(ctx); }
   OHP_CUDA(cudaMemcpyAsync(&m->max_row, d_max, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   OHP_CUDA(cudaStreamSynchronize(st));
-  cudaFree(d_max);
+  OHP_FREE(ctx, d_max);
   m->n_tiles = (int32_t)((m->nnz + kSpmvTile - 1) / kSpmvTile);
   if (m->n_tiles == 0 && N > 0) m->n_tiles = 1;
-  OHP_CUDA(cudaMalloc(&m->tile_row, sizeof(int32_t) * (m->n_tiles + 1)));
+  OHP_CUDA(OHP_MALLOC(ctx, &m->tile_row, sizeof(int32_t) * (m->n_tiles + 1)));
   k_tile_rows<<<nblk(m->n_tiles + 1, BS), BS, 0, st>>>(m->rowptr, N, kSpmvTile, m->n_tiles, m->tile_row); OHP_CHECK_LAUNCH(ctx);
   if (ctx->nranks > 1 && m->n_tiles > 0) {
     const int G = std::max(1, std::min(m->n_tiles, ctx->num_sms));
-    OHP_CUDA(cudaMalloc(&m->ghost_cta, ctx->num_sms));
+    OHP_CUDA(OHP_MALLOC(ctx, &m->ghost_cta, ctx->num_sms));
     OHP_CUDA(cudaMemsetAsync(m->ghost_cta, 1, ctx->num_sms, st));
     k_ghost_cta<<<G, 256, 0, st>>>(m->colidx, m->nnz, m->n_owned, m->n_tiles, kSpmvTile, m->ghost_cta); OHP_CHECK_LAUNCH(ctx);
   }
@@ -758,5 +944,6 @@ int ohp_assembly_view_make(ohp_mesh m, const double *u, double *out, ohp_assembl
   vw->row_vertex_dev = m->row_vertex; vw->v2c_ptr_dev = m->v2c_ptr; vw->v2c_dev = m->v2c;
   vw->slot_dev = m->slot; vw->rowptr_dev = m->rowptr; vw->u_dev = u; vw->out_dev = out;
   vw->stream = (void *)m->ctx->stream;
+  vw->owned_dev = m->owned; vw->n_partials = 0;
   return 0;
 }

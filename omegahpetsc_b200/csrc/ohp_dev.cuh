@@ -86,6 +86,23 @@ __device__ __forceinline__ bool grid_sum(double (&v)[NV], double *partials, unsi
 /* ------------------------------------------------------------------------------------ */
 enum { OHP_MODE_SERIAL = 0, OHP_MODE_NCCL = 1, OHP_MODE_P2P = 2 };
 
+/* Device-side timeline of the CG loop (OHP_TRACE_CG=<file>): selected threads append (event, iteration, block,
+ * %globaltimer) records to a ring in HBM; the host dumps them after the solve.  This is how the shares of the
+ * iteration that are not data movement (launch ramp, halo wait, all-reduce, rank skew) are measured on the
+ * multi-GPU runs, where a profiler cannot be attached.  A null buffer costs one predicated branch. */
+enum { TR_VEC_BEGIN = 1, TR_VEC_HALO_PUSHED = 2, TR_VEC_END = 3, TR_SPMV_BEGIN = 4, TR_SPMV_HALO_READY = 5, TR_SPMV_CTA_DONE = 6,
+       TR_SPMV_LAST_BLOCK = 7, TR_AR_POSTED = 8, TR_AR_DONE = 9, TR_SPMV_END = 10, TR_UPD_BEGIN = 11, TR_UPD_END = 12 };
+__device__ __forceinline__ unsigned long long trace_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_put(const ohp_trace &tr, int ev, int it) {
+  if (!tr.buf || it < tr.it0 || it >= tr.it1) return;
+  const unsigned k = atomicAdd(tr.count, 1u);
+  if (k < tr.cap) { ohp_trace_rec r; r.t = trace_now(); r.ev = ev; r.it = it; r.blk = (int)blockIdx.x; r.pad = 0; tr.buf[k] = r; }
+}
+
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -99,15 +116,18 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-/* spin until *flag >= seq.  A peer that died must not hang this GPU: after 2 s the wait gives up and raises
- * seq[2]; once it is raised every later wait returns at once, so the chunk in flight drains quickly and the
- * host (which reads seq[2] after the chunk) fails the solve with an error instead of hanging the box. */
-__device__ __forceinline__ void p2p_wait(const unsigned long long *flag, unsigned long long seq, unsigned long long *err) {
+/* spin until *flag >= seq.  A peer that died must not hang this GPU: after `timeout_ns` (ohp_p2p_dev::timeout_ns,
+ * OHP_P2P_TIMEOUT_S, default 60 s -- far above any rank skew a healthy run can show: the ranks enter every solve
+ * through a stream-ordered barrier) the wait gives up and raises seq[2]; once it is raised every later wait
+ * returns at once, so the chunk in flight drains quickly and the host (which reads seq[2] after the chunk) fails
+ * the solve with an error, then clears the flag, instead of hanging the box. */
+__device__ __forceinline__ void p2p_wait(const unsigned long long *flag, unsigned long long seq, unsigned long long *err,
+                                         unsigned long long timeout_ns) {
   if (ld_acquire_sys(flag) >= seq) return;
   if (*(volatile unsigned long long *)err) return;
   const unsigned long long t0 = global_ns();
   while (ld_acquire_sys(flag) < seq) {
-    if (global_ns() - t0 > 2000000000ull) { *(volatile unsigned long long *)err = 1ull; return; }
+    if (global_ns() - t0 > timeout_ns) { *(volatile unsigned long long *)err = 1ull; return; }
   }
 }
 
@@ -128,7 +148,7 @@ template <int NV> __device__ __forceinline__ void p2p_allreduce(const ohp_p2p_de
     for (int k = 0; k < NV; ++k) s->v[k] = mine[k];
     st_release_sys(&s->seq, seq);
     const ohp_ar_slot *r = pd.slots[pd.rank] + par * kMaxRanks + lane;
-    p2p_wait(&r->seq, seq, pd.seq + 2);
+    p2p_wait(&r->seq, seq, pd.seq + 2, pd.timeout_ns);
 #pragma unroll
     for (int k = 0; k < NV; ++k) got[k] = r->v[k];
   }
@@ -161,6 +181,32 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint3
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+/* L2 residency control for the matrix stream.  The matrix never changes during a solve and is re-read every
+ * iteration, so the tiles that fit a share of the 126 MB L2 are loaded with an evict_last policy (they survive
+ * the vector traffic between two SpMVs) and the rest with evict_first (they stream through without displacing
+ * the resident ones).  Which tiles are resident is a fixed function of the tile index, so the same lines hit
+ * every iteration. */
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_1d_hint(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+/* plain (coherent, L1-cacheable) load: for vectors that peers or this kernel write while it runs, where the
+ * read-only path (ld.global.nc, __ldg) is undefined */
+__device__ __forceinline__ double ld_weak(const double *p) {
+  double v;
+  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -171,9 +217,12 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
 /* sum_{k in [a,b)} vs[k] * x[cs[k]], ascending k; loads batched 8 at a time for memory-level parallelism */
 /* IDX = int32_t: absolute local column ids.  IDX = int16_t: column = row + delta (the compressed
  * index stream used when every |column - row| fits 16 bits, which mesh-ordered matrices do). */
-template <class IDX>
+/* (An escape code for the few offsets that do not fit 16 bits -- ~1 % of the entries of a Morton-ordered box -- was
+ * measured in round 2: the data-dependent second load in the gather loop cost 33 % of the SpMV (0.192 vs 0.144 ms on
+ * the 16 M-triangle box), far more than the 6 % the 32-bit stream costs, so such matrices use the 32-bit stream.) */
+template <class IDX, bool COHERENT = false>
 __device__ __forceinline__ double row_dot(const double *__restrict__ vs, const IDX *__restrict__ cs,
-                                          int a, int b, const double *__restrict__ x, double s, int row) {
+                                          int a, int b, const double *x, double s, int row) {
   for (int k = a; k < b; k += 8) {
     double xv[8], vv[8];
 #pragma unroll
@@ -181,7 +230,7 @@ __device__ __forceinline__ double row_dot(const double *__restrict__ vs, const I
       const bool ok = (k + j) < b;
       const int c = ok ? (sizeof(IDX) == 2 ? row + (int)cs[k + j] : (int)cs[k + j]) : 0;
       vv[j] = ok ? vs[k + j] : 0.0;
-      xv[j] = ok ? __ldg(x + c) : 0.0;
+      xv[j] = ok ? (COHERENT ? ld_weak(x + c) : __ldg(x + c)) : 0.0;
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -239,6 +288,8 @@ struct ohp_cgcg_epi {
   int nvpart, jacobi, hist_cap;
   double *hist;
   const uint8_t *ghost_cta; /* non-NULL: the SpMV itself waits for the halo, and only in the CTAs flagged here */
+  int pin_tiles;            /* leading tiles of every CTA loaded with the L2 evict_last policy (0 = no hints at all) */
+  ohp_trace trace;          /* optional device-side timeline (OHP_TRACE_CG) */
 };
 
 #endif

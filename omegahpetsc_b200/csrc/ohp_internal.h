@@ -27,6 +27,14 @@ void ohp_set_error(const char *fmt, ...);
                cudaGetErrorString(e__));                                                      \
   } while (0)
 
+/* Device memory comes from the device's stream-ordered pool (cudaMallocAsync on the context stream, release threshold
+ * raised to "never" in ohp_init): after warm-up neither an allocation nor a free enters the driver's resource manager,
+ * which serialises with every NVML / nvidia-smi query on the box (measured in round 2: with a clock sampler running,
+ * single cudaMalloc/cudaFree calls inside a Newton step stalled it by 0.2-1.5 s).  The exchange heap of the NVLink peer
+ * path stays cudaMalloc'ed (CUDA IPC cannot export pool memory). */
+#define OHP_MALLOC(ctx_, pptr, bytes) cudaMallocAsync((void **)(pptr), (size_t)(bytes), (ctx_)->stream)
+#define OHP_FREE(ctx_, ptr) do { if (ptr) cudaFreeAsync((void *)(ptr), (ctx_)->stream); } while (0)
+
 #define OHP_TRY(expr)                 \
   do {                                \
     int rc__ = (expr);                \
@@ -52,6 +60,10 @@ struct ohp_cg_state {
 
 struct ohp_halo;  /* ohp_comm.cu */
 
+/* device-side timeline of the CG loop (OHP_TRACE_CG, see ohp_dev.cuh) */
+struct ohp_trace_rec { unsigned long long t; int ev, it, blk, pad; };
+struct ohp_trace { ohp_trace_rec *buf; unsigned *count; unsigned cap; int it0, it1; };
+
 /* ---- peer-to-peer (NVLink) view of the communicator, passed BY VALUE to the CG kernels ---- */
 constexpr int kMaxRanks = 8;
 struct ohp_ar_slot { double v[3]; unsigned long long seq; }; /* 32 B: payload, then the sequence number (release-stored last) */
@@ -65,7 +77,8 @@ struct ohp_p2p_dev {
   ohp_ar_slot *slots[kMaxRanks];     /* slots[q]: rank q's all-reduce mailbox (2 parities x kMaxRanks sources) */
   unsigned long long *hflags[kMaxRanks]; /* hflags[q][src]: sequence number of src's last halo push into q */
   double *p[2][kMaxRanks];           /* p[b][q]: rank q's search-direction buffer b (owned dofs + ghost tail) */
-  unsigned long long *seq;           /* local counters: [0] all-reduces issued, [1] halo pushes issued */
+  unsigned long long *seq;           /* local counters: [0] all-reduces issued, [1] halo pushes issued, [2] wait-timeout flag */
+  unsigned long long timeout_ns;     /* how long a peer wait may spin before it raises seq[2] */
 };
 struct ohp_p2p {
   void *heap = nullptr;              /* cudaMalloc'ed, exported with cudaIpcGetMemHandle */
@@ -89,6 +102,7 @@ struct ohp_context_s {
   ohp_cg_state *d_cg;
   ohp_cg_state *h_cg;   /* pinned */
   int *d_flag;          /* device error flag for setup kernels */
+  ohp_trace trace;      /* buf == NULL unless OHP_TRACE_CG is set */
   /* communicator (NULL = serial) */
   void *nccl_lib;
   void *comm;
@@ -134,6 +148,12 @@ struct ohp_mesh_s {
   int32_t max_tile_rows; /* most rows starting inside one tile */
   ohp_halo *halo;    /* dof-level halo plan (NULL when serial) */
   ohp_p2p *p2p;      /* NVLink peer mapping (NULL until ohp_mesh_p2p_attach) */
+  /* facets (DMPlexInterpolate's edges / faces), built on demand for Plex queries */
+  bool facets_built;
+  int32_t n_facets, *facet_verts, *facet_support, *cell_facets;
+  /* "marker" label set point by point by the caller (DMSetLabelValue) instead of detected here */
+  bool has_user_label;
+  std::vector<int32_t> user_label;
   uint8_t *ghost_cta; /* per persistent-SpMV CTA: 1 if its tiles reference ghost columns (NULL when serial) */
 };
 
@@ -160,16 +180,25 @@ int ohp_assembly_view_make(ohp_mesh mesh, const double *u, double *out, ohp_asse
 
 /* ohp_comm.cu */
 int ohp_halo_build(ohp_mesh mesh);
-void ohp_halo_free(ohp_halo *h);
+void ohp_halo_free(ohp_context ctx, ohp_halo *h);
 /* fill the ghost tail x[n_owned ..] from the owners (on the context stream) */
 int ohp_halo_exchange(ohp_mesh mesh, double *x);
 int ohp_allreduce_sum(ohp_context ctx, double *d_vals, int n);
 int ohp_vertex_halo_i32(ohp_mesh mesh, int32_t *vertex_data_dev);
 int ohp_allgather_i64(ohp_context ctx, int64_t mine, std::vector<int64_t> &all);
+int ohp_sparse_exchange(ohp_context ctx, int elem_bytes, const void *d_send, const std::vector<int64_t> &scount,
+                        void **d_recv, std::vector<int64_t> &rcount);
 void ohp_comm_destroy(ohp_context ctx);
 void ohp_p2p_free(ohp_context ctx, ohp_p2p *p);
+/* solve entry in the peer-to-peer modes: a stream-ordered barrier over the communicator, so that the first fused
+ * all-reduce / halo wait of a solve never measures start-up skew (lazy module load, allocation, a profiler) */
+int ohp_p2p_entry_barrier(ohp_mesh mesh);
+/* after a solve: did a peer wait time out?  Clears the flag once it has been reported. */
+int ohp_p2p_check(ohp_mesh mesh, const char *what);
 
 /* ohp_linalg.cu */
+ohp_trace ohp_cg_trace_open(ohp_context ctx);
+void ohp_cg_trace_dump(ohp_context ctx, const char *algo);
 int ohp_spmv_launch(ohp_mat A, const double *x, double *y);
 int ohp_extract_dinv(ohp_mat A);
 
@@ -178,6 +207,6 @@ int ohp_cg_persistent_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_optio
 
 /* ohp_problems.cu */
 int ohp_problem_lookup(int id, ohp_assembly_launcher *res, ohp_assembly_launcher *jac,
-                       ohp_assembly_launcher *proj);
+                       ohp_assembly_launcher *proj, ohp_assembly_launcher *l2);
 
 #endif

@@ -84,10 +84,12 @@ __device__ __forceinline__ const double *cg_pick_input(const ohp_cg_state *st, c
 
 /* run by every thread of the LAST block of a CG SpMV (dot[0] = (x, A x) valid in thread 0) */
 __device__ __forceinline__ void cg_spmv_epilogue(ohp_cg_state *st, double (&dot)[1], double *sums, int mode,
-                                                 const ohp_p2p_dev &pd, const ohp_cgcg_epi &epi) {
+                                                 const ohp_p2p_dev &pd, const ohp_cgcg_epi &epi, int its_now = 0) {
+  if (threadIdx.x == 0) trace_put(epi.trace, TR_SPMV_LAST_BLOCK, its_now);
   if (!epi.vpart) { /* classic: (p, Ap) -> alpha */
     if (mode == OHP_MODE_P2P) p2p_allreduce<1>(pd, dot);
     if (threadIdx.x == 0) {
+      trace_put(epi.trace, TR_AR_DONE, its_now);
       sums[0] = dot[0];
       if (mode != OHP_MODE_NCCL) cg_fin_spmv(st, dot[0]);
     }
@@ -98,8 +100,13 @@ __device__ __forceinline__ void cg_spmv_epilogue(ohp_cg_state *st, double (&dot)
   double tot[3] = {0.0, threadIdx.x == 0 ? dot[0] : 0.0, 0.0};
   for (int b = threadIdx.x; b < epi.nvpart; b += blockDim.x) { tot[0] += __ldcg(epi.vpart + 2 * b); tot[2] += __ldcg(epi.vpart + 2 * b + 1); }
   block_sum<3>(tot, s_red3);
+  if (threadIdx.x == 0) trace_put(epi.trace, TR_AR_POSTED, its_now);
   if (mode == OHP_MODE_P2P) p2p_allreduce<3>(pd, tot);
-  if (threadIdx.x == 0) cgcg_scalars(st, epi.hist, epi.hist_cap, tot[0], tot[1], epi.jacobi ? tot[2] : tot[0]);
+  if (threadIdx.x == 0) {
+    trace_put(epi.trace, TR_AR_DONE, its_now);
+    cgcg_scalars(st, epi.hist, epi.hist_cap, tot[0], tot[1], epi.jacobi ? tot[2] : tot[0]);
+    trace_put(epi.trace, TR_SPMV_END, its_now);
+  }
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -151,116 +158,169 @@ k_spmv_stream(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ co
 /* A row that straddles a tile boundary is carried in a register by the thread that       */
 /* started it (same thread finishes it in the next tile), so the order stays serial.      */
 /* ------------------------------------------------------------------------------------ */
+/* the consumer warps' tile loop; COHERENT selects plain loads of x (CTAs whose columns include ghost dofs that
+ * peers write over NVLink while the kernel runs) instead of the read-only path */
+template <bool CG, int S, int NC, class IDX, bool SPLIT, bool COHERENT>
+__device__ __forceinline__ double spmv_consume(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colidx,
+                                               const double *__restrict__ vals,
+                                               const double *x, double *__restrict__ y, const double *vals_s, const IDX *cols_s,
+                                               const int32_t *rp_s, uint32_t full0, uint32_t empty0, int t0, int t1) {
+  constexpr int T = kSpmvTile;
+  const int tid = threadIdx.x, lane = tid & 31;
+  double dot = 0.0, carry = 0.0;
+  int pend = -1;
+  for (int t = t0; t < t1; ++t) {
+    const int i = t - t0, s = i % S;
+    mbar_wait(full0 + 8 * s, (i / S) & 1);
+    const int32_t *rp = rp_s + s * kTmaRpStride;
+    const double *vs = vals_s + s * T;
+    const IDX *cs = cols_s + s * T;
+    const int rs = rp[kSpmvRowCap + 2], re = rp[kSpmvRowCap + 3];
+    const int base = t * T, lim = base + T;
+    if (pend >= 0) { /* finish (or continue) the row this thread carried over the tile boundary */
+      const int end = rp[0];
+      carry = row_dot<IDX, COHERENT>(vs, cs, 0, min(end, lim) - base, x, carry, pend);
+      if (end <= lim) { y[pend] = carry; if (CG) dot += carry * (COHERENT ? ld_weak(x + pend) : __ldg(x + pend)); pend = -1; }
+    }
+    if (!SPLIT) {
+      for (int r = rs + tid; r < re; r += NC) {
+        const int a = rp[r - rs], b = rp[r - rs + 1];
+        const double sum = row_dot<IDX, COHERENT>(vs, cs, a - base, min(b, lim) - base, x, 0.0, r);
+        if (b > lim) { carry = sum; pend = r; }
+        else { y[r] = sum; if (CG) dot += sum * (COHERENT ? ld_weak(x + r) : __ldg(x + r)); }
+      }
+    } else {
+      /* SPLIT (matrices with long rows, e.g. 15 non-zeros per row in 3-D): when a tile starts few rows, 2 or 4
+       * adjacent lanes share a row so that it still costs one gather latency; their partial sums are combined in
+       * a fixed butterfly order.  The choice depends on the tile only, so results stay reproducible. */
+      const int nrows = re - rs;
+      const int tpr = (nrows * 4 <= NC) ? 4 : (nrows * 2 <= NC) ? 2 : 1;
+      const int sub = tid & (tpr - 1), grp = tid / tpr, ngrp = NC / tpr;
+      for (int rb = rs; rb < re; rb += ngrp) { /* uniform trip count: the shuffles below need the whole warp */
+        const int r = rb + grp;
+        const bool valid = r < re;
+        int a = 0, b = 0;
+        if (valid) { a = rp[r - rs]; b = rp[r - rs + 1]; }
+        const int bl = min(b, lim);
+        int ca = a, cb = bl;
+        if (tpr > 1) {
+          if (b > lim) { if (sub != 0) cb = ca; }          /* a straddling row stays with its leader (serial order) */
+          else { const int chunk = (bl - a + tpr - 1) / tpr; ca = min(a + sub * chunk, bl); cb = min(ca + chunk, bl); }
+        }
+        double part = (valid && cb > ca) ? row_dot<IDX, COHERENT>(vs, cs, ca - base, cb - base, x, 0.0, r) : 0.0;
+        if (tpr > 1) part += __shfl_xor_sync(0xffffffffu, part, 1); /* tpr is uniform over the CTA */
+        if (tpr > 2) part += __shfl_xor_sync(0xffffffffu, part, 2);
+        if (valid && sub == 0) {
+          if (b > lim) { carry = part; pend = r; }
+          else { y[r] = part; if (CG) dot += part * (COHERENT ? ld_weak(x + r) : __ldg(x + r)); }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty0 + 8 * s);
+  }
+  if (pend >= 0) { /* the row runs past this CTA's last tile: finish it straight from HBM */
+    const int end = __ldg(rowptr + pend + 1);
+    for (int k = t1 * T; k < end; ++k) {
+      const int c = sizeof(IDX) == 2 ? pend + (int)colidx[k] : (int)colidx[k];
+      carry += vals[k] * (COHERENT ? ld_weak(x + c) : __ldg(x + c));
+    }
+    y[pend] = carry;
+    if (CG) dot += carry * (COHERENT ? ld_weak(x + pend) : __ldg(x + pend));
+  }
+  return dot;
+}
+
 template <bool CG, int kTmaStages, int kTmaConsumers, class IDX, bool SPLIT, int MINB = 1>
 __global__ void __launch_bounds__(kTmaConsumers + 32, MINB)
-k_spmv_tma(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colidx, const double *__restrict__ vals,
-           const double *__restrict__ x, double *__restrict__ y, const int32_t *__restrict__ tile_row, int n_tiles,
+k_spmv_tma(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colidx, const double *__restrict__ vals, const double *x, double *__restrict__ y, const int32_t *__restrict__ tile_row, int n_tiles,
            ohp_cg_state *st, double *partials, unsigned *ticket, double *sums, int mode,
-           const double *__restrict__ x_alt, const ohp_p2p_dev pd, const ohp_cgcg_epi epi) {
+           const double *x_alt, const ohp_p2p_dev pd, const ohp_cgcg_epi epi) {
   constexpr int T = kSpmvTile, S = kTmaStages, NC = kTmaConsumers;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  pdl_wait();
-  pdl_launch();
-  if (CG && st->done) return;
-  if (CG) x = cg_pick_input(st, epi, x, x_alt);
   double *vals_s = reinterpret_cast<double *>(smem_raw);
   IDX *cols_s = reinterpret_cast<IDX *>(vals_s + S * T);
   int32_t *rp_s = reinterpret_cast<int32_t *>(cols_s + S * T);
   uint64_t *bars = reinterpret_cast<uint64_t *>(rp_s + S * kTmaRpStride);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int t0 = (int)(((int64_t)n_tiles * blockIdx.x) / gridDim.x);
+  const int t1 = (int)(((int64_t)n_tiles * (blockIdx.x + 1)) / gridDim.x);
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 33); mbar_init(empty0 + 8 * s, NC / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  /* halo/compute overlap: the vector kernel only PUSHED its halo; the neighbours' values are awaited here, and
-   * only by the CTAs whose tiles reference ghost columns (the strips' first and last CTAs): interior CTAs start at once */
-  if (CG && mode == OHP_MODE_P2P && epi.ghost_cta && epi.ghost_cta[blockIdx.x] && tid < pd.n_nbr)
-    p2p_wait(pd.hflags[pd.rank] + pd.nbr[tid], pd.seq[1], pd.seq + 2);
   __syncthreads();
-  const int t0 = (int)(((int64_t)n_tiles * blockIdx.x) / gridDim.x);
-  const int t1 = (int)(((int64_t)n_tiles * (blockIdx.x + 1)) / gridDim.x);
-  double dot[1] = {0.0};
-  if (warp == NC / 32) {
-    /* ---------------- producer warp ---------------- */
-    for (int t = t0; t < t1; ++t) {
-      const int i = t - t0, s = i % S;
-      mbar_wait(empty0 + 8 * s, ((i / S) & 1) ^ 1);
-      const int rs = __ldg(tile_row + t), re = __ldg(tile_row + t + 1);
-      if (lane == 0) {
-        mbar_expect_tx(full0 + 8 * s, T * (8 + (int)sizeof(IDX)));
+  /* The matrix (vals, colidx, rowptr, tile_row) is constant during a solve: the producer warp starts streaming the
+   * first stages BEFORE griddepcontrol.wait, i.e. while the predecessor kernel is still draining; only x, the
+   * scalars and everything written below depend on the predecessor. */
+  const bool is_producer = (warp == NC / 32);
+  int issued = 0;
+  const uint64_t pol_last = l2_policy_evict_last(), pol_first = l2_policy_evict_first();
+  auto issue_tile = [&](int t) {
+    const int i = t - t0, s = i % S;
+    const int rs = __ldg(tile_row + t), re = __ldg(tile_row + t + 1);
+    if (lane == 0) {
+      mbar_expect_tx(full0 + 8 * s, T * (8 + (int)sizeof(IDX)));
+      if (epi.pin_tiles > 0) {
+        const uint64_t pol = (i < epi.pin_tiles) ? pol_last : pol_first;
+        tma_load_1d_hint(smem_u32(vals_s + s * T), vals + (size_t)t * T, T * 8, full0 + 8 * s, pol);
+        tma_load_1d_hint(smem_u32(cols_s + s * T), colidx + (size_t)t * T, T * (int)sizeof(IDX), full0 + 8 * s, pol);
+      } else {
         tma_load_1d(smem_u32(vals_s + s * T), vals + (size_t)t * T, T * 8, full0 + 8 * s);
         tma_load_1d(smem_u32(cols_s + s * T), colidx + (size_t)t * T, T * (int)sizeof(IDX), full0 + 8 * s);
       }
-      int32_t *rp = rp_s + s * kTmaRpStride;
-      for (int j = lane; j <= re - rs; j += 32) cp_async4(smem_u32(rp + j), rowptr + rs + j);
-      if (lane < 2) cp_async4(smem_u32(rp + kSpmvRowCap + 2 + lane), tile_row + t + lane);
-      cp_async_mbar_arrive_noinc(full0 + 8 * s);
+    }
+    int32_t *rp = rp_s + s * kTmaRpStride;
+    for (int j = lane; j <= re - rs; j += 32) cp_async4(smem_u32(rp + j), rowptr + rs + j);
+    if (lane < 2) cp_async4(smem_u32(rp + kSpmvRowCap + 2 + lane), tile_row + t + lane);
+    cp_async_mbar_arrive_noinc(full0 + 8 * s);
+  };
+#ifndef OHP_AB_NOPREFETCH
+  if (is_producer) {
+    for (; issued < S && t0 + issued < t1; ++issued) issue_tile(t0 + issued); /* stages are free at kernel start */
+  }
+#endif
+  pdl_wait();
+  pdl_launch();
+  if (CG && st->done) {
+    /* bulk copies already in flight must land before the CTA's shared memory is released */
+    if (is_producer) for (int i = 0; i < issued; ++i) mbar_wait(full0 + 8 * (i % S), 0);
+    return;
+  }
+  const int its_now = CG ? st->its : 0;
+  if (CG) x = cg_pick_input(st, epi, x, x_alt);
+  if (CG && blockIdx.x == 0 && tid == 0) trace_put(epi.trace, TR_SPMV_BEGIN, its_now);
+  /* halo/compute overlap: the vector kernel only PUSHED its halo; the neighbours' values are awaited here, and
+   * only by the CTAs whose tiles reference ghost columns (the strips' first and last CTAs): interior CTAs start at once */
+#ifdef OHP_AB_NOCOHERENT
+  const bool ghost_cta = false;
+#else
+  const bool ghost_cta = CG && mode == OHP_MODE_P2P && epi.ghost_cta && epi.ghost_cta[blockIdx.x];
+#endif
+  double dot[1] = {0.0};
+  if (is_producer) {
+    /* ---------------- producer warp ---------------- */
+    for (int t = t0 + issued; t < t1; ++t) {
+      const int i = t - t0, s = i % S;
+      mbar_wait(empty0 + 8 * s, ((i / S) & 1) ^ 1);
+      issue_tile(t);
     }
   } else {
     /* ---------------- consumer warps ---------------- */
-    double carry = 0.0;
-    int pend = -1;
-    for (int t = t0; t < t1; ++t) {
-      const int i = t - t0, s = i % S;
-      mbar_wait(full0 + 8 * s, (i / S) & 1);
-      const int32_t *rp = rp_s + s * kTmaRpStride;
-      const double *vs = vals_s + s * T;
-      const IDX *cs = cols_s + s * T;
-      const int rs = rp[kSpmvRowCap + 2], re = rp[kSpmvRowCap + 3];
-      const int base = t * T, lim = base + T;
-      if (pend >= 0) { /* finish (or continue) the row this thread carried over the tile boundary */
-        const int end = rp[0];
-        carry = row_dot<IDX>(vs, cs, 0, min(end, lim) - base, x, carry, pend);
-        if (end <= lim) { y[pend] = carry; if (CG) dot[0] += carry * __ldg(x + pend); pend = -1; }
-      }
-      if (!SPLIT) {
-        for (int r = rs + tid; r < re; r += NC) {
-          const int a = rp[r - rs], b = rp[r - rs + 1];
-          const double sum = row_dot<IDX>(vs, cs, a - base, min(b, lim) - base, x, 0.0, r);
-          if (b > lim) { carry = sum; pend = r; }
-          else { y[r] = sum; if (CG) dot[0] += sum * __ldg(x + r); }
-        }
-      } else {
-        /* SPLIT (matrices with long rows, e.g. 15 non-zeros per row in 3-D): when a tile starts few rows, 2 or 4
-         * adjacent lanes share a row so that it still costs one gather latency; their partial sums are combined in
-         * a fixed butterfly order.  The choice depends on the tile only, so results stay reproducible. */
-        const int nrows = re - rs;
-        const int tpr = (nrows * 4 <= NC) ? 4 : (nrows * 2 <= NC) ? 2 : 1;
-        const int sub = tid & (tpr - 1), grp = tid / tpr, ngrp = NC / tpr;
-        for (int rb = rs; rb < re; rb += ngrp) { /* uniform trip count: the shuffles below need the whole warp */
-          const int r = rb + grp;
-          const bool valid = r < re;
-          int a = 0, b = 0;
-          if (valid) { a = rp[r - rs]; b = rp[r - rs + 1]; }
-          const int bl = min(b, lim);
-          int ca = a, cb = bl;
-          if (tpr > 1) {
-            if (b > lim) { if (sub != 0) cb = ca; }          /* a straddling row stays with its leader (serial order) */
-            else { const int chunk = (bl - a + tpr - 1) / tpr; ca = min(a + sub * chunk, bl); cb = min(ca + chunk, bl); }
-          }
-          double part = (valid && cb > ca) ? row_dot<IDX>(vs, cs, ca - base, cb - base, x, 0.0, r) : 0.0;
-          if (tpr > 1) part += __shfl_xor_sync(0xffffffffu, part, 1); /* tpr is uniform over the CTA */
-          if (tpr > 2) part += __shfl_xor_sync(0xffffffffu, part, 2);
-          if (valid && sub == 0) {
-            if (b > lim) { carry = part; pend = r; }
-            else { y[r] = part; if (CG) dot[0] += part * __ldg(x + r); }
-          }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty0 + 8 * s);
+    if (ghost_cta) {
+      if (tid < pd.n_nbr) p2p_wait(pd.hflags[pd.rank] + pd.nbr[tid], pd.seq[1], pd.seq + 2, pd.timeout_ns);
+      asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");
+      if (tid == 0) trace_put(epi.trace, TR_SPMV_HALO_READY, its_now);
+      dot[0] = spmv_consume<CG, S, NC, IDX, SPLIT, true>(rowptr, colidx, vals, x, y, vals_s, cols_s, rp_s, full0, empty0, t0, t1);
+    } else {
+      dot[0] = spmv_consume<CG, S, NC, IDX, SPLIT, false>(rowptr, colidx, vals, x, y, vals_s, cols_s, rp_s, full0, empty0, t0, t1);
     }
-    if (pend >= 0) { /* the row runs past this CTA's last tile: finish it straight from HBM */
-      const int end = __ldg(rowptr + pend + 1);
-      for (int k = t1 * T; k < end; ++k) carry += vals[k] * __ldg(x + (sizeof(IDX) == 2 ? pend + (int)colidx[k] : (int)colidx[k]));
-      y[pend] = carry;
-      if (CG) dot[0] += carry * __ldg(x + pend);
-    }
+    if (CG && tid == 0) trace_put(epi.trace, TR_SPMV_CTA_DONE, its_now);
   }
   if (CG) {
-    if (grid_sum<1>(dot, partials, ticket)) cg_spmv_epilogue(st, dot, sums, mode, pd, epi);
+    if (grid_sum<1>(dot, partials, ticket)) cg_spmv_epilogue(st, dot, sums, mode, pd, epi, its_now);
   }
 }
 
@@ -273,28 +333,36 @@ static int spmv_smem_bytes(ohp_mesh m) { return (int)sizeof(double) * (kSpmvTile
 static int spmv_configure(ohp_mesh m) {
   const int bytes = spmv_smem_bytes(m);
   if (bytes > 200 * 1024) OHP_FAIL(OHP_ERR_SUP, "SpMV: longest row %d exceeds the shared-memory tile", m->max_row);
-  static int configured_bytes = 0;
-  if (bytes > configured_bytes) {
-    OHP_CUDA(cudaFuncSetAttribute(k_spmv_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    OHP_CUDA(cudaFuncSetAttribute(k_spmv_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    configured_bytes = bytes;
-  }
+  OHP_CUDA(cudaFuncSetAttribute(k_spmv_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  OHP_CUDA(cudaFuncSetAttribute(k_spmv_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   return 0;
+}
+
+/* how many leading tiles of every CTA stay L2-resident (evict_last): OHP_L2PIN_MB megabytes of matrix stream in
+ * total (default kL2PinDefaultMB; 0 switches the cache hints off) */
+constexpr double kL2PinDefaultMB = 0.0;
+static int spmv_pin_tiles(ohp_mesh m, int grid, int idx_bytes) {
+  static const char *env = getenv("OHP_L2PIN_MB");
+  const double mb = env ? atof(env) : kL2PinDefaultMB;
+  if (!(mb > 0.0) || grid <= 0) return 0;
+  const double tile_bytes = (double)kSpmvTile * (8 + idx_bytes);
+  const int64_t total = (int64_t)(mb * 1e6 / tile_bytes);
+  const int per_cta = (int)std::min<int64_t>(total / grid, (int64_t)(m->n_tiles + grid - 1) / grid);
+  return std::max(per_cta, 1);
 }
 
 template <int S, int NC, class IDX, bool SPLIT, int MINB = 1>
 static int spmv_tma_launch_ts(ohp_mat A, const IDX *cols, const double *x, double *y, ohp_cg_state *st, double *sums, int mode,
-                              const double *x_alt, const ohp_p2p_dev &pd, const ohp_cgcg_epi &epi) {
+                              const double *x_alt, const ohp_p2p_dev &pd, const ohp_cgcg_epi &epi_in) {
   ohp_mesh m = A->mesh;
   ohp_context ctx = m->ctx;
   constexpr int smem = tma_smem_bytes(S, (int)sizeof(IDX));
-  static bool configured = false;
-  if (!configured) {
-    OHP_CUDA(cudaFuncSetAttribute(k_spmv_tma<true, S, NC, IDX, SPLIT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    OHP_CUDA(cudaFuncSetAttribute(k_spmv_tma<false, S, NC, IDX, SPLIT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  /* per device, not per process: the attribute belongs to the context of the current device */
+  OHP_CUDA(cudaFuncSetAttribute(k_spmv_tma<true, S, NC, IDX, SPLIT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  OHP_CUDA(cudaFuncSetAttribute(k_spmv_tma<false, S, NC, IDX, SPLIT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = std::max(1, std::min(m->n_tiles, ctx->num_sms * MINB));
+  ohp_cgcg_epi epi = epi_in;
+  epi.pin_tiles = spmv_pin_tiles(m, grid, (int)sizeof(IDX));
   if (st) {
     static const char *nopdl = getenv("OHP_NOPDL");
     OHP_CUDA(ohp_launch(k_spmv_tma<true, S, NC, IDX, SPLIT, MINB>, dim3(grid), dim3(NC + 32), (size_t)smem, ctx->stream, mode != OHP_MODE_NCCL && !nopdl,
@@ -390,7 +458,7 @@ extern "C" int ohp_vec_create(ohp_mesh m, ohp_vec *out) {
   ohp_vec v = new ohp_vec_s();
   v->mesh = m; v->n = m->n_owned;
   const size_t len = (size_t)std::max(1, m->n_owned + m->n_ghost);
-  OHP_CUDA(cudaMalloc(&v->d, sizeof(double) * len));
+  OHP_CUDA(OHP_MALLOC(m->ctx, &v->d, sizeof(double) * len));
   OHP_CUDA(cudaMemsetAsync(v->d, 0, sizeof(double) * len, m->ctx->stream));
   *out = v;
   return 0;
@@ -400,7 +468,7 @@ extern "C" int ohp_vec_destroy(ohp_vec v) {
   if (!v) return 0;
   cudaSetDevice(v->mesh->ctx->device);
   cudaStreamSynchronize(v->mesh->ctx->stream);
-  cudaFree(v->d);
+  OHP_FREE(v->mesh->ctx, v->d);
   delete v;
   return 0;
 }
@@ -482,7 +550,7 @@ extern "C" int ohp_mat_create(ohp_mesh m, ohp_mat *out) {
   OHP_CUDA(cudaSetDevice(m->ctx->device));
   ohp_mat A = new ohp_mat_s();
   A->mesh = m; A->r = A->z = A->p = A->p1 = A->w = A->dinv = A->hist = A->s = A->r1 = A->z1 = A->s1 = nullptr; A->hist_cap = 0;
-  OHP_CUDA(cudaMalloc(&A->vals, sizeof(double) * ohp_padded_nnz(m->nnz)));
+  OHP_CUDA(OHP_MALLOC(m->ctx, &A->vals, sizeof(double) * ohp_padded_nnz(m->nnz)));
   OHP_CUDA(cudaMemsetAsync(A->vals, 0, sizeof(double) * ohp_padded_nnz(m->nnz), m->ctx->stream));
   *out = A;
   return 0;
@@ -491,7 +559,7 @@ extern "C" int ohp_mat_destroy(ohp_mat A) {
   if (!A) return 0;
   cudaSetDevice(A->mesh->ctx->device);
   cudaStreamSynchronize(A->mesh->ctx->stream);
-  cudaFree(A->vals); cudaFree(A->r); cudaFree(A->z); cudaFree(A->p); cudaFree(A->p1); cudaFree(A->s); cudaFree(A->r1); cudaFree(A->z1); cudaFree(A->s1); cudaFree(A->w); cudaFree(A->dinv); cudaFree(A->hist);
+  OHP_FREE(A->mesh->ctx, A->vals); OHP_FREE(A->mesh->ctx, A->r); OHP_FREE(A->mesh->ctx, A->z); OHP_FREE(A->mesh->ctx, A->p); OHP_FREE(A->mesh->ctx, A->p1); OHP_FREE(A->mesh->ctx, A->s); OHP_FREE(A->mesh->ctx, A->r1); OHP_FREE(A->mesh->ctx, A->z1); OHP_FREE(A->mesh->ctx, A->s1); OHP_FREE(A->mesh->ctx, A->w); OHP_FREE(A->mesh->ctx, A->dinv); OHP_FREE(A->mesh->ctx, A->hist);
   delete A;
   return 0;
 }
@@ -584,7 +652,7 @@ k_cg_pupdate(double *__restrict__ p0, double *__restrict__ p1, const double *__r
       if (s_last && threadIdx.x < pd.n_nbr) { /* every push of this rank has landed: publish, then wait for the neighbours */
         const int q = pd.nbr[threadIdx.x];
         st_release_sys(pd.hflags[q] + pd.rank, s_seq);
-        if (wait_here) p2p_wait(pd.hflags[pd.rank] + q, s_seq, pd.seq + 2);
+        if (wait_here) p2p_wait(pd.hflags[pd.rank] + q, s_seq, pd.seq + 2, pd.timeout_ns);
       }
       return;
     }
@@ -654,10 +722,11 @@ __global__ void __launch_bounds__(256)
 k_cgcg_vec(double *R0, double *R1, double *U0, double *U1, double *S0, double *S1, double *__restrict__ p,
            const double *__restrict__ w, double *__restrict__ x, const double *__restrict__ b,
            const double *__restrict__ dinv, int n, const ohp_cg_state *st, double *vpart, const ohp_p2p_dev pd,
-           int n_halo_blocks, unsigned *halo_ticket, int wait_here) {
+           int n_halo_blocks, unsigned *halo_ticket, int wait_here, const ohp_trace trace) {
   pdl_wait();
   pdl_launch();
   if (st->done) return;
+  if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) trace_put(trace, TR_VEC_BEGIN, st->its);
   const bool init = (st->x_pending == 0);
   const int k = init ? 1 : st->its; /* init writes the index-0 buffers, like an iteration of odd parity */
   const double alpha = st->alpha, beta = st->beta;
@@ -693,8 +762,9 @@ k_cgcg_vec(double *R0, double *R1, double *U0, double *U1, double *S0, double *S
       if (s_last && threadIdx.x < pd.n_nbr) {
         const int q = pd.nbr[threadIdx.x];
         st_release_sys(pd.hflags[q] + pd.rank, s_seq);
-        if (wait_here) p2p_wait(pd.hflags[pd.rank] + q, s_seq, pd.seq + 2);
+        if (wait_here) p2p_wait(pd.hflags[pd.rank] + q, s_seq, pd.seq + 2, pd.timeout_ns);
       }
+      if (s_last && threadIdx.x == 0) trace_put(trace, TR_VEC_HALO_PUSHED, st->its);
       return;
     }
     blk -= n_halo_blocks; nb -= n_halo_blocks;
@@ -725,7 +795,10 @@ k_cgcg_vec(double *R0, double *R1, double *U0, double *U1, double *S0, double *S
   }
   __shared__ double s_red2[2 * 32];
   block_sum<2>(sums, s_red2);
-  if (threadIdx.x == 0) { vpart[2 * blk] = sums[0]; vpart[2 * blk + 1] = sums[1]; }
+  if (threadIdx.x == 0) {
+    vpart[2 * blk] = sums[0]; vpart[2 * blk + 1] = sums[1];
+    if (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1 || blockIdx.x == gridDim.x / 2) trace_put(trace, TR_VEC_END, st->its);
+  }
 }
 
 __global__ void k_extract_dinv(const int32_t *rowptr, const int32_t *colidx, const double *vals, int n, double *dinv) {
@@ -749,6 +822,60 @@ extern "C" int ohp_ksp_default_options(ohp_ksp_options *o) {
   return 0;
 }
 
+namespace {
+/* CUDA events that are destroyed on every exit path */
+struct EventBag {
+  std::vector<cudaEvent_t> ev;
+  ~EventBag() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+  cudaError_t record(cudaStream_t st, cudaEvent_t *out = nullptr) {
+    cudaEvent_t e;
+    cudaError_t rc = cudaEventCreate(&e);
+    if (rc != cudaSuccess) return rc;
+    ev.push_back(e);
+    if (out) *out = e;
+    return cudaEventRecord(e, st);
+  }
+};
+}  // namespace
+
+/* OHP_TRACE_CG=<path>: record a device-side timeline of iterations [OHP_TRACE_IT0 (default 200), +OHP_TRACE_N
+ * (default 40)) of every solve and write it to <path>.rank<r>.csv (columns: event, iteration, block, ns) */
+ohp_trace ohp_cg_trace_open(ohp_context ctx) {
+  static const char *path = getenv("OHP_TRACE_CG");
+  ohp_trace none = {};
+  if (!path) return none;
+  if (!ctx->trace.buf) {
+    const unsigned cap = 1u << 18;
+    if (OHP_MALLOC(ctx, &ctx->trace.buf, sizeof(ohp_trace_rec) * cap) != cudaSuccess) return none;
+    if (OHP_MALLOC(ctx, &ctx->trace.count, sizeof(unsigned)) != cudaSuccess) { OHP_FREE(ctx, ctx->trace.buf); ctx->trace.buf = nullptr; return none; }
+    ctx->trace.cap = cap;
+    const char *i0 = getenv("OHP_TRACE_IT0"), *n = getenv("OHP_TRACE_N");
+    ctx->trace.it0 = i0 ? atoi(i0) : 200;
+    ctx->trace.it1 = ctx->trace.it0 + (n ? atoi(n) : 40);
+  }
+  cudaMemsetAsync(ctx->trace.count, 0, sizeof(unsigned), ctx->stream);
+  return ctx->trace;
+}
+void ohp_cg_trace_dump(ohp_context ctx, const char *algo) {
+  static const char *path = getenv("OHP_TRACE_CG");
+  if (!path || !ctx->trace.buf) return;
+  unsigned n = 0;
+  cudaMemcpyAsync(&n, ctx->trace.count, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  n = std::min(n, ctx->trace.cap);
+  std::vector<ohp_trace_rec> rec(n);
+  cudaMemcpy(rec.data(), ctx->trace.buf, sizeof(ohp_trace_rec) * n, cudaMemcpyDeviceToHost);
+  std::sort(rec.begin(), rec.end(), [](const ohp_trace_rec &a, const ohp_trace_rec &b) { return a.t < b.t; });
+  char name[1200];
+  snprintf(name, sizeof(name), "%s.rank%d.csv", path, ctx->rank);
+  FILE *f = fopen(name, "w");
+  if (!f) return;
+  fprintf(f, "# algo=%s ranks=%d events: 1 vec_begin 2 vec_halo_pushed 3 vec_end 4 spmv_begin 5 spmv_halo_ready 6 spmv_cta_done 7 spmv_last_block "
+             "8 allreduce_posted 9 allreduce_done 10 spmv_end 11 upd_begin 12 upd_end\nevent,iteration,block,ns\n", algo, ctx->nranks);
+  for (const ohp_trace_rec &r : rec) fprintf(f, "%d,%d,%d,%llu\n", r.ev, r.it, r.blk, r.t);
+  fclose(f);
+}
+
 static int cgcg_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o, ohp_ksp_result *res, bool p2p) {
   ohp_mesh m = A->mesh;
   ohp_context ctx = m->ctx;
@@ -757,7 +884,7 @@ static int cgcg_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o,
   const size_t len = (size_t)std::max(1, n + m->n_ghost);
   const bool jac = (o->pc == OHP_PC_JACOBI);
   auto need = [&](double **ptr) -> int {
-    if (!*ptr) { OHP_CUDA(cudaMalloc(ptr, sizeof(double) * len)); OHP_CUDA(cudaMemsetAsync(*ptr, 0, sizeof(double) * len, st)); }
+    if (!*ptr) { OHP_CUDA(OHP_MALLOC(ctx, ptr, sizeof(double) * len)); OHP_CUDA(cudaMemsetAsync(*ptr, 0, sizeof(double) * len, st)); }
     return 0;
   };
   OHP_TRY(need(&A->p)); OHP_TRY(need(&A->w)); OHP_TRY(need(&A->s)); OHP_TRY(need(&A->s1));
@@ -776,8 +903,8 @@ static int cgcg_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o,
   int hist_cap = 0;
   if (o->history && o->history_cap > 0) {
     if (A->hist_cap < o->history_cap) {
-      cudaFree(A->hist);
-      OHP_CUDA(cudaMalloc(&A->hist, sizeof(double) * o->history_cap));
+      OHP_FREE(ctx, A->hist);
+      OHP_CUDA(OHP_MALLOC(ctx, &A->hist, sizeof(double) * o->history_cap));
       A->hist_cap = o->history_cap;
     }
     hist = A->hist; hist_cap = o->history_cap;
@@ -793,7 +920,10 @@ static int cgcg_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o,
   const int nhalo = p2p ? std::max(1, std::min(16, (pd.soff[pd.n_nbr] + 255) / 256)) : 0;
   double *vpart = ctx->d_partials + kMaxPartials; /* second half of the scratch: the SpMV uses the first */
   ohp_cgcg_epi epi;
+  memset(&epi, 0, sizeof(epi));
   epi.vpart = vpart; epi.nvpart = vgrid; epi.jacobi = jac ? 1 : 0; epi.hist = hist; epi.hist_cap = hist_cap;
+  epi.trace = ohp_cg_trace_open(ctx);
+  if (p2p) OHP_TRY(ohp_p2p_entry_barrier(m));
   static const char *nooverlap = getenv("OHP_NOOVERLAP");
   const bool overlap = p2p && spmv_use_tma(m) && m->ghost_cta && !nooverlap && !getenv("OHP_SPMV");
   const int wait_in_vec = overlap ? 0 : 1;
@@ -801,26 +931,26 @@ static int cgcg_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o,
   static const char *nopdl = getenv("OHP_NOPDL");
   const bool pdl = !nopdl;
   const int check_every = o->check_every > 0 ? o->check_every : 50;
+  EventBag bag, profbag;
   cudaEvent_t ev0, ev1;
-  OHP_CUDA(cudaEventCreate(&ev0)); OHP_CUDA(cudaEventCreate(&ev1));
-  OHP_CUDA(cudaEventRecord(ev0, st));
+  OHP_CUDA(bag.record(st, &ev0));
   int launched = 0;
-  std::vector<cudaEvent_t> prof; /* optional per-launch timing of the SpMV, skipping the first (cold) chunk */
+  std::vector<cudaEvent_t> &prof = profbag.ev; /* optional per-launch timing of the SpMV, skipping the first (cold) chunk */
   const int nprof = std::max(0, o->profile);
   for (;;) {
     for (int it = 0; it < check_every; ++it) {
       if (p2p) {
-        if (jac) OHP_CUDA(ohp_launch(k_cgcg_vec<OHP_MODE_P2P, true>, dim3(vgrid + nhalo), dim3(256), 0, st, pdl, R0, R1, U0, U1, A->s, A->s1, A->p, (const double *)A->w, x->d, (const double *)b->d, (const double *)A->dinv, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, nhalo, ctx->d_ticket + 2, wait_in_vec));
-        else OHP_CUDA(ohp_launch(k_cgcg_vec<OHP_MODE_P2P, false>, dim3(vgrid + nhalo), dim3(256), 0, st, pdl, R0, R1, U0, U1, A->s, A->s1, A->p, (const double *)A->w, x->d, (const double *)b->d, (const double *)A->dinv, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, nhalo, ctx->d_ticket + 2, wait_in_vec));
+        if (jac) OHP_CUDA(ohp_launch(k_cgcg_vec<OHP_MODE_P2P, true>, dim3(vgrid + nhalo), dim3(256), 0, st, pdl, R0, R1, U0, U1, A->s, A->s1, A->p, (const double *)A->w, x->d, (const double *)b->d, (const double *)A->dinv, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, nhalo, ctx->d_ticket + 2, wait_in_vec, epi.trace));
+        else OHP_CUDA(ohp_launch(k_cgcg_vec<OHP_MODE_P2P, false>, dim3(vgrid + nhalo), dim3(256), 0, st, pdl, R0, R1, U0, U1, A->s, A->s1, A->p, (const double *)A->w, x->d, (const double *)b->d, (const double *)A->dinv, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, nhalo, ctx->d_ticket + 2, wait_in_vec, epi.trace));
       } else {
-        if (jac) OHP_CUDA(ohp_launch(k_cgcg_vec<OHP_MODE_SERIAL, true>, dim3(vgrid), dim3(256), 0, st, pdl, R0, R1, U0, U1, A->s, A->s1, A->p, (const double *)A->w, x->d, (const double *)b->d, (const double *)A->dinv, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, 0, (unsigned *)nullptr, 1));
-        else OHP_CUDA(ohp_launch(k_cgcg_vec<OHP_MODE_SERIAL, false>, dim3(vgrid), dim3(256), 0, st, pdl, R0, R1, U0, U1, A->s, A->s1, A->p, (const double *)A->w, x->d, (const double *)b->d, (const double *)A->dinv, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, 0, (unsigned *)nullptr, 1));
+        if (jac) OHP_CUDA(ohp_launch(k_cgcg_vec<OHP_MODE_SERIAL, true>, dim3(vgrid), dim3(256), 0, st, pdl, R0, R1, U0, U1, A->s, A->s1, A->p, (const double *)A->w, x->d, (const double *)b->d, (const double *)A->dinv, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, 0, (unsigned *)nullptr, 1, epi.trace));
+        else OHP_CUDA(ohp_launch(k_cgcg_vec<OHP_MODE_SERIAL, false>, dim3(vgrid), dim3(256), 0, st, pdl, R0, R1, U0, U1, A->s, A->s1, A->p, (const double *)A->w, x->d, (const double *)b->d, (const double *)A->dinv, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, 0, (unsigned *)nullptr, 1, epi.trace));
       }
       ctx->launches++;
       const bool timed = (int)prof.size() < 2 * nprof && (launched > 0 || o->max_it <= check_every);
-      if (timed) { cudaEvent_t e; OHP_CUDA(cudaEventCreate(&e)); OHP_CUDA(cudaEventRecord(e, st)); prof.push_back(e); }
+      if (timed) OHP_CUDA(profbag.record(st));
       OHP_TRY(spmv_enqueue(A, U0, A->w, ctx->d_cg, ctx->d_scalars, mode, U1, pd, epi));
-      if (timed) { cudaEvent_t e; OHP_CUDA(cudaEventCreate(&e)); OHP_CUDA(cudaEventRecord(e, st)); prof.push_back(e); }
+      if (timed) OHP_CUDA(profbag.record(st));
     }
     launched += check_every;
     OHP_CUDA(cudaMemcpyAsync(ctx->h_cg, ctx->d_cg, sizeof(ohp_cg_state), cudaMemcpyDeviceToHost, st));
@@ -828,13 +958,13 @@ static int cgcg_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o,
     if (ctx->h_cg->done) break;
     if (launched > o->max_it + 2 * check_every) OHP_FAIL(OHP_ERR_LIB, "ohp_ksp_cg (single-reduction): iteration control did not terminate");
   }
-  OHP_CUDA(cudaEventRecord(ev1, st));
+  OHP_CUDA(bag.record(st, &ev1));
   OHP_CUDA(cudaEventSynchronize(ev1));
   res->total_ms = 0.f;
   cudaEventElapsedTime(&res->total_ms, ev0, ev1);
-  cudaEventDestroy(ev0); cudaEventDestroy(ev1);
   res->its = ctx->h_cg->its; res->reason = ctx->h_cg->reason; res->rnorm = ctx->h_cg->dp; res->rnorm0 = ctx->h_cg->rnorm0;
   res->spmv_ms = 0.f; res->spmv_samples = 0;
+  ohp_cg_trace_dump(ctx, "cgcg");
   {
     /* SpMV launch number j closes iteration j - 1 (launch 0 is the initial pass): count the ones that did real work */
     double acc = 0.0;
@@ -845,15 +975,9 @@ static int cgcg_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o,
       cudaEventElapsedTime(&ms, prof[i], prof[i + 1]);
       if (first_timed + (int)(i / 2) <= res->its) { acc += ms; used++; }
     }
-    for (cudaEvent_t e : prof) cudaEventDestroy(e);
     if (used) { res->spmv_ms = (float)(acc / used); res->spmv_samples = used; }
   }
-  if (p2p) {
-    unsigned long long err = 0;
-    OHP_CUDA(cudaMemcpyAsync(&err, pd.seq + 2, sizeof(err), cudaMemcpyDeviceToHost, st));
-    OHP_CUDA(cudaStreamSynchronize(st));
-    if (err) OHP_FAIL(OHP_ERR_LIB, "ohp_ksp_cg (single-reduction): a peer-to-peer wait timed out");
-  }
+  if (p2p) OHP_TRY(ohp_p2p_check(m, "ohp_ksp_cg (single-reduction)"));
   if (hist) {
     const int ncopy = std::min(hist_cap, res->its + 1);
     OHP_CUDA(cudaMemcpyAsync(o->history, hist, sizeof(double) * ncopy, cudaMemcpyDeviceToHost, st));
@@ -896,10 +1020,10 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
   }
   const size_t len = (size_t)std::max(1, n + m->n_ghost);
   if (!A->r) {
-    OHP_CUDA(cudaMalloc(&A->r, sizeof(double) * len));
-    OHP_CUDA(cudaMalloc(&A->p, sizeof(double) * len));
-    OHP_CUDA(cudaMalloc(&A->p1, sizeof(double) * len));
-    OHP_CUDA(cudaMalloc(&A->w, sizeof(double) * len));
+    OHP_CUDA(OHP_MALLOC(ctx, &A->r, sizeof(double) * len));
+    OHP_CUDA(OHP_MALLOC(ctx, &A->p, sizeof(double) * len));
+    OHP_CUDA(OHP_MALLOC(ctx, &A->p1, sizeof(double) * len));
+    OHP_CUDA(OHP_MALLOC(ctx, &A->w, sizeof(double) * len));
     OHP_CUDA(cudaMemsetAsync(A->p, 0, sizeof(double) * len, st));
     OHP_CUDA(cudaMemsetAsync(A->p1, 0, sizeof(double) * len, st));
   }
@@ -912,7 +1036,7 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
   double *P0 = p2p ? pd.p[0][ctx->rank] : A->p, *P1 = p2p ? pd.p[1][ctx->rank] : A->p1;
   const bool jac = (o->pc == OHP_PC_JACOBI);
   if (jac) {
-    if (!A->z) { OHP_CUDA(cudaMalloc(&A->z, sizeof(double) * len)); OHP_CUDA(cudaMalloc(&A->dinv, sizeof(double) * len)); }
+    if (!A->z) { OHP_CUDA(OHP_MALLOC(ctx, &A->z, sizeof(double) * len)); OHP_CUDA(OHP_MALLOC(ctx, &A->dinv, sizeof(double) * len)); }
     k_extract_dinv<<<nblk(n, 256), 256, 0, st>>>(m->rowptr, m->colidx, A->vals, n, A->dinv);
     OHP_CHECK_LAUNCH(ctx);
   }
@@ -921,8 +1045,8 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
   int hist_cap = 0;
   if (o->history && o->history_cap > 0) {
     if (A->hist_cap < o->history_cap) {
-      cudaFree(A->hist);
-      OHP_CUDA(cudaMalloc(&A->hist, sizeof(double) * o->history_cap));
+      OHP_FREE(ctx, A->hist);
+      OHP_CUDA(OHP_MALLOC(ctx, &A->hist, sizeof(double) * o->history_cap));
       A->hist_cap = o->history_cap;
     }
     hist = A->hist; hist_cap = o->history_cap;
@@ -941,8 +1065,11 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
   static const char *nooverlap = getenv("OHP_NOOVERLAP");
   const bool overlap = p2p && spmv_use_tma(m) && m->ghost_cta && !nooverlap && !getenv("OHP_SPMV");
   const int wait_in_vec = overlap ? 0 : 1;
-  ohp_cgcg_epi cepi = {};
+  ohp_cgcg_epi cepi;
+  memset(&cepi, 0, sizeof(cepi));
   cepi.ghost_cta = overlap ? m->ghost_cta : nullptr;
+  cepi.trace = ohp_cg_trace_open(ctx);
+  if (p2p) OHP_TRY(ohp_p2p_entry_barrier(m));
   const int nhalo = p2p ? std::max(1, std::min(16, (pd.soff[pd.n_nbr] + 255) / 256)) : 0;
   const int vgrid = vec_grid(ctx, n);
   double *sums = ctx->d_scalars;
@@ -957,12 +1084,11 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
   const int check_every = o->check_every > 0 ? o->check_every : 50;
   int launched = 0;
   /* optional per-launch timing of the dominant kernel, skipping the first (cold) chunk */
-  std::vector<cudaEvent_t> prof;
+  EventBag bag, profbag;
+  std::vector<cudaEvent_t> &prof = profbag.ev;
   const int nprof = std::max(0, o->profile);
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
-  OHP_CUDA(cudaEventCreate(&ev_t0));
-  OHP_CUDA(cudaEventCreate(&ev_t1));
-  OHP_CUDA(cudaEventRecord(ev_t0, st));
+  OHP_CUDA(bag.record(st, &ev_t0));
   for (;;) {
     OHP_CUDA(cudaMemcpyAsync(ctx->h_cg, ctx->d_cg, sizeof(ohp_cg_state), cudaMemcpyDeviceToHost, st));
     OHP_CUDA(cudaStreamSynchronize(st));
@@ -978,9 +1104,9 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
         OHP_TRY(ohp_halo_exchange(m, ((launched + it) & 1) ? P1 : P0));
       }
       const bool timed = (int)prof.size() < 2 * nprof && (launched > 0 || o->max_it <= check_every);
-      if (timed) { cudaEvent_t e; OHP_CUDA(cudaEventCreate(&e)); OHP_CUDA(cudaEventRecord(e, st)); prof.push_back(e); }
+      if (timed) OHP_CUDA(profbag.record(st));
       OHP_TRY(spmv_enqueue(A, P0, A->w, ctx->d_cg, sums, mode, P1, pd, cepi));
-      if (timed) { cudaEvent_t e; OHP_CUDA(cudaEventCreate(&e)); OHP_CUDA(cudaEventRecord(e, st)); prof.push_back(e); }
+      if (timed) OHP_CUDA(profbag.record(st));
       if (nccl) {
         OHP_TRY(ohp_allreduce_sum(ctx, sums, 1));
         k_cg_fin<<<1, 1, 0, st>>>(ctx->d_cg, sums, 1, hist, hist_cap); OHP_CHECK_LAUNCH(ctx);
@@ -997,18 +1123,13 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
   }
   k_cg_final_x<<<vgrid, 256, 0, st>>>(x->d, P0, P1, n, ctx->d_cg); OHP_CHECK_LAUNCH(ctx);
   res->its = ctx->h_cg->its; res->reason = ctx->h_cg->reason; res->rnorm = ctx->h_cg->dp; res->rnorm0 = ctx->h_cg->rnorm0;
-  if (p2p) {
-    unsigned long long err = 0;
-    OHP_CUDA(cudaMemcpyAsync(&err, pd.seq + 2, sizeof(err), cudaMemcpyDeviceToHost, st));
-    OHP_CUDA(cudaStreamSynchronize(st));
-    if (err) OHP_FAIL(OHP_ERR_LIB, "ohp_ksp_cg: a peer-to-peer wait timed out (a neighbouring rank stopped responding)");
-  }
-  OHP_CUDA(cudaEventRecord(ev_t1, st));
+  if (p2p) OHP_TRY(ohp_p2p_check(m, "ohp_ksp_cg"));
+  OHP_CUDA(bag.record(st, &ev_t1));
   OHP_CUDA(cudaEventSynchronize(ev_t1));
   res->total_ms = 0.f;
   cudaEventElapsedTime(&res->total_ms, ev_t0, ev_t1);
-  cudaEventDestroy(ev_t0); cudaEventDestroy(ev_t1);
   res->spmv_ms = 0.f; res->spmv_samples = 0;
+  ohp_cg_trace_dump(ctx, "classic");
   {
     /* only launches that ran before convergence did real work: iteration k is sample k - first_timed */
     double acc = 0.0;
@@ -1019,7 +1140,6 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
       cudaEventElapsedTime(&ms, prof[i], prof[i + 1]);
       if (first_timed_it + (int)(i / 2) < res->its) { acc += ms; used++; }
     }
-    for (cudaEvent_t e : prof) cudaEventDestroy(e);
     if (used) { res->spmv_ms = (float)(acc / used); res->spmv_samples = used; }
   }
   if (hist) {

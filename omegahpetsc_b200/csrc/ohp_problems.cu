@@ -76,76 +76,78 @@ struct ProblemNonlinear : QuadraticBC {
   }
 };
 
-struct ProblemEntry {
-  ohp_assembly_launcher residual, jacobian, project;
+/* COEFF_CIRCLE / COEFF_CROSS: f0_circle_u (ex12.cpp:155-166), f0_cross_u (:168-177) with f1_u and g3_uu;
+ * Dirichlet and "exact" data circle_u_2d (:127-136), cross_u_2d (:138-145), selected at :1197-1213 */
+struct ProblemCircle {
+  static constexpr bool kJacobianUsesU = false;
+  OHP_HD static void f0(OHP_PF_ARGS, double f0[]) {
+    const double alpha = 500., radius2 = 0.15 * 0.15;
+    const double r2 = (x[0] - 0.5) * (x[0] - 0.5) + (x[1] - 0.5) * (x[1] - 0.5);
+    const double xi = alpha * (radius2 - r2);
+    f0[0] = (-4.0 * alpha - 8.0 * alpha * alpha * r2 * tanh(xi)) * (1.0 / cosh(xi)) * (1.0 / cosh(xi));
+  }
+  OHP_HD static void f1(OHP_PF_ARGS, double f1[]) { for (int d = 0; d < dim; ++d) f1[d] = u_x[d]; }
+  OHP_HD static void g3(OHP_PJ_ARGS, double g3[]) { for (int d = 0; d < dim; ++d) g3[d * dim + d] = 1.0; }
+  OHP_HD static int bc(int dim, double time, const double x[], int Nc, double *u, void *ctx) {
+    if (dim == 3) return QuadraticBC::bc(dim, time, x, Nc, u, ctx); /* ex12.cpp:1229-1231: 3-D keeps the quadratic */
+    const double alpha = 500., radius2 = 0.15 * 0.15;
+    const double r2 = (x[0] - 0.5) * (x[0] - 0.5) + (x[1] - 0.5) * (x[1] - 0.5);
+    *u = tanh(alpha * (radius2 - r2)) + 1.0;
+    return 0;
+  }
+  OHP_HD static int exact(int dim, double time, const double x[], int Nc, double *u, void *ctx) { return bc(dim, time, x, Nc, u, ctx); }
 };
+struct ProblemCross {
+  static constexpr bool kJacobianUsesU = false;
+  OHP_HD static double cross(const double x[]) {
+    const double alpha = 50 * 4;
+    const double xy = (x[0] - 0.5) * (x[1] - 0.5);
+    return sin(alpha * xy) * (alpha * fabs(xy) < 2 * 3.14159265358979323846 ? 1 : 0.01);
+  }
+  OHP_HD static void f0(OHP_PF_ARGS, double f0[]) { f0[0] = cross(x); }
+  OHP_HD static void f1(OHP_PF_ARGS, double f1[]) { for (int d = 0; d < dim; ++d) f1[d] = u_x[d]; }
+  OHP_HD static void g3(OHP_PJ_ARGS, double g3[]) { for (int d = 0; d < dim; ++d) g3[d * dim + d] = 1.0; }
+  OHP_HD static int bc(int dim, double time, const double x[], int Nc, double *u, void *ctx) {
+    if (dim == 3) return QuadraticBC::bc(dim, time, x, Nc, u, ctx);
+    *u = cross(x);
+    return 0;
+  }
+  OHP_HD static int exact(int dim, double time, const double x[], int Nc, double *u, void *ctx) { return bc(dim, time, x, Nc, u, ctx); }
+};
+
+struct ProblemEntry {
+  ohp_assembly_launcher residual, jacobian, project, l2diff;
+};
+template <class P> ProblemEntry builtin() {
+  return {ohp::launch_residual_any<P>, ohp::launch_jacobian_any<P>, ohp::launch_project_exact_any<P>, ohp::launch_l2_diff_any<P>};
+}
 
 std::mutex g_reg_mutex;
 std::vector<ProblemEntry> &registry() {
-  static std::vector<ProblemEntry> r = {
-      {ohp::launch_residual_any<ProblemCoeffNone>, ohp::launch_jacobian_any<ProblemCoeffNone>, ohp::launch_project_exact_any<ProblemCoeffNone>},
-      {ohp::launch_residual_any<ProblemAnalytic>, ohp::launch_jacobian_any<ProblemAnalytic>, ohp::launch_project_exact_any<ProblemAnalytic>},
-      {ohp::launch_residual_any<ProblemNonlinear>, ohp::launch_jacobian_any<ProblemNonlinear>, ohp::launch_project_exact_any<ProblemNonlinear>},
-  };
+  static std::vector<ProblemEntry> r = {builtin<ProblemCoeffNone>(), builtin<ProblemAnalytic>(), builtin<ProblemNonlinear>(),
+                                        builtin<ProblemCircle>(), builtin<ProblemCross>()};
   return r;
-}
-
-/* DMComputeL2Diff [PETSc-internal, reached from ex12.cpp:1611,1637]: sqrt(sum_c sum_q w_q detJ (u_h - u_exact)^2),
- * evaluated with the same quadrature; deterministic two-stage sum */
-template <int DIM>
-__global__ void __launch_bounds__(256) k_l2_diff(const ohp_assembly_view vw, const uint8_t *owned, double *partials) {
-  constexpr int NC = DIM + 1;
-  double acc = 0.0;
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < vw.n_cells; c += gridDim.x * blockDim.x) {
-    /* partitioned meshes overlap by one layer of cells: a cell is integrated by the rank that owns its first corner */
-    if (!owned[vw.cells_dev[(size_t)c * NC]]) continue;
-    int cv[NC];
-    double X[NC][DIM], ue[NC];
-    ohp::load_cell<DIM, QuadraticBC, true>(vw, c, cv, X, ue);
-    ohp::CellGeom<DIM> g;
-    ohp::cell_geometry<DIM>(X, g);
-    for (int q = 0; q < ohp::Quadrature<DIM>::NQ; ++q) {
-      double phi[NC], xq[DIM], uq = 0.0, ex = 0.0;
-      ohp::p1_basis<DIM>(q, phi);
-      for (int d = 0; d < DIM; ++d) {
-        double s = g.v0[d];
-        for (int f = 0; f < DIM; ++f) s += g.J[d * DIM + f] * (ohp::Quadrature<DIM>::xi(q, f) + 1.0);
-        xq[d] = s;
-      }
-      for (int j = 0; j < NC; ++j) uq += phi[j] * ue[j];
-      QuadraticBC::exact(DIM, 0.0, xq, 1, &ex, nullptr);
-      acc += ohp::Quadrature<DIM>::w(q) * fabs(g.detJ) * (uq - ex) * (uq - ex);
-    }
-  }
-  __shared__ double red[8];
-#pragma unroll
-  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    partials[blockIdx.x] = t;
-  }
 }
 
 }  // namespace
 
-int ohp_problem_lookup(int id, ohp_assembly_launcher *res, ohp_assembly_launcher *jac, ohp_assembly_launcher *proj) {
+int ohp_problem_lookup(int id, ohp_assembly_launcher *res, ohp_assembly_launcher *jac, ohp_assembly_launcher *proj,
+                       ohp_assembly_launcher *l2) {
   std::lock_guard<std::mutex> lock(g_reg_mutex);
   auto &r = registry();
   if (id < 0 || id >= (int)r.size()) OHP_FAIL(OHP_ERR_ARG_OUTOFRANGE, "unknown problem id %d", id);
   if (res) *res = r[id].residual;
   if (jac) *jac = r[id].jacobian;
   if (proj) *proj = r[id].project;
+  if (l2) *l2 = r[id].l2diff;
   return 0;
 }
 
 extern "C" int ohp_problem_register(ohp_assembly_launcher residual, ohp_assembly_launcher jacobian,
-                                    ohp_assembly_launcher project_exact, int *problem_id) {
+                                    ohp_assembly_launcher project_exact, ohp_assembly_launcher l2_diff, int *problem_id) {
   if (!residual || !jacobian || !problem_id) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_problem_register: null launcher");
   std::lock_guard<std::mutex> lock(g_reg_mutex);
-  registry().push_back({residual, jacobian, project_exact});
+  registry().push_back({residual, jacobian, project_exact, l2_diff});
   *problem_id = (int)registry().size() - 1;
   return 0;
 }
@@ -160,7 +162,7 @@ extern "C" int ohp_residual(ohp_mesh m, int problem, ohp_vec u, ohp_vec F) {
   NEED(m, "ohp_residual");
   if (u->n != m->n_owned || F->n != m->n_owned) OHP_FAIL(OHP_ERR_ARG_SIZ, "ohp_residual: vector size mismatch");
   ohp_assembly_launcher fn;
-  OHP_TRY(ohp_problem_lookup(problem, &fn, nullptr, nullptr));
+  OHP_TRY(ohp_problem_lookup(problem, &fn, nullptr, nullptr, nullptr));
   if (m->ctx->nranks > 1) OHP_TRY(ohp_halo_exchange(m, u->d)); /* DMGlobalToLocal */
   ohp_assembly_view vw;
   ohp_assembly_view_make(m, u->d, F->d, &vw);
@@ -174,7 +176,7 @@ extern "C" int ohp_jacobian(ohp_mesh m, int problem, ohp_vec u, ohp_mat J) {
   NEED(m, "ohp_jacobian");
   if (u->n != m->n_owned || J->mesh != m) OHP_FAIL(OHP_ERR_ARG_SIZ, "ohp_jacobian: size mismatch");
   ohp_assembly_launcher fn;
-  OHP_TRY(ohp_problem_lookup(problem, nullptr, &fn, nullptr));
+  OHP_TRY(ohp_problem_lookup(problem, nullptr, &fn, nullptr, nullptr));
   if (m->ctx->nranks > 1) OHP_TRY(ohp_halo_exchange(m, u->d));
   ohp_assembly_view vw;
   ohp_assembly_view_make(m, u->d, J->vals, &vw);
@@ -188,7 +190,7 @@ extern "C" int ohp_project(ohp_mesh m, int problem, int which, ohp_vec u) {
   NEED(m, "ohp_project");
   if (which == 0) return ohp_vec_set(u, 0.0); /* zero(), ex12.cpp:76-80 */
   ohp_assembly_launcher fn;
-  OHP_TRY(ohp_problem_lookup(problem, nullptr, nullptr, &fn));
+  OHP_TRY(ohp_problem_lookup(problem, nullptr, nullptr, &fn, nullptr));
   if (!fn) OHP_FAIL(OHP_ERR_SUP, "ohp_project: problem %d has no exact solution registered", problem);
   ohp_assembly_view vw;
   ohp_assembly_view_make(m, nullptr, u->d, &vw);
@@ -198,16 +200,30 @@ extern "C" int ohp_project(ohp_mesh m, int problem, int which, ohp_vec u) {
   return 0;
 }
 
+extern "C" int ohp_project_function(ohp_mesh m, ohp_assembly_launcher fn, ohp_vec u) {
+  NEED(m, "ohp_project_function");
+  if (!fn || !u) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_project_function: null argument");
+  ohp_assembly_view vw;
+  ohp_assembly_view_make(m, nullptr, u->d, &vw);
+  int rc = fn(&vw);
+  m->ctx->launches++;
+  if (rc) OHP_FAIL(rc, "ohp_project_function: kernel launch failed");
+  return 0;
+}
+
 extern "C" int ohp_l2_error(ohp_mesh m, int problem, ohp_vec u, double *err) {
   NEED(m, "ohp_l2_error");
-  (void)problem; /* all built-in problems share the quadratic exact solution (ex12.cpp:1222,1230) */
   ohp_context ctx = m->ctx;
+  ohp_assembly_launcher fn = nullptr;
+  OHP_TRY(ohp_problem_lookup(problem, nullptr, nullptr, nullptr, &fn)); /* the problem's OWN exact solution */
+  if (!fn) OHP_FAIL(OHP_ERR_SUP, "ohp_l2_error: problem %d has no exact solution registered", problem);
   if (ctx->nranks > 1) OHP_TRY(ohp_halo_exchange(m, u->d));
   ohp_assembly_view vw;
-  ohp_assembly_view_make(m, u->d, nullptr, &vw);
+  ohp_assembly_view_make(m, u->d, ctx->d_partials, &vw);
   const int grid = std::min(std::max(1, (m->nC + 255) / 256), 1024);
-  if (m->dim == 2) k_l2_diff<2><<<grid, 256, 0, ctx->stream>>>(vw, m->owned, ctx->d_partials);
-  else k_l2_diff<3><<<grid, 256, 0, ctx->stream>>>(vw, m->owned, ctx->d_partials);
+  vw.n_partials = grid;
+  int lrc = fn(&vw);
+  if (lrc) OHP_FAIL(lrc, "ohp_l2_error: kernel launch failed (%s)", cudaGetErrorString(cudaGetLastError()));
   OHP_CHECK_LAUNCH(ctx);
   std::vector<double> part(grid);
   OHP_CUDA(cudaMemcpyAsync(part.data(), ctx->d_partials, sizeof(double) * grid, cudaMemcpyDeviceToHost, ctx->stream));
@@ -229,6 +245,7 @@ extern "C" int ohp_l2_error(ohp_mesh m, int problem, ohp_vec u, double *err) {
 /* ------------------------------------------------------------------------------------ */
 extern "C" int ohp_snes_default_options(ohp_snes_options *o) {
   o->rtol = 1e-8; o->abstol = 1e-50; o->stol = 1e-8; o->max_it = 50;
+  o->snes_monitor = nullptr; o->ksp_monitor = nullptr; o->monitor_ctx = nullptr;
   return ohp_ksp_default_options(&o->ksp);
 }
 
@@ -273,6 +290,7 @@ extern "C" int ohp_snes_solve(ohp_mesh m, int problem, ohp_mat J, ohp_vec u, con
   OHP_TRY(ohp_vec_create(m, &w));
   OHP_TRY(ohp_vec_create(m, &Fw));
   PhaseTimer tm(ctx->stream);
+  std::vector<double> khist;
   memset(res, 0, sizeof(*res));
   int rc = 0, its = 0, kits = 0, reason = 0;
   double fnorm = 0.0, fnorm0 = 0.0;
@@ -288,6 +306,7 @@ extern "C" int ohp_snes_solve(ohp_mesh m, int problem, ohp_mat J, ohp_vec u, con
   res->n_residual++;
   SN_TRY(ohp_vec_norm2(F, &fnorm));
   fnorm0 = fnorm;
+  if (o->snes_monitor) o->snes_monitor(o->monitor_ctx, 0, fnorm);
   if (fnorm < o->abstol) reason = 2;
   while (!reason && its < o->max_it) {
     tm.begin(1);
@@ -295,9 +314,15 @@ extern "C" int ohp_snes_solve(ohp_mesh m, int problem, ohp_mat J, ohp_vec u, con
     tm.end(1);
     res->n_jacobian++;
     ohp_ksp_result kr;
+    ohp_ksp_options ko = o->ksp;
+    if (o->ksp_monitor && !ko.history) { /* -ksp_monitor: record the norms on the device, copy them back per solve */
+      khist.assign((size_t)std::min<int64_t>((int64_t)ko.max_it + 2, 1 << 24), 0.0);
+      ko.history = khist.data(); ko.history_cap = (int32_t)khist.size();
+    }
     tm.begin(2);
-    SN_TRY(ohp_ksp_cg(J, F, y, &o->ksp, &kr));
+    SN_TRY(ohp_ksp_cg(J, F, y, &ko, &kr));
     tm.end(2);
+    if (o->ksp_monitor) o->ksp_monitor(o->monitor_ctx, its, std::min(kr.its, ko.history_cap - 1), ko.history, kr.reason);
     kits += kr.its;
     res->spmv_ms = kr.spmv_ms; res->spmv_samples = kr.spmv_samples;
     if (kr.reason < 0) { reason = -3; break; }
@@ -327,6 +352,7 @@ extern "C" int ohp_snes_solve(ohp_mesh m, int problem, ohp_mat J, ohp_vec u, con
     SN_TRY(ohp_vec_copy(Fw, F));
     fnorm = gnorm;
     ++its;
+    if (o->snes_monitor) o->snes_monitor(o->monitor_ctx, its, fnorm);
     SN_TRY(ohp_vec_norm2(u, &xnorm));
     if (fnorm < o->abstol) reason = 2;
     else if (fnorm <= o->rtol * fnorm0) reason = 3;

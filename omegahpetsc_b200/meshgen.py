@@ -44,6 +44,36 @@ def box3d(nx, ny, nz, pinned=False):
     return cells, coords
 
 
+def _part1by1(x):
+    x = x.astype(np.uint64) & np.uint64(0xffff)
+    x = (x | (x << np.uint64(8))) & np.uint64(0x00ff00ff)
+    x = (x | (x << np.uint64(4))) & np.uint64(0x0f0f0f0f)
+    x = (x | (x << np.uint64(2))) & np.uint64(0x33333333)
+    x = (x | (x << np.uint64(1))) & np.uint64(0x55555555)
+    return x
+
+
+def morton_reorder(cells, coords, sizes, pinned=False):
+    """Renumber the vertices (and sort the cells) of a 2-D box along a Morton (Z-order) curve.  Stands in for the
+    space-filling-curve reordering of Omega_h::build_box (ex12.cpp:805): the mesh is the same, the numbering
+    is not row-major any more, so |column - row| of the matrix is no longer bounded by the grid width."""
+    nx, ny = sizes
+    i = np.rint(coords[:, 0] * nx).astype(np.int64)
+    j = np.rint(coords[:, 1] * ny).astype(np.int64)
+    key = _part1by1(i) | (_part1by1(j) << np.uint64(1))
+    order = np.argsort(key, kind="stable")              # new vertex k = old vertex order[k]
+    new_of_old = np.empty(order.size, dtype=np.int32)
+    new_of_old[order] = np.arange(order.size, dtype=np.int32)
+    c2 = new_of_old[cells]
+    ckey = c2.min(axis=1)
+    corder = np.argsort(ckey, kind="stable")
+    out_cells = _alloc(cells.shape, np.int32, pinned)
+    out_coords = _alloc(coords.shape, np.float64, pinned)
+    out_cells[:] = c2[corder]
+    out_coords[:] = coords[order]
+    return out_cells, out_coords
+
+
 def _alloc(shape, dtype, pinned):
     if not pinned:
         return np.empty(shape, dtype=dtype)

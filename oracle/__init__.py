@@ -145,6 +145,16 @@ def num_threads(omp=True):
     return lib(omp).orc_num_threads()
 
 
+def use_all_cores():
+    """OpenMP thread count := every core this process may run on, whatever OMP_NUM_THREADS says
+    (torch.distributed.run exports OMP_NUM_THREADS=1).  Returns the count in use."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return lib(True).orc_set_num_threads(int(n))
+
+
 # ---------------------------------------------------------------------------
 # synthetic inputs (SURVEY 8d: C4 box of nx*ny quads split on the same diagonal,
 # vertices row-major; C5 cube of n^3 hexes x 6 Kuhn tets)

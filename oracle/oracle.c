@@ -19,6 +19,7 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * leg may load this library.  The product never links or calls it.
  */
+#define _GNU_SOURCE
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -90,6 +91,33 @@ static void cb_g3_nonlinear(PJ_ARGS, double g3[]) {
     for (int e = 0; e < dim; ++e) g3[d * dim + e] += u_x[d] * u_x[e];
   }
 }
+/* circle / cross forcing terms: ex12.cpp:155-166 (f0_circle_u), :168-177 (f0_cross_u); flux and g3 are f1_u, g3_uu */
+static void cb_f0_circle(PF_ARGS, double f0[]) {
+  const double alpha = 500., radius2 = 0.15 * 0.15;
+  const double r2 = (x[0] - 0.5) * (x[0] - 0.5) + (x[1] - 0.5) * (x[1] - 0.5);
+  const double xi = alpha * (radius2 - r2);
+  f0[0] = (-4.0 * alpha - 8.0 * alpha * alpha * r2 * tanh(xi)) * (1.0 / cosh(xi)) * (1.0 / cosh(xi));
+}
+static void cb_f0_cross(PF_ARGS, double f0[]) {
+  const double alpha = 50 * 4;
+  const double xy = (x[0] - 0.5) * (x[1] - 0.5);
+  f0[0] = sin(alpha * xy) * (alpha * fabs(xy) < 2 * M_PI ? 1 : 0.01);
+}
+/* their Dirichlet / exact data: ex12.cpp:127-136 (circle_u_2d), :138-145 (cross_u_2d) */
+static int cb_circle_2d(int dim, double time, const double x[], int Nc, double *u, void *ctx) {
+  (void)dim; (void)time; (void)Nc; (void)ctx;
+  const double alpha = 500., radius2 = 0.15 * 0.15;
+  const double r2 = (x[0] - 0.5) * (x[0] - 0.5) + (x[1] - 0.5) * (x[1] - 0.5);
+  *u = tanh(alpha * (radius2 - r2)) + 1.0;
+  return 0;
+}
+static int cb_cross_2d(int dim, double time, const double x[], int Nc, double *u, void *ctx) {
+  (void)dim; (void)time; (void)Nc; (void)ctx;
+  const double alpha = 50 * 4;
+  const double xy = (x[0] - 0.5) * (x[1] - 0.5);
+  *u = sin(alpha * xy) * (alpha * fabs(xy) < 2 * M_PI ? 1 : 0.01);
+  return 0;
+}
 /* Dirichlet / exact data: ex12.cpp:113-117 (2-D), :408-412 (3-D); guess :76-80 */
 static int cb_quadratic_2d(int dim, double time, const double x[], int Nc, double *u, void *ctx) {
   (void)dim; (void)time; (void)Nc; (void)ctx;
@@ -108,13 +136,16 @@ typedef struct {
   orc_bcfn bc;
 } orc_problem;
 
-/* problem ids mirror SetupProblem's switch (ex12.cpp:1170-1204): 0 COEFF_NONE, 1 ANALYTIC, 2 NONLINEAR */
+/* problem ids mirror SetupProblem's switch (ex12.cpp:1170-1204): 0 COEFF_NONE, 1 ANALYTIC, 2 NONLINEAR, 3 CIRCLE,
+ * 4 CROSS; the exact solution / Dirichlet function follows ex12.cpp:1206-1225 */
 static int orc_problem_get(int id, int dim, orc_problem *p) {
   p->bc = (dim == 3) ? cb_quadratic_3d : cb_quadratic_2d; /* ex12.cpp:1222,1230 */
   switch (id) {
     case 0: p->f0 = cb_f0_const; p->f1 = cb_f1_grad; p->g3 = cb_g3_ident; return 0;
     case 1: p->f0 = cb_f0_analytic; p->f1 = cb_f1_analytic; p->g3 = cb_g3_analytic; return 0;
     case 2: p->f0 = cb_f0_nonlinear; p->f1 = cb_f1_nonlinear; p->g3 = cb_g3_nonlinear; return 0;
+    case 3: p->f0 = cb_f0_circle; p->f1 = cb_f1_grad; p->g3 = cb_g3_ident; if (dim == 2) p->bc = cb_circle_2d; return 0;
+    case 4: p->f0 = cb_f0_cross; p->f1 = cb_f1_grad; p->g3 = cb_g3_ident; if (dim == 2) p->bc = cb_cross_2d; return 0;
   }
   return 1;
 }
@@ -606,6 +637,17 @@ int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
 #else
+  return 1;
+#endif
+}
+
+/* torchrun exports OMP_NUM_THREADS=1 to its children; the CPU baseline must still use every host core */
+int orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
   return 1;
 #endif
 }

@@ -26,6 +26,23 @@ def load(name, world):
         if world != 4:  # fewer GPUs: merge consecutive parts
             eo, vo = eo * world // 4, vo * world // 4
         return cells, coords, eo.astype(np.int32), vo.astype(np.int32)
+    if name == "24k_24p":  # config 3 at 2/4/8 GPUs: the reference's 24-part XGC partition, consecutive parts merged
+        # the 24p files hold SUBSETS of the mesh with their own local numbering; the serial mesh + the ownership of every
+        # vertex / element is rebuilt from the gids (gid = owner-contiguous global id)
+        o = ohp.Osh(golden_mesh_path("24k.osh"))
+        cells, coords = o.elem_verts(), o.coords()
+        vo = np.full(coords.shape[0], -1, np.int32)
+        key = {tuple(np.round(x, 12)): i for i, x in enumerate(coords)}
+        for r in range(24):
+            p = ohp.Osh(golden_mesh_path("24k_24p_%d.osh" % r))
+            own = p.tag(0, "ownership")
+            pc = p.coords()
+            for i in np.nonzero(own == r)[0]:
+                vo[key[tuple(np.round(pc[i], 12))]] = r
+        assert (vo >= 0).all()
+        vo = (vo * world // 24).astype(np.int32)
+        eo = vo[cells].max(axis=1).astype(np.int32)   # XGC convention: ghosts live on lower parts (owner = lowest part touching)
+        return cells, coords, eo, vo
     if name.startswith("box2d_"):
         n = int(name.split("_")[1])
         cells, coords = meshgen.box2d(n, n + 3)
@@ -71,6 +88,8 @@ def main():
                 pos = np.searchsorted(g[order], ex["ghost_gid"][sel])
                 assert np.array_equal(g[order][pos], ex["ghost_gid"][sel])
                 roots[sel] = l[order][pos]
+        roots_dev = ctx.ghost_roots_from_gids(ex["ghost_gid"], ex["ghost_owner"], ex["core_gid"], owned_core)
+        assert np.array_equal(roots_dev, roots), "device gid join vs host join (picpart files)"
         cells, coords = pcells, pcoords
         part = dict(cells=ex["core_elem_verts"], coords=ex["core_coords"], gverts=gv_core,
                     ghost_local=ex["ghost_core_idx"], ghost_owner=ex["ghost_owner"])
@@ -81,6 +100,10 @@ def main():
         part = partition.local_part(cells, coords, eo, vo, rank)
         m = ohp.Mesh(ctx, part["cells"], part["coords"])
         roots = partition.resolve_ghost_roots(part, vo, rank, world, dist.all_gather_object)
+        # A6 behind the C-ABI: the same roots from the device-side gid join (ohp_ghost_roots_from_gids)
+        gv_ = part["gverts"]
+        roots_dev = ctx.ghost_roots_from_gids(gv_[part["ghost_local"]], part["ghost_owner"], gv_, vo[gv_] == rank)
+        assert np.array_equal(roots_dev, roots), "device gid join vs host join"
         if name.startswith("box3d"):
             # the Plex-point form of the SF, as ex12 builds it: leaf = nCells + vertex, root = owner's nCells + its vertex
             ncs = [None] * world
@@ -91,7 +114,10 @@ def main():
             m.set_ghosts(part["ghost_local"], part["ghost_owner"], roots)
     m.setup()
     if os.environ.get("OHP_COMM", "p2p") != "nccl":
-        m.p2p_enable(dist.all_gather_object, world)
+        if name.startswith("box3d"):
+            m.p2p_enable_native()      # handles all-gathered over the library's own communicator
+        else:
+            m.p2p_enable(dist.all_gather_object, world)
     info = m.info()
 
     import oracle

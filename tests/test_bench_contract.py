@@ -26,6 +26,24 @@ def test_reference_arm_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "CG" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+    # the oracle uses every host core whatever OMP_NUM_THREADS says (torchrun exports 1), and says how much it measured
+    import oracle
+    assert cb["cores"] == oracle.use_all_cores()
+    assert isinstance(d["extrapolated"], bool) and 0.0 < d["measured_fraction"] <= 1.0
+
+
+def test_reference_arm_ignores_torchrun_omp_setting():
+    d = run(["--impl", "reference", "--n", "64", "--steps", "1", "--warmup", "0"], env={"OMP_NUM_THREADS": "1"})
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+
+
+def test_both_arms_print_the_same_workload_string():
+    import bench
+    a = bench.workload_string("box2d_2896", (2896, 2896), 2, 16773632)
+    assert "box2d_2896" in a and "16773632 cells" in a and "rtol 1e-09" in a
+    # nothing run-dependent (iteration counts, nnz, rank counts) may enter the string the driver compares
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"workload": workload_string(') == 3   # reference arm, GPU arm, secondary
 
 
 def test_reference_arm_nonzero_ranks_stay_silent():
@@ -34,7 +52,29 @@ def test_reference_arm_nonzero_ranks_stay_silent():
     assert p.returncode == 0 and p.stdout.strip() == ""
 
 
-def test_known_iteration_counts_are_recorded():
-    with open(os.path.join(ROOT, "profiles", "cg_iterations.json")) as f:
-        k = json.load(f)
-    assert k["box2d_2896:2896x2896"] == 7643 and k["box3d_110:110x110x110"] == 386
+def test_oracle_iteration_counts_are_recorded():
+    """The CPU arm extrapolates to the ORACLE's own converged counts (tools/oracle_cg_iterations.py), not to
+    anything the GPU arm measured."""
+    import bench
+    assert bench.oracle_iterations("box2d_2896", (2896, 2896)) == 7643
+    assert bench.oracle_iterations("box3d_110", (110, 110, 110)) == 386
+    assert bench.oracle_iterations("box2d_2896", (64, 64)) is None
+
+
+def test_morton_workload_is_the_same_mesh_renumbered():
+    import numpy as np
+    import oracle
+    from omegahpetsc_b200 import meshgen
+    c, x = meshgen.box2d(24, 17)
+    c2, x2 = meshgen.morton_reorder(c, x, (24, 17))
+    assert sorted(map(tuple, np.round(x2, 12))) == sorted(map(tuple, np.round(x, 12)))
+    tri = lambda cc, xx: sorted(tuple(sorted(map(tuple, np.round(xx[t], 12)))) for t in cc)
+    assert tri(c, x) == tri(c2, x2)
+    X = x2[c2]
+    area2 = (X[:, 1, 0] - X[:, 0, 0]) * (X[:, 2, 1] - X[:, 0, 1]) - (X[:, 1, 1] - X[:, 0, 1]) * (X[:, 2, 0] - X[:, 0, 0])
+    assert (area2 > 0).all()
+    b = oracle.mark_boundary(c2, x2.shape[0])
+    g, N = oracle.numbering(b)
+    rp, ci = oracle.pattern(c2, g, N)
+    rows = np.repeat(np.arange(N), np.diff(rp))
+    assert np.abs(ci - rows).max() > 3 * 25   # no longer banded by the grid width

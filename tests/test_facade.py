@@ -112,3 +112,46 @@ def test_vec_view_vtu(tmp_path, oracle_mod):
     full = (coords ** 2).sum(axis=1)
     full[gidx >= 0] = ref["u"]
     assert np.abs(vals - full).max() < 1e-9
+
+
+@pytest.mark.gpu
+def test_boundary_found_by_walking_the_plex_like_ex12(oracle_mod):
+    """`-boundary plex` runs the reference's own loop (ex12.cpp:966-1033: DMPlexGetHeightStratum, DMPlexGetSupportSize,
+    DMPlexGetCone, DMSetLabelValue) against the facade; same result as the device-side detection."""
+    build()
+    outs = []
+    for b in ("device", "plex"):
+        p = subprocess.run([EXE, "-mesh", golden_mesh_path("24k.osh"), "-ksp_rtol", "1e-9", "-ksp_max_it", "100000", "-boundary", b, "-dm_view"],
+                           capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stdout + p.stderr
+        outs.append(re.search(r"N: (\d+) Newton its: (\d+) CG its: (\d+) L_2 Error: ([0-9.e+-]+)", p.stdout).groups())
+        assert "DM Object: Mesh in 2 dimensions" in p.stdout and "2-cells: 23754" in p.stdout and "0-cells: 12060" in p.stdout
+        if b == "plex":
+            assert "1-cells: 35813" in p.stdout   # the 24k fixture has 35 813 edges (SURVEY Appendix B)
+    assert outs[0] == outs[1] and int(outs[0][0]) == 11696
+
+
+@pytest.mark.gpu
+def test_circle_forcing_and_monitors(oracle_mod):
+    build()
+    p = subprocess.run([EXE, "-mesh", "box", "-cells", "64,64", "-variable_coefficient", "circle", "-ksp_rtol", "1e-10", "-snes_monitor_short",
+                        "-ksp_monitor_short", "-ksp_converged_reason", "-snes_converged_reason"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    c, x = oracle_mod.box2d(64, 64)
+    bnd = oracle_mod.mark_boundary(c, x.shape[0])
+    gidx, N = oracle_mod.numbering(bnd)
+    rowptr, colidx = oracle_mod.pattern(c, gidx, N)
+    ref = oracle_mod.newton(3, c, x, gidx, N, rowptr, colidx, ksp_rtol=1e-10, ksp_maxit=10000)
+    m = re.search(r"N: (\d+) Newton its: (\d+) CG its: (\d+) L_2 Error: ([0-9.e+-]+)", p.stdout)
+    assert int(m.group(1)) == N and int(m.group(2)) == 1 and abs(int(m.group(3)) - ref["ksp_its"]) <= 2
+    # PETSc's monitor layout: SNES lines indented 2, KSP lines indented 4, one KSP line per iteration + the initial norm
+    assert p.stdout.count(" KSP Residual norm ") == int(m.group(3)) + 1
+    assert re.search(r"^  0 SNES Function norm ", p.stdout, re.M) and re.search(r"^  1 SNES Function norm ", p.stdout, re.M)
+    assert re.search(r"^    0 KSP Residual norm ", p.stdout, re.M)
+    assert "Linear solve converged due to CONVERGED_RTOL iterations %s" % m.group(3) in p.stdout
+    # the L2 error is measured against circle_u_2d, the problem's own exact solution (not the quadratic)
+    exact = np.tanh(500.0 * (0.15 ** 2 - ((x[:, 0] - 0.5) ** 2 + (x[:, 1] - 0.5) ** 2))) + 1.0
+    assert float(m.group(4)) < 0.2 * np.sqrt(np.mean(exact ** 2))
+    # a function without a device instantiation is refused, not evaluated on the host
+    q = subprocess.run([EXE, "-mesh", "box", "-cells", "8,8", "-variable_coefficient", "cross", "-run_type", "perf"], capture_output=True, text=True, timeout=120)
+    assert q.returncode == 0, q.stdout + q.stderr

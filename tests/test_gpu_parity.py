@@ -386,7 +386,33 @@ def test_full_size_16M_triangles(ctx):
     J.mult(u, Au)
     Au.aypx(-1.0, F0)  # r = b - A x
     assert Au.norm() == pytest.approx(out["rnorm"], rel=1e-6)
+    # the oracle itself at FULL size (OpenMP): numbering and pattern bit-exact, F(0) and J(0) to 1e-12, 300 CG iterations
+    full_size_oracle_compare(m, J, cells_coords=(oracle.box2d(n, n)), cg_hist=out["hist"])
     m.destroy()
+
+
+def full_size_oracle_compare(m, J, cells_coords, cg_hist=None):
+    import oracle
+    oracle.use_all_cores()
+    cells, coords = cells_coords
+    bnd = oracle.mark_boundary(cells, coords.shape[0], omp=True)
+    gidx, N = oracle.numbering(bnd)
+    rowptr, colidx = oracle.pattern(cells, gidx, N, omp=True)
+    assert np.array_equal(m.boundary(), bnd) and np.array_equal(m.numbering(), gidx.astype(np.int64))
+    rp, ci = m.csr()
+    assert np.array_equal(rp, rowptr) and np.array_equal(ci, colidx.astype(np.int64))
+    u0, F0 = m.create_global_vector(), m.create_global_vector()
+    m.residual(0, u0.set(0.0), F0)
+    m.jacobian(0, u0, J)
+    Fo = oracle.residual(0, cells, coords, gidx, N, np.zeros(N), omp=True)
+    vo = oracle.jacobian(0, cells, coords, gidx, N, np.zeros(N), rowptr, colidx, omp=True)
+    assert np.abs(F0.to_host() - Fo).max() <= VAL_RTOL * np.abs(Fo).max()
+    vd = J.values()
+    assert rowwise_close(vd, vo, rowptr, VAL_RTOL) and np.array_equal(vd == 0.0, vo == 0.0)
+    if cg_hist is not None:
+        ref = oracle.cg(rowptr, colidx, vo, Fo, rtol=1e-9, maxit=len(cg_hist) - 1, omp=True, history=True)
+        assert np.allclose(cg_hist, ref["hist"], rtol=1e-6), "residual history of the first iterations"
+    u0.destroy(); F0.destroy()
 
 
 def test_persistent_cg_kernel_small_mesh(ctx, oracle_mod):
@@ -439,4 +465,149 @@ def test_full_size_3d_8M_tets(ctx):
     assert res["reason"] == 3 and res["its"] == 1
     exact = m.project(0, 1, m.create_global_vector()).to_host()
     assert np.abs(u.to_host() - exact).max() < 1e-7
+    full_size_oracle_compare(m, J, (cells, coords))
+    m.destroy()
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: circle / cross problems, the problem's own exact solution, Plex facets, caller-set labels,
+# orderings whose column offsets do not fit 16 bits, monitors
+# ------------------------------------------------------------------------------------------------
+def exact_of(problem, coords):
+    x, y = coords[:, 0], coords[:, 1]
+    if problem == 3:
+        return np.tanh(500.0 * (0.15 ** 2 - ((x - 0.5) ** 2 + (y - 0.5) ** 2))) + 1.0
+    if problem == 4:
+        xy = (x - 0.5) * (y - 0.5)
+        return np.sin(200.0 * xy) * np.where(200.0 * np.abs(xy) < 2 * np.pi, 1.0, 0.01)
+    return (coords ** 2).sum(axis=1)
+
+
+def numpy_l2_error(oracle, problem, cells, coords, gidx, u):
+    xi, w = oracle.quadrature(2)
+    full = exact_of(problem, coords)
+    full[gidx >= 0] = u
+    X = coords[cells]
+    J = 0.5 * np.stack([X[:, 1] - X[:, 0], X[:, 2] - X[:, 0]], axis=2)
+    detJ = J[:, 0, 0] * J[:, 1, 1] - J[:, 0, 1] * J[:, 1, 0]
+    err = 0.0
+    for q in range(4):
+        phi = np.array([-(xi[q, 0] + xi[q, 1]) / 2, (1 + xi[q, 0]) / 2, (1 + xi[q, 1]) / 2])
+        xq = X[:, 0] + J @ (xi[q] + 1.0)
+        err += (w[q] * np.abs(detJ) * (full[cells] @ phi - exact_of(problem, xq)) ** 2).sum()
+    return float(np.sqrt(err))
+
+
+@pytest.mark.parametrize("problem", [3, 4])
+@pytest.mark.parametrize("name", ["box2d_100x70", "sheared_21x13", "T24k"])
+def test_circle_and_cross_forcing(ctx, oracle_mod, name, problem):
+    """f0_circle_u / f0_cross_u with their own Dirichlet data (ex12.cpp:127-177, selected at :1197-1213)."""
+    cells, coords = get_mesh(name)
+    bnd, gidx, N, rowptr, colidx = oracle_setup(oracle_mod, cells, coords)
+    m = ohp.Mesh(ctx, cells, coords).setup()
+    J, u, F = m.create_matrix(), m.create_global_vector(), m.create_global_vector()
+    uh = probe_field(coords, gidx)
+    u.from_host(uh)
+    Fo = oracle_mod.residual(problem, cells, coords, gidx, N, uh)
+    vo = oracle_mod.jacobian(problem, cells, coords, gidx, N, uh, rowptr, colidx)
+    assert np.abs(m.residual(problem, u, F).to_host() - Fo).max() <= VAL_RTOL * np.abs(Fo).max()
+    assert rowwise_close(m.jacobian(problem, u, J).values(), vo, rowptr, VAL_RTOL)
+    res = m.snes_solve(problem, J, u.set(0.0), ksp=ohp.ksp_options(rtol=1e-10, max_it=100000))
+    ref = oracle_mod.newton(problem, cells, coords, gidx, N, rowptr, colidx, ksp_rtol=1e-10, ksp_maxit=100000)
+    assert (res["its"], res["reason"]) == (ref["snes_its"], ref["reason"]) == (1, 3)
+    assert np.abs(u.to_host() - ref["u"]).max() <= 1e-7 * max(1.0, np.abs(ref["u"]).max())
+    # DMComputeL2Diff uses THIS problem's exact solution (it used to be the quadratic for every problem)
+    assert m.l2_error(problem, u) == pytest.approx(numpy_l2_error(oracle_mod, problem, cells, coords, gidx, ref["u"]), rel=1e-6)
+    assert np.abs(m.project(problem, 1, F).to_host() - exact_of(problem, coords)[gidx >= 0]).max() <= 1e-14
+    m.destroy()
+
+
+@pytest.mark.parametrize("name", ["one_tri", "fan4", "T23", "box2d_33x17", "T24k", "box3d_5x4x3", "warped3d_6x5x7"])
+def test_facets_like_plex_interpolate(ctx, name):
+    """DMPlexGetHeightStratum(1) / GetSupportSize / GetCone (ex12.cpp:966-1010) against a numpy construction."""
+    cells, coords = get_mesh(name)
+    nc = cells.shape[1]
+    loc = [(0, 1), (1, 2), (2, 0)] if nc == 3 else [(0, 1, 2), (0, 3, 1), (0, 2, 3), (2, 1, 3)]
+    first, support, order = {}, {}, []
+    for c, cv in enumerate(cells):
+        for f in loc:
+            key = tuple(sorted(int(cv[k]) for k in f))
+            if key not in first:
+                first[key] = (len(order), tuple(int(cv[k]) for k in f))
+                order.append(key)
+            support[key] = support.get(key, 0) + 1
+    m = ohp.Mesh(ctx, cells, coords)
+    fv, sup, cf = m.facets()
+    assert fv.shape[0] == len(order)
+    for i, key in enumerate(order):        # numbered by creating cell, then local facet; cone in that cell's orientation
+        assert tuple(fv[i]) == first[key][1] and sup[i] == support[key]
+    for c, cv in enumerate(cells):
+        for j, f in enumerate(loc):
+            assert cf[c, j] == first[tuple(sorted(int(cv[k]) for k in f))][0]
+    # facets with one supporting cell carry exactly the boundary vertices (ex12.cpp:986-1010)
+    m.setup()
+    bverts = np.zeros(coords.shape[0], np.uint8)
+    bverts[np.unique(fv[sup == 1])] = 1
+    assert np.array_equal(bverts, m.boundary())
+    m.destroy()
+
+
+def test_label_set_by_the_caller(ctx, oracle_mod):
+    """DMSetLabelValue point by point (ex12.cpp:1023-1026): the caller's label replaces the library's detection."""
+    cells, coords = get_mesh("box2d_33x17")
+    bnd = oracle_mod.mark_boundary(cells, coords.shape[0])
+    extra = np.nonzero(bnd == 0)[0][[5, 77, 200]]
+    lab = bnd.copy()
+    lab[extra] = 1
+    gidx, N = oracle_mod.numbering(lab)
+    rowptr, colidx = oracle_mod.pattern(cells, gidx, N)
+    m = ohp.Mesh(ctx, cells, coords)
+    m.set_label(np.nonzero(lab)[0])
+    m.setup()
+    assert np.array_equal(m.boundary(), lab) and np.array_equal(m.numbering(), gidx.astype(np.int64))
+    rp, ci = m.csr()
+    assert np.array_equal(rp, rowptr) and np.array_equal(ci, colidx.astype(np.int64))
+    with pytest.raises(ohp.OhpError):
+        m.set_label([0])  # after setup
+    m.destroy()
+
+
+def test_morton_ordering_uses_the_32bit_column_stream(ctx, oracle_mod):
+    """A space-filling-curve ordering (what Omega_h::build_box produces, ex12.cpp:805): |column - row| no longer fits
+    16 bits everywhere, so the SpMV streams the 32-bit column ids.  Same parity bar as every mesh."""
+    from omegahpetsc_b200 import meshgen
+    n = 700
+    c0, x0 = meshgen.box2d(n, n)
+    cells, coords = meshgen.morton_reorder(c0, x0, (n, n))
+    bnd, gidx, N, rowptr, colidx = oracle_setup(oracle_mod, cells, coords)
+    rows = np.repeat(np.arange(N), np.diff(rowptr))
+    far = np.abs(colidx - rows) > 32767
+    assert far.any(), "this mesh must have offsets beyond 16 bits"
+    m = ohp.Mesh(ctx, cells, coords).setup()
+    rp, ci = m.csr()
+    assert np.array_equal(m.numbering(), gidx.astype(np.int64)) and np.array_equal(rp, rowptr) and np.array_equal(ci, colidx.astype(np.int64))
+    J, u, y = m.create_matrix(), m.create_global_vector(), m.create_global_vector()
+    m.jacobian(0, u, J)
+    xh = np.random.default_rng(3).standard_normal(N)
+    J.mult(u.from_host(xh), y)
+    yo = oracle_mod.spmv(rowptr, colidx, J.values(), xh)
+    assert np.abs(y.to_host() - yo).max() <= 1e-13 * np.abs(yo).max()
+    res = m.snes_solve(0, J, u.set(0.0), ksp=ohp.ksp_options(rtol=1e-10, max_it=100000))
+    assert res["reason"] == 3 and np.abs(u.to_host() - (coords ** 2).sum(axis=1)[gidx >= 0]).max() < 1e-7
+    m.destroy()
+
+
+def test_monitors_report_every_iteration(ctx, oracle_mod):
+    """-snes_monitor / -ksp_monitor (CMakeLists.txt:56-57): norms per Newton iteration and per CG iteration."""
+    cells, coords = get_mesh("T24k")
+    bnd, gidx, N, rowptr, colidx = oracle_setup(oracle_mod, cells, coords)
+    m = ohp.Mesh(ctx, cells, coords).setup()
+    J, u = m.create_matrix(), m.create_global_vector()
+    mon = {}
+    res = m.snes_solve(2, J, u.set(0.0), ksp=ohp.ksp_options(rtol=1e-9, max_it=100000), monitor=mon)
+    assert res["reason"] > 0 and res["its"] >= 2
+    assert [it for it, _ in mon["snes"]] == list(range(res["its"] + 1))
+    assert mon["snes"][0][1] == pytest.approx(res["fnorm0"]) and mon["snes"][-1][1] == pytest.approx(res["fnorm"])
+    assert len(mon["ksp"]) == res["its"] and sum(len(h) - 1 for h in mon["ksp"]) == res["ksp_its"]
+    assert all(r == 2 for r in mon["ksp_reason"]) and all(h[-1] <= 1e-9 * h[0] for h in mon["ksp"])
     m.destroy()

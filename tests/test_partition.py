@@ -68,3 +68,22 @@ def test_generators_closed_forms():
     X = coords[cells]
     vol = np.einsum("ij,ij->i", np.cross(X[:, 1] - X[:, 0], X[:, 2] - X[:, 0]), X[:, 3] - X[:, 0]) / 6.0
     assert (vol > 0).all() and vol.sum() == pytest.approx(1.0, rel=1e-14)
+
+
+def test_config3_at_8_gpus_is_the_24_part_fixture_merged():
+    """BASELINE config 3 has no 2- or 8-part fixtures: they are derived by merging consecutive parts of the reference's
+    24-part XGC partition.  Host-only check of that derivation (tests/mgpu_worker.load)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import mgpu_worker
+    for world, counts in ((8, [431, 1285, 1889, 1897, 2340, 2820, 3364, 9728]), (2, [5502, 18252])):
+        cells, coords, eo, vo = mgpu_worker.load("24k_24p", world)
+        assert cells.shape == (23754, 3) and coords.shape == (12060, 2)
+        assert np.bincount(eo, minlength=world).tolist() == counts        # SURVEY 8d: "owned elements 8p: 431 ... 9728"
+        for r in range(world):                                            # chain: a part's ghosts live on lower parts only
+            gv = np.unique(cells[eo == r])
+            assert (vo[gv] <= r).all()
+        nghost = [int((vo[np.unique(cells[eo == r])] != r).sum()) for r in range(world)]
+        if world == 8:
+            assert nghost == [0, 47, 96, 141, 176, 214, 256, 306]          # SURVEY 8d ghost counts
