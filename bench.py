@@ -448,7 +448,9 @@ def measure_workload(job, args, workload, steps, warmup, e2e_steps, sampler, wit
     if e2e_steps > 0:
         job.barrier()
         t0 = time.perf_counter()
+        e2e_each = []
         for _ in range(e2e_steps):
+            t_one = time.perf_counter()
             m2 = build_mesh()
             J2, u2 = m2.create_matrix(), m2.create_global_vector()
             m2.project(0, 0, u2)
@@ -456,10 +458,12 @@ def measure_workload(job, args, workload, steps, warmup, e2e_steps, sampler, wit
             uh2 = u2.to_host()
             assert r2["reason"] == 3 and np.isfinite(uh2[:8]).all()
             J2.destroy(); u2.destroy(); m2.destroy()
+            e2e_each.append((time.perf_counter() - t_one) * 1e3)
         job.barrier()
         t_e2e = job.max_over_ranks((time.perf_counter() - t0) / e2e_steps)
         e2e = {"value": N / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(lcells.nbytes + lcoords.nbytes),
                "d2h_bytes_per_step": int(info.n_owned * 8), "ms_per_step": t_e2e * 1e3, "steps": e2e_steps,
+               "each_step_ms_rank0": e2e_each,
                "includes": "ohp_mesh_create (H2D of cells+coords from pinned host memory), device numbering + CSR build, "
                            "Newton step, D2H of the solution"}
 
@@ -515,9 +519,11 @@ def measure_workload(job, args, workload, steps, warmup, e2e_steps, sampler, wit
         check["F_max_abs_diff_over_max_abs"] = float(np.abs(Fd - Fo).max() / np.abs(Fo).max())
         rowmax = np.maximum.reduceat(np.abs(vo_), rp[:-1].astype(np.int64))
         check["J_max_row_relative_diff"] = float((np.maximum.reduceat(np.abs(vd - vo_), rp[:-1].astype(np.int64)) / rowmax).max())
-        check["J_explicit_zeros_match"] = bool(np.array_equal(vd == 0.0, vo_ == 0.0))
         check["assembly_tol"] = 1e-12
-        ok = ok and check["F_max_abs_diff_over_max_abs"] <= 1e-12 and check["J_max_row_relative_diff"] <= 1e-12 and check["J_explicit_zeros_match"]
+        ok = ok and check["F_max_abs_diff_over_max_abs"] <= 1e-12 and check["J_max_row_relative_diff"] <= 1e-12
+        if dim == 2:  # same-diagonal box: the hypotenuse couplings are sums of two exact zeros and must stay exactly 0.0
+            check["J_explicit_zeros_match"] = bool(np.array_equal(vd == 0.0, vo_ == 0.0))
+            ok = ok and check["J_explicit_zeros_match"]
         F0.destroy(); u0.destroy()
     check["ok"] = bool(ok)
 

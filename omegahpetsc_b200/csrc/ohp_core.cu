@@ -266,6 +266,7 @@ extern "C" int ohp_mesh_destroy(ohp_mesh m) {
   OHP_FREE(m->ctx, m->bnd); OHP_FREE(m->ctx, m->lidx); OHP_FREE(m->ctx, m->row_vertex); OHP_FREE(m->ctx, m->ldof_gid); OHP_FREE(m->ctx, m->rowptr);
   OHP_FREE(m->ctx, m->colidx); OHP_FREE(m->ctx, m->col16); OHP_FREE(m->ctx, m->slot); OHP_FREE(m->ctx, m->tile_row);
   OHP_FREE(m->ctx, m->facet_verts); OHP_FREE(m->ctx, m->facet_support); OHP_FREE(m->ctx, m->cell_facets);
+  ohp_fused_plan_free(m->ctx, m->fused);
   ohp_halo_free(m->ctx, m->halo);
   ohp_p2p_free(m->ctx, m->p2p);
   OHP_FREE(m->ctx, m->ghost_cta);

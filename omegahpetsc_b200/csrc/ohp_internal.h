@@ -154,6 +154,7 @@ struct ohp_mesh_s {
   /* "marker" label set point by point by the caller (DMSetLabelValue) instead of detected here */
   bool has_user_label;
   std::vector<int32_t> user_label;
+  struct ohp_fused_plan *fused; /* tables of the fused persistent CG kernel, built on first use (ohp_cg_fused.cu) */
   uint8_t *ghost_cta; /* per persistent-SpMV CTA: 1 if its tiles reference ghost columns (NULL when serial) */
 };
 
@@ -201,6 +202,10 @@ ohp_trace ohp_cg_trace_open(ohp_context ctx);
 void ohp_cg_trace_dump(ohp_context ctx, const char *algo);
 int ohp_spmv_launch(ohp_mat A, const double *x, double *y);
 int ohp_extract_dinv(ohp_mat A);
+
+/* ohp_cg_fused.cu */
+int ohp_cg_fused_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o, ohp_ksp_result *res, bool p2p);
+void ohp_fused_plan_free(ohp_context ctx, struct ohp_fused_plan *p);
 
 /* ohp_cg_persistent.cu */
 int ohp_cg_persistent_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o, ohp_ksp_result *res, bool p2p);

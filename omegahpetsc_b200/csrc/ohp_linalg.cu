@@ -333,8 +333,12 @@ static int spmv_smem_bytes(ohp_mesh m) { return (int)sizeof(double) * (kSpmvTile
 static int spmv_configure(ohp_mesh m) {
   const int bytes = spmv_smem_bytes(m);
   if (bytes > 200 * 1024) OHP_FAIL(OHP_ERR_SUP, "SpMV: longest row %d exceeds the shared-memory tile", m->max_row);
-  OHP_CUDA(cudaFuncSetAttribute(k_spmv_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  OHP_CUDA(cudaFuncSetAttribute(k_spmv_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  static int configured_bytes[64] = {0}; /* per device id */
+  if (bytes > configured_bytes[m->ctx->device & 63]) {
+    OHP_CUDA(cudaFuncSetAttribute(k_spmv_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    OHP_CUDA(cudaFuncSetAttribute(k_spmv_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    configured_bytes[m->ctx->device & 63] = bytes;
+  }
   return 0;
 }
 
@@ -357,9 +361,13 @@ static int spmv_tma_launch_ts(ohp_mat A, const IDX *cols, const double *x, doubl
   ohp_mesh m = A->mesh;
   ohp_context ctx = m->ctx;
   constexpr int smem = tma_smem_bytes(S, (int)sizeof(IDX));
-  /* per device, not per process: the attribute belongs to the context of the current device */
-  OHP_CUDA(cudaFuncSetAttribute(k_spmv_tma<true, S, NC, IDX, SPLIT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  OHP_CUDA(cudaFuncSetAttribute(k_spmv_tma<false, S, NC, IDX, SPLIT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  /* once per DEVICE, not per process: the attribute belongs to the context of the device (one bit per device id) */
+  static unsigned long long configured_devices = 0ull;
+  if (!((configured_devices >> (ctx->device & 63)) & 1ull)) {
+    OHP_CUDA(cudaFuncSetAttribute(k_spmv_tma<true, S, NC, IDX, SPLIT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    OHP_CUDA(cudaFuncSetAttribute(k_spmv_tma<false, S, NC, IDX, SPLIT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured_devices |= 1ull << (ctx->device & 63);
+  }
   const int grid = std::max(1, std::min(m->n_tiles, ctx->num_sms * MINB));
   ohp_cgcg_epi epi = epi_in;
   epi.pin_tiles = spmv_pin_tiles(m, grid, (int)sizeof(IDX));
@@ -1008,6 +1016,8 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
     bool persistent = feasible && ctx->nranks == 1 && n < kPersistentBelowRows; /* measured: see DESIGN.md section 5 */
     if (force && force[0] == 'c') persistent = false; /* classic or cgcg */
     if (force && force[0] == 'p') persistent = feasible;
+    /* OHP_CG=fused: the one-synchronisation persistent kernel (ohp_cg_fused.cu) */
+    if (force && force[0] == 'f' && feasible) return ohp_cg_fused_solve(A, b, x, o, res, can_p2p);
     if (persistent) return ohp_cg_persistent_solve(A, b, x, o, res, can_p2p);
     /* single-reduction recurrence in two launches: default for partitioned runs over NVLink peer memory (one
      * all-reduce and one kernel boundary fewer per iteration); OHP_CG=cgcg forces it on one GPU */

@@ -391,7 +391,7 @@ def test_full_size_16M_triangles(ctx):
     m.destroy()
 
 
-def full_size_oracle_compare(m, J, cells_coords, cg_hist=None):
+def full_size_oracle_compare(m, J, cells_coords, cg_hist=None, exact_zeros=True):
     import oracle
     oracle.use_all_cores()
     cells, coords = cells_coords
@@ -408,7 +408,9 @@ def full_size_oracle_compare(m, J, cells_coords, cg_hist=None):
     vo = oracle.jacobian(0, cells, coords, gidx, N, np.zeros(N), rowptr, colidx, omp=True)
     assert np.abs(F0.to_host() - Fo).max() <= VAL_RTOL * np.abs(Fo).max()
     vd = J.values()
-    assert rowwise_close(vd, vo, rowptr, VAL_RTOL) and np.array_equal(vd == 0.0, vo == 0.0)
+    assert rowwise_close(vd, vo, rowptr, VAL_RTOL)
+    if exact_zeros:  # 2-D same-diagonal box: every hypotenuse coupling is a sum of two exact zeros (SURVEY 8c anchor 1)
+        assert np.array_equal(vd == 0.0, vo == 0.0)
     if cg_hist is not None:
         ref = oracle.cg(rowptr, colidx, vo, Fo, rtol=1e-9, maxit=len(cg_hist) - 1, omp=True, history=True)
         assert np.allclose(cg_hist, ref["hist"], rtol=1e-6), "residual history of the first iterations"
@@ -465,7 +467,9 @@ def test_full_size_3d_8M_tets(ctx):
     assert res["reason"] == 3 and res["its"] == 1
     exact = m.project(0, 1, m.create_global_vector()).to_host()
     assert np.abs(u.to_host() - exact).max() < 1e-7
-    full_size_oracle_compare(m, J, (cells, coords))
+    # (3-D Kuhn tets: the zero couplings are cancellations ACROSS cells, so whether they come out as 0.0 or 1e-18
+    #  depends on the summation order; they are covered by the 1e-12 row-relative bound)
+    full_size_oracle_compare(m, J, (cells, coords), exact_zeros=False)
     m.destroy()
 
 
@@ -514,7 +518,10 @@ def test_circle_and_cross_forcing(ctx, oracle_mod, name, problem):
     assert rowwise_close(m.jacobian(problem, u, J).values(), vo, rowptr, VAL_RTOL)
     res = m.snes_solve(problem, J, u.set(0.0), ksp=ohp.ksp_options(rtol=1e-10, max_it=100000))
     ref = oracle_mod.newton(problem, cells, coords, gidx, N, rowptr, colidx, ksp_rtol=1e-10, ksp_maxit=100000)
-    assert (res["its"], res["reason"]) == (ref["snes_its"], ref["reason"]) == (1, 3)
+    # on the XGC coordinates (r > 1) sech^2 underflows: F(0) == 0 exactly and SNESConvergedDefault stops at
+    # iteration 0 with FNORM_ABS, in the oracle as well as here
+    assert (res["its"], res["reason"]) == (ref["snes_its"], ref["reason"])
+    assert (res["its"], res["reason"]) in ((1, 3), (0, 2))
     assert np.abs(u.to_host() - ref["u"]).max() <= 1e-7 * max(1.0, np.abs(ref["u"]).max())
     # DMComputeL2Diff uses THIS problem's exact solution (it used to be the quadratic for every problem)
     assert m.l2_error(problem, u) == pytest.approx(numpy_l2_error(oracle_mod, problem, cells, coords, gidx, ref["u"]), rel=1e-6)
@@ -599,12 +606,14 @@ def test_morton_ordering_uses_the_32bit_column_stream(ctx, oracle_mod):
 
 def test_monitors_report_every_iteration(ctx, oracle_mod):
     """-snes_monitor / -ksp_monitor (CMakeLists.txt:56-57): norms per Newton iteration and per CG iteration."""
-    cells, coords = get_mesh("T24k")
+    cells, coords = get_mesh("box2d_100x70")
     bnd, gidx, N, rowptr, colidx = oracle_setup(oracle_mod, cells, coords)
     m = ohp.Mesh(ctx, cells, coords).setup()
     J, u = m.create_matrix(), m.create_global_vector()
     mon = {}
-    res = m.snes_solve(2, J, u.set(0.0), ksp=ohp.ksp_options(rtol=1e-9, max_it=100000), monitor=mon)
+    # nonlinear problem (nu = |grad u|^2-dependent, ex12.cpp:292-383): start away from u = 0, where J is singular
+    u.from_host(0.7 * (coords ** 2).sum(axis=1)[gidx >= 0])
+    res = m.snes_solve(2, J, u, ksp=ohp.ksp_options(rtol=1e-9, max_it=100000), monitor=mon)
     assert res["reason"] > 0 and res["its"] >= 2
     assert [it for it, _ in mon["snes"]] == list(range(res["its"] + 1))
     assert mon["snes"][0][1] == pytest.approx(res["fnorm0"]) and mon["snes"][-1][1] == pytest.approx(res["fnorm"])
