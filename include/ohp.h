@@ -310,6 +310,10 @@ int ohp_l2_error(ohp_mesh mesh, int problem, ohp_vec u, double *err);
 /* KSP CG (PETSc-internal KSPSolve_CG selected by -ksp_type cg at ex12.cpp:1543).        */
 /* ------------------------------------------------------------------------------------ */
 enum { OHP_PC_NONE = 0, OHP_PC_JACOBI = 1 };
+/* -ksp_type: cg (the library picks the recurrence -- classic, single-reduction or pipelined -- from the global problem
+ * size and the transport; all give CG's iterates in exact arithmetic) or pipecg (PETSc's KSPPIPECG, Ghysels-Vanroose:
+ * forces the pipelined recurrence, whose reductions overlap the SpMV) */
+enum { OHP_KSP_CG = 0, OHP_KSP_PIPECG = 1 };
 typedef struct {
   double rtol, abstol, dtol; /* -ksp_rtol (1e-5; CTests 1e-9 CMakeLists.txt:53) -ksp_atol 1e-50 -ksp_divtol 1e5 */
   int32_t max_it;            /* -ksp_max_it 10000 */
@@ -318,6 +322,7 @@ typedef struct {
   int32_t history_cap;       /* length of `history` (0 = none) */
   double *history;           /* host array receiving the monitored norm per iteration (-ksp_monitor) */
   int32_t profile;           /* >0: bracket up to this many SpMV launches with CUDA events (-log_view analogue) */
+  int32_t ksp_type;          /* OHP_KSP_CG (default) | OHP_KSP_PIPECG */
 } ohp_ksp_options;
 typedef struct {
   int32_t its;

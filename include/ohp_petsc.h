@@ -662,7 +662,9 @@ inline PetscErrorCode SNESSetFromOptions(SNES snes) {
   PetscOptionsGetReal(NULL, NULL, "-ksp_divtol", &snes->opts.ksp.dtol, NULL);
   PetscOptionsGetInt(NULL, NULL, "-ksp_max_it", &snes->opts.ksp.max_it, NULL);
   PetscOptionsGetString(NULL, NULL, "-ksp_type", buf, sizeof(buf), &set);
-  if (set && strcmp(buf, "cg")) { fprintf(stderr, "[0]PETSC ERROR: -ksp_type %s: only cg is built (north_star)\n", buf); return PETSC_ERR_SUP; }
+  snes->opts.ksp.ksp_type = OHP_KSP_CG;
+  if (set && !strcmp(buf, "pipecg")) snes->opts.ksp.ksp_type = OHP_KSP_PIPECG; /* KSPPIPECG: reductions overlap the SpMV */
+  else if (set && strcmp(buf, "cg")) { fprintf(stderr, "[0]PETSC ERROR: -ksp_type %s: only cg and pipecg are built (north_star)\n", buf); return PETSC_ERR_SUP; }
   snes->opts.ksp.pc = OHP_PC_NONE;
   PetscOptionsGetString(NULL, NULL, "-pc_type", buf, sizeof(buf), &set);
   if (set) {

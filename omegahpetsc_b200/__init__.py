@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get("OHP_LIB") or os.path.join(_HERE, "lib", "libohp.so") 
 
 PROBLEM_COEFF_NONE, PROBLEM_ANALYTIC, PROBLEM_NONLINEAR, PROBLEM_CIRCLE, PROBLEM_CROSS = 0, 1, 2, 3, 4
 PC_NONE, PC_JACOBI = 0, 1
+KSP_CG, KSP_PIPECG = 0, 1
 
 _i32p = ctypes.POINTER(ctypes.c_int32)
 _i64p = ctypes.POINTER(ctypes.c_int64)
@@ -46,7 +47,8 @@ class MeshInfo(ctypes.Structure):
 class KspOptions(ctypes.Structure):
     _fields_ = [("rtol", ctypes.c_double), ("abstol", ctypes.c_double), ("dtol", ctypes.c_double),
                 ("max_it", ctypes.c_int32), ("pc", ctypes.c_int32), ("check_every", ctypes.c_int32),
-                ("history_cap", ctypes.c_int32), ("history", _f64p), ("profile", ctypes.c_int32)]
+                ("history_cap", ctypes.c_int32), ("history", _f64p), ("profile", ctypes.c_int32),
+                ("ksp_type", ctypes.c_int32)]
 
 
 class KspResult(ctypes.Structure):
@@ -381,11 +383,12 @@ class Mat:
         return y
 
 
-def ksp_options(rtol=1e-5, abstol=1e-50, dtol=1e5, max_it=10000, pc=PC_NONE, check_every=0, profile=0):
+def ksp_options(rtol=1e-5, abstol=1e-50, dtol=1e5, max_it=10000, pc=PC_NONE, check_every=0, profile=0, ksp_type=KSP_CG):
     o = KspOptions()
     _chk(lib().ohp_ksp_default_options(ctypes.byref(o)))
     o.rtol, o.abstol, o.dtol, o.max_it, o.pc, o.check_every = rtol, abstol, dtol, int(max_it), int(pc), int(check_every)
     o.profile = int(profile)
+    o.ksp_type = int(ksp_type)
     return o
 
 

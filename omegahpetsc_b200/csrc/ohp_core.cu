@@ -267,6 +267,7 @@ extern "C" int ohp_mesh_destroy(ohp_mesh m) {
   OHP_FREE(m->ctx, m->colidx); OHP_FREE(m->ctx, m->col16); OHP_FREE(m->ctx, m->slot); OHP_FREE(m->ctx, m->tile_row);
   OHP_FREE(m->ctx, m->facet_verts); OHP_FREE(m->ctx, m->facet_support); OHP_FREE(m->ctx, m->cell_facets);
   ohp_fused_plan_free(m->ctx, m->fused);
+  ohp_pf_plan_free(m->ctx, m->pfplan);
   ohp_halo_free(m->ctx, m->halo);
   ohp_p2p_free(m->ctx, m->p2p);
   OHP_FREE(m->ctx, m->ghost_cta);

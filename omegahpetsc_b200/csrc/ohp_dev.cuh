@@ -131,9 +131,8 @@ __device__ __forceinline__ void p2p_wait(const unsigned long long *flag, unsigne
   }
 }
 
-template <int NV> __device__ __forceinline__ void p2p_allreduce(const ohp_p2p_dev &pd, double (&v)[NV]) {
-  if (threadIdx.x >= 32) return;
-  const int lane = threadIdx.x;
+/* one full warp; v valid in lane 0 on entry, the totals valid in every lane on return */
+template <int NV> __device__ __forceinline__ void p2p_allreduce_warp(const ohp_p2p_dev &pd, double (&v)[NV], int lane) {
   unsigned long long seq = 0;
   if (lane == 0) { seq = pd.seq[0] + 1; pd.seq[0] = seq; }
   seq = __shfl_sync(0xffffffffu, seq, 0);
@@ -158,6 +157,10 @@ template <int NV> __device__ __forceinline__ void p2p_allreduce(const ohp_p2p_de
   }
 #pragma unroll
   for (int k = 0; k < NV; ++k) v[k] = tot[k];
+}
+template <int NV> __device__ __forceinline__ void p2p_allreduce(const ohp_p2p_dev &pd, double (&v)[NV]) {
+  if (threadIdx.x >= 32) return;
+  p2p_allreduce_warp<NV>(pd, v, (int)threadIdx.x);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -288,7 +291,10 @@ struct ohp_cgcg_epi {
   int nvpart, jacobi, hist_cap;
   double *hist;
   const uint8_t *ghost_cta; /* non-NULL: the SpMV itself waits for the halo, and only in the CTAs flagged here */
-  int pin_tiles;            /* leading tiles of every CTA loaded with the L2 evict_last policy (0 = no hints at all) */
+  int pipe;                 /* pipelined recurrence: no dot product here, the host names the input buffer.  1: an extra
+                             * warp of CTA 0 reduces the vector kernel's partials (nvpart x 3), all-reduces them and
+                             * advances the scalars WHILE the other warps stream the matrix; 2: nothing to reduce */
+  int pin_tiles;            /* > 0: leading tiles of every CTA loaded evict_last, the rest evict_first; < 0: all evict_first; 0: no hints */
   ohp_trace trace;          /* optional device-side timeline (OHP_TRACE_CG) */
 };
 

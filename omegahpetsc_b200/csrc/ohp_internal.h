@@ -154,6 +154,7 @@ struct ohp_mesh_s {
   /* "marker" label set point by point by the caller (DMSetLabelValue) instead of detected here */
   bool has_user_label;
   std::vector<int32_t> user_label;
+  struct ohp_pf_plan *pfplan;   /* tables of the one-launch pipelined CG (ohp_linalg.cu), built on first use */
   struct ohp_fused_plan *fused; /* tables of the fused persistent CG kernel, built on first use (ohp_cg_fused.cu) */
   uint8_t *ghost_cta; /* per persistent-SpMV CTA: 1 if its tiles reference ghost columns (NULL when serial) */
 };
@@ -171,6 +172,7 @@ struct ohp_mat_s {
    * (p[its & 1] is written from p[(its & 1) ^ 1]) so that a halo push never races its own update */
   double *r, *z, *p, *p1, *w, *dinv, *s;
   double *r1, *z1, *s1; /* second buffers of the single-reduction recurrence (r, u, s are double-buffered there) */
+  double *pm0, *pm1, *pw0, *pw1; /* pipelined recurrence: SpMV inputs m = M^-1 w (serial runs) and w, double-buffered */
   double *hist;
   int32_t hist_cap;
 };
@@ -202,6 +204,8 @@ ohp_trace ohp_cg_trace_open(ohp_context ctx);
 void ohp_cg_trace_dump(ohp_context ctx, const char *algo);
 int ohp_spmv_launch(ohp_mat A, const double *x, double *y);
 int ohp_extract_dinv(ohp_mat A);
+
+void ohp_pf_plan_free(ohp_context ctx, struct ohp_pf_plan *pl);
 
 /* ohp_cg_fused.cu */
 int ohp_cg_fused_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o, ohp_ksp_result *res, bool p2p);

@@ -78,8 +78,45 @@ __global__ void k_cg_fin(ohp_cg_state *st, const double *sums, int which, double
  * U[0] on the first pass, then the buffer the vector kernel of this iteration wrote, U[(its + 1) & 1] */
 __device__ __forceinline__ const double *cg_pick_input(const ohp_cg_state *st, const ohp_cgcg_epi &epi, const double *x0,
                                                        const double *x1) {
+  if (epi.pipe) return x0; /* pipelined recurrence: the host names the buffer (it knows the pass number) */
   if (epi.vpart) return (st->x_pending != 0 && ((st->its + 1) & 1)) ? x1 : x0;
   return (st->its & 1) ? x1 : x0;
+}
+
+/* Pipelined recurrence: run by ONE extra warp of CTA 0 of the SpMV n = A m, concurrently with the matrix stream.  Adds
+ * the partial sums (r,u), (w,u), (u,u) that the vector kernel's blocks left (fixed order), all-reduces them over the
+ * ranks' mailboxes and advances the scalar recurrences, so that neither the reduction nor the all-reduce nor rank skew
+ * of up to one SpMV duration is on the critical path of the iteration: the next vector kernel finds alpha, beta and
+ * `done` ready.  (epi.pipe == 2: a SpMV of the pipelined solver with nothing to reduce -- set-up and replacement passes.) */
+__device__ __forceinline__ void pipe_reduce(ohp_cg_state *st, int mode, const ohp_p2p_dev &pd, const ohp_cgcg_epi &epi, int lane) {
+  double t[3] = {0.0, 0.0, 0.0};
+  for (int b0 = 0; b0 < epi.nvpart; b0 += 32 * 8) { /* 24 loads in flight per lane, added in a fixed order */
+    double a[8][3];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int b = b0 + j * 32 + lane;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) a[j][k] = b < epi.nvpart ? __ldcg(epi.vpart + 3 * b + k) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) t[k] += a[j][k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) t[k] += __shfl_xor_sync(0xffffffffu, t[k], o);
+  }
+  const int its_now = st->its;
+  if (lane == 0) trace_put(epi.trace, TR_AR_POSTED, its_now);
+  if (mode == OHP_MODE_P2P) p2p_allreduce_warp<3>(pd, t, lane);
+  if (lane == 0) {
+    trace_put(epi.trace, TR_AR_DONE, its_now);
+    cgcg_scalars(st, epi.hist, epi.hist_cap, t[0], t[1], epi.jacobi ? t[2] : t[0]);
+    trace_put(epi.trace, TR_SPMV_END, its_now);
+  }
 }
 
 /* run by every thread of the LAST block of a CG SpMV (dot[0] = (x, A x) valid in thread 0) */
@@ -231,8 +268,78 @@ __device__ __forceinline__ double spmv_consume(const int32_t *__restrict__ rowpt
   return dot;
 }
 
+
+/* spmv_consume with the output step abstracted: emit(row, sum) is called exactly once per row, by one thread, with the
+ * row's sum taken in serial CSR order (same carry / lane-sharing rules as above).  Used by the fused pipelined-CG kernel,
+ * whose emit applies the whole vector update of the row while n = (A m)[row] is still in a register. */
+template <int S, int NC, class IDX, bool SPLIT, bool COHERENT, class Emit>
+__device__ __forceinline__ void spmv_consume_emit(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colidx,
+                                                  const double *__restrict__ vals, const double *x, const double *vals_s,
+                                                  const IDX *cols_s, const int32_t *rp_s, uint32_t full0, uint32_t empty0,
+                                                  int t0, int t1, Emit &emit) {
+  constexpr int T = kSpmvTile;
+  const int tid = threadIdx.x, lane = tid & 31;
+  double carry = 0.0;
+  int pend = -1;
+  for (int t = t0; t < t1; ++t) {
+    const int i = t - t0, s = i % S;
+    mbar_wait(full0 + 8 * s, (i / S) & 1);
+    const int32_t *rp = rp_s + s * kTmaRpStride;
+    const double *vs = vals_s + s * T;
+    const IDX *cs = cols_s + s * T;
+    const int rs = rp[kSpmvRowCap + 2], re = rp[kSpmvRowCap + 3];
+    const int base = t * T, lim = base + T;
+    if (pend >= 0) {
+      const int end = rp[0];
+      carry = row_dot<IDX, COHERENT>(vs, cs, 0, min(end, lim) - base, x, carry, pend);
+      if (end <= lim) { emit(pend, carry); pend = -1; }
+    }
+    if (!SPLIT) {
+      for (int r = rs + tid; r < re; r += NC) {
+        const int a = rp[r - rs], b = rp[r - rs + 1];
+        const double sum = row_dot<IDX, COHERENT>(vs, cs, a - base, min(b, lim) - base, x, 0.0, r);
+        if (b > lim) { carry = sum; pend = r; }
+        else emit(r, sum);
+      }
+    } else {
+      const int nrows = re - rs;
+      const int tpr = (nrows * 4 <= NC) ? 4 : (nrows * 2 <= NC) ? 2 : 1;
+      const int sub = tid & (tpr - 1), grp = tid / tpr, ngrp = NC / tpr;
+      for (int rb = rs; rb < re; rb += ngrp) {
+        const int r = rb + grp;
+        const bool valid = r < re;
+        int a = 0, b = 0;
+        if (valid) { a = rp[r - rs]; b = rp[r - rs + 1]; }
+        const int bl = min(b, lim);
+        int ca = a, cb = bl;
+        if (tpr > 1) {
+          if (b > lim) { if (sub != 0) cb = ca; }
+          else { const int chunk = (bl - a + tpr - 1) / tpr; ca = min(a + sub * chunk, bl); cb = min(ca + chunk, bl); }
+        }
+        double part = (valid && cb > ca) ? row_dot<IDX, COHERENT>(vs, cs, ca - base, cb - base, x, 0.0, r) : 0.0;
+        if (tpr > 1) part += __shfl_xor_sync(0xffffffffu, part, 1);
+        if (tpr > 2) part += __shfl_xor_sync(0xffffffffu, part, 2);
+        if (valid && sub == 0) {
+          if (b > lim) { carry = part; pend = r; }
+          else emit(r, part);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty0 + 8 * s);
+  }
+  if (pend >= 0) {
+    const int end = __ldg(rowptr + pend + 1);
+    for (int k = t1 * T; k < end; ++k) {
+      const int c = sizeof(IDX) == 2 ? pend + (int)colidx[k] : (int)colidx[k];
+      carry += vals[k] * (COHERENT ? ld_weak(x + c) : __ldg(x + c));
+    }
+    emit(pend, carry);
+  }
+}
+
 template <bool CG, int kTmaStages, int kTmaConsumers, class IDX, bool SPLIT, int MINB = 1>
-__global__ void __launch_bounds__(kTmaConsumers + 32, MINB)
+__global__ void __launch_bounds__(kTmaConsumers + 64, MINB)
 k_spmv_tma(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colidx, const double *__restrict__ vals, const double *x, double *__restrict__ y, const int32_t *__restrict__ tile_row, int n_tiles,
            ohp_cg_state *st, double *partials, unsigned *ticket, double *sums, int mode,
            const double *x_alt, const ohp_p2p_dev pd, const ohp_cgcg_epi epi) {
@@ -256,6 +363,7 @@ k_spmv_tma(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colidx, c
    * first stages BEFORE griddepcontrol.wait, i.e. while the predecessor kernel is still draining; only x, the
    * scalars and everything written below depend on the predecessor. */
   const bool is_producer = (warp == NC / 32);
+  const bool is_reducer = (warp == NC / 32 + 1); /* only launched (block size NC + 64) by the pipelined recurrence */
   int issued = 0;
   const uint64_t pol_last = l2_policy_evict_last(), pol_first = l2_policy_evict_first();
   auto issue_tile = [&](int t) {
@@ -263,7 +371,7 @@ k_spmv_tma(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colidx, c
     const int rs = __ldg(tile_row + t), re = __ldg(tile_row + t + 1);
     if (lane == 0) {
       mbar_expect_tx(full0 + 8 * s, T * (8 + (int)sizeof(IDX)));
-      if (epi.pin_tiles > 0) {
+      if (epi.pin_tiles != 0) { /* > 0: that many leading tiles evict_last; < 0: every tile evict_first */
         const uint64_t pol = (i < epi.pin_tiles) ? pol_last : pol_first;
         tma_load_1d_hint(smem_u32(vals_s + s * T), vals + (size_t)t * T, T * 8, full0 + 8 * s, pol);
         tma_load_1d_hint(smem_u32(cols_s + s * T), colidx + (size_t)t * T, T * (int)sizeof(IDX), full0 + 8 * s, pol);
@@ -287,6 +395,10 @@ k_spmv_tma(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colidx, c
   if (CG && st->done) {
     /* bulk copies already in flight must land before the CTA's shared memory is released */
     if (is_producer) for (int i = 0; i < issued; ++i) mbar_wait(full0 + 8 * (i % S), 0);
+    return;
+  }
+  if (is_reducer) {
+    if (CG && epi.pipe == 1 && blockIdx.x == 0) pipe_reduce(st, mode, pd, epi, lane);
     return;
   }
   const int its_now = CG ? st->its : 0;
@@ -319,7 +431,7 @@ k_spmv_tma(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colidx, c
     }
     if (CG && tid == 0) trace_put(epi.trace, TR_SPMV_CTA_DONE, its_now);
   }
-  if (CG) {
+  if (CG && !epi.pipe) {
     if (grid_sum<1>(dot, partials, ticket)) cg_spmv_epilogue(st, dot, sums, mode, pd, epi, its_now);
   }
 }
@@ -342,13 +454,20 @@ static int spmv_configure(ohp_mesh m) {
   return 0;
 }
 
-/* how many leading tiles of every CTA stay L2-resident (evict_last): OHP_L2PIN_MB megabytes of matrix stream in
- * total (default kL2PinDefaultMB; 0 switches the cache hints off) */
-constexpr double kL2PinDefaultMB = 0.0;
+/* L2 policy of the matrix stream.  The matrix is read exactly once per SpMV and is larger than what the L2 can keep next
+ * to the vectors, so by default EVERY tile is loaded with evict_first: the stream passes through without displacing the
+ * CG vectors, which are re-read within the iteration.  Measured at 1.05 M rows per GPU (the 8-GPU share of the 16 M-triangle
+ * box, working set ~ L2 size): 37.4 -> 32.6 us per iteration (two-launch single-reduction loop), 38.9 -> 33.0 (pipelined);
+ * at 2.1 M rows 67.2 -> 63.0.  Keeping a share of the tiles with evict_last instead (OHP_L2PIN_MB=<megabytes>) was never
+ * better than keeping none (16 MB: 32.8, 32 MB: 34.3, 48 MB: 35.4, 64 MB: 37.0 us): resident matrix lines cost more in
+ * evicted vector lines than they save.  OHP_L2PIN_MB=off loads without hints (A/B runs).
+ * Return value: number of leading tiles per CTA loaded evict_last, the rest evict_first; 0 = no hints. */
 static int spmv_pin_tiles(ohp_mesh m, int grid, int idx_bytes) {
   static const char *env = getenv("OHP_L2PIN_MB");
-  const double mb = env ? atof(env) : kL2PinDefaultMB;
-  if (!(mb > 0.0) || grid <= 0) return 0;
+  if (env && (env[0] == 'o' || env[0] == 'O')) return 0;
+  const double mb = env ? atof(env) : 0.0;
+  if (grid <= 0) return 0;
+  if (!(mb > 0.0)) return -1; /* all tiles evict_first */
   const double tile_bytes = (double)kSpmvTile * (8 + idx_bytes);
   const int64_t total = (int64_t)(mb * 1e6 / tile_bytes);
   const int per_cta = (int)std::min<int64_t>(total / grid, (int64_t)(m->n_tiles + grid - 1) / grid);
@@ -373,7 +492,7 @@ static int spmv_tma_launch_ts(ohp_mat A, const IDX *cols, const double *x, doubl
   epi.pin_tiles = spmv_pin_tiles(m, grid, (int)sizeof(IDX));
   if (st) {
     static const char *nopdl = getenv("OHP_NOPDL");
-    OHP_CUDA(ohp_launch(k_spmv_tma<true, S, NC, IDX, SPLIT, MINB>, dim3(grid), dim3(NC + 32), (size_t)smem, ctx->stream, mode != OHP_MODE_NCCL && !nopdl,
+    OHP_CUDA(ohp_launch(k_spmv_tma<true, S, NC, IDX, SPLIT, MINB>, dim3(grid), dim3(NC + (epi.pipe ? 64 : 32)), (size_t)smem, ctx->stream, mode != OHP_MODE_NCCL && !nopdl,
                         m->rowptr, cols, A->vals, x, y, m->tile_row, m->n_tiles, st, ctx->d_partials, ctx->d_ticket + 1, sums, mode, x_alt, pd, epi));
   }
   else k_spmv_tma<false, S, NC, IDX, SPLIT, MINB><<<grid, NC + 32, smem, ctx->stream>>>(
@@ -404,7 +523,8 @@ static int spmv_enqueue(ohp_mat A, const double *x, double *y, ohp_cg_state *st,
   ohp_mesh m = A->mesh;
   ohp_context ctx = m->ctx;
   static const char *force = getenv("OHP_SPMV"); /* "stream" forces the fallback kernel; "0".."5" pick a TMA config (A/B runs) */
-  const bool tma = spmv_use_tma(m) && !(force && force[0] == 's');
+  /* a rank that owns no rows still runs the pipelined solver's reducer warp, which lives in the TMA kernel's CTA 0 */
+  const bool tma = (spmv_use_tma(m) || (epi.pipe && m->n_tiles == 0)) && !(force && force[0] == 's');
   if (tma) {
     const int cfg = (force && force[0] >= '0' && force[0] <= '9') ? force[0] - '0' : 0;
     switch (cfg) {
@@ -567,7 +687,7 @@ extern "C" int ohp_mat_destroy(ohp_mat A) {
   if (!A) return 0;
   cudaSetDevice(A->mesh->ctx->device);
   cudaStreamSynchronize(A->mesh->ctx->stream);
-  OHP_FREE(A->mesh->ctx, A->vals); OHP_FREE(A->mesh->ctx, A->r); OHP_FREE(A->mesh->ctx, A->z); OHP_FREE(A->mesh->ctx, A->p); OHP_FREE(A->mesh->ctx, A->p1); OHP_FREE(A->mesh->ctx, A->s); OHP_FREE(A->mesh->ctx, A->r1); OHP_FREE(A->mesh->ctx, A->z1); OHP_FREE(A->mesh->ctx, A->s1); OHP_FREE(A->mesh->ctx, A->w); OHP_FREE(A->mesh->ctx, A->dinv); OHP_FREE(A->mesh->ctx, A->hist);
+  OHP_FREE(A->mesh->ctx, A->vals); OHP_FREE(A->mesh->ctx, A->r); OHP_FREE(A->mesh->ctx, A->z); OHP_FREE(A->mesh->ctx, A->p); OHP_FREE(A->mesh->ctx, A->p1); OHP_FREE(A->mesh->ctx, A->s); OHP_FREE(A->mesh->ctx, A->r1); OHP_FREE(A->mesh->ctx, A->z1); OHP_FREE(A->mesh->ctx, A->s1); OHP_FREE(A->mesh->ctx, A->pm0); OHP_FREE(A->mesh->ctx, A->pm1); OHP_FREE(A->mesh->ctx, A->pw0); OHP_FREE(A->mesh->ctx, A->pw1); OHP_FREE(A->mesh->ctx, A->w); OHP_FREE(A->mesh->ctx, A->dinv); OHP_FREE(A->mesh->ctx, A->hist);
   delete A;
   return 0;
 }
@@ -826,7 +946,7 @@ int ohp_extract_dinv(ohp_mat A) {
 
 extern "C" int ohp_ksp_default_options(ohp_ksp_options *o) {
   o->rtol = 1e-5; o->abstol = 1e-50; o->dtol = 1e5; o->max_it = 10000; o->pc = OHP_PC_NONE;
-  o->check_every = 0; o->history_cap = 0; o->history = nullptr; o->profile = 0;
+  o->check_every = 0; o->history_cap = 0; o->history = nullptr; o->profile = 0; o->ksp_type = OHP_KSP_CG;
   return 0;
 }
 
@@ -994,6 +1114,889 @@ static int cgcg_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o,
   return 0;
 }
 
+
+/* ------------------------------------------------------------------------------------ */
+/* Pipelined CG (Ghysels & Vanroose; PETSc's -ksp_type pipecg) as two launches per iteration: */
+/*   k_spmv_*      : n = A m  (m = M^-1 w); an extra warp of its CTA 0 meanwhile reduces the     */
+/*                   previous vector kernel's partial sums, all-reduces them and advances       */
+/*                   alpha / beta / norm / its (pipe_reduce)                                    */
+/*   k_pipecg_vec  : z = n + beta z; s = w + beta s; p = u + beta p; x += alpha p; r -= alpha s; */
+/*                   w -= alpha z; u = M^-1 r; m = M^-1 w; partial (r,u), (w,u), (u,u) per block; */
+/*                   halo blocks push the new m to the neighbours                               */
+/* Same iterates as CG in exact arithmetic, same scalar formulas as the single-reduction         */
+/* recurrence (cgcg_scalars), same convergence test (KSPConvergedDefault on ||u||).  What it     */
+/* buys in the strong-scaling regime: the dot products of iteration i are not needed before the  */
+/* vector kernel of iteration i+1, so the grid-wide reduction, the 8-rank all-reduce and up to   */
+/* one SpMV duration of rank skew overlap the matrix stream instead of sitting between the two   */
+/* kernels (device timeline of the two-launch single-reduction loop at 1 M rows: 16 of 43 us).   */
+/* Price: 104 instead of 88 bytes of vector traffic per row and two extra SpMVs per solve.       */
+/*                                                                                               */
+/* Attainable accuracy.  The recurrences for w = A u, s = A p, z = A q drift from the products    */
+/* they stand for, and r from b - A x (measured: on the 2048^2 box the TRUE residual stalled at   */
+/* 2.8e-8 |b| after 5454 iterations although the recurred norm met rtol = 1e-9).  So every         */
+/* kPipeReplaceEvery iterations one pass RECOMPUTES them (the residual-replacement form of         */
+/* Cools & Vanroose): p = u + beta p and x += alpha p as usual, then s = A p, z = A M^-1 s,         */
+/* r = b - A x, w = A M^-1 r with four extra SpMVs -- 2 % more SpMVs at a period of 200, after       */
+/* which iteration counts and true residuals match classic CG (tests/, bench check object).       */
+/*                                                                                               */
+/* The host knows the pass number L (the device only knows `done`), so each launch is told what    */
+/* to do: kind 0 sets up r = b, u, m = u; kind 1 takes w = A u from the SpMV output; kind 2 is a    */
+/* regular iteration.  m is double-buffered: every halo push alternates between the two exported   */
+/* buffers and every pass makes an odd number of pushes (1, or 5 in a replacement pass), so pass L  */
+/* leaves m in buffer L & 1; w (== m without a preconditioner) and z follow the same parity, which  */
+/* lets the halo blocks recompute what they push from buffers nobody writes during the kernel.    */
+/* A push into a buffer is safe because the neighbour's SpMV that last read it completed before the */
+/* neighbour's previous push, which this rank's previous SpMV has waited for.                      */
+/* ------------------------------------------------------------------------------------ */
+constexpr int kPipeReplaceEvery = 200;
+enum { PK_INIT = 0, PK_TAKE_W = 1, PK_ITER = 2, PK_PX = 3, PK_STAGE_S = 4, PK_STAGE_X = 5, PK_NEW_R = 6, PK_STAGE_P = 7 };
+struct ohp_pipe_vecs {
+  double *M0, *M1;   /* SpMV input m = M^-1 w (the NVLink-exported buffers on a partitioned run) */
+  double *W0, *W1;   /* w (== M when there is no preconditioner) */
+  double *Z0, *Z1;
+  double *r, *s, *p, *x;
+  const double *nb, *b, *dinv;
+};
+
+/* the value pass `kind` stages into the SpMV input buffer for dof l: computed from arrays that no block writes in that
+ * pass, so the halo blocks and the row blocks get bitwise the same number */
+template <bool JACOBI>
+__device__ __forceinline__ double pipe_staged(const ohp_pipe_vecs &v, int kind, int l, double alpha, double beta,
+                                              const double *wo, const double *zo) {
+  double t;
+  switch (kind) {
+    case PK_INIT: t = v.b[l]; break;
+    case PK_TAKE_W: t = v.nb[l]; break;
+    case PK_ITER: { const double zi = fma(beta, zo[l], v.nb[l]); t = fma(-alpha, zi, wo[l]); break; }
+    case PK_STAGE_S: t = v.s[l]; break;
+    case PK_STAGE_X: return v.x[l];
+    case PK_NEW_R: t = v.b[l] - v.nb[l]; break;
+    default: return v.p[l]; /* PK_STAGE_P */
+  }
+  return JACOBI ? v.dinv[l] * t : t;
+}
+
+template <int MODE, bool JACOBI>
+__global__ void __launch_bounds__(256)
+k_pipecg_vec(const ohp_pipe_vecs v, int n, const ohp_cg_state *st, double *vpart, const ohp_p2p_dev pd, int n_halo_blocks,
+             unsigned *halo_ticket, int wait_here, const ohp_trace trace, int kind, int cur) {
+  pdl_wait();
+  pdl_launch();
+  if (st->done) return;
+  if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) trace_put(trace, TR_VEC_BEGIN, st->its);
+  const double alpha = st->alpha, beta = st->beta;
+  const double *__restrict__ nb = v.nb;
+  const double *wo = cur ? v.W0 : v.W1, *zo = cur ? v.Z0 : v.Z1;
+  double *wn = cur ? v.W1 : v.W0, *zn = cur ? v.Z1 : v.Z0, *mn = cur ? v.M1 : v.M0;
+  int blk = blockIdx.x, nblocks = gridDim.x;
+  if (MODE == OHP_MODE_P2P) {
+    if (blk < n_halo_blocks) {
+      if (kind == PK_PX) return; /* p and x are updated in place: staged by the next launch (PK_STAGE_P) */
+      const int nsend = pd.soff[pd.n_nbr];
+      for (int i = blk * blockDim.x + threadIdx.x; i < nsend; i += n_halo_blocks * blockDim.x) {
+        const int l = pd.send_ldof[i];
+        const double val = pipe_staged<JACOBI>(v, kind, l, alpha, beta, wo, zo);
+        int q = 0;
+        while (i >= pd.soff[q + 1]) ++q;
+        pd.p[cur][pd.nbr[q]][pd.dst_off[q] + (i - pd.soff[q])] = val;
+      }
+      __threadfence_system();
+      __syncthreads();
+      __shared__ unsigned long long s_seq;
+      __shared__ bool s_last;
+      if (threadIdx.x == 0) {
+        s_last = (atomicInc(halo_ticket, n_halo_blocks - 1) == (unsigned)(n_halo_blocks - 1));
+        if (s_last) { __threadfence(); s_seq = pd.seq[1] + 1; pd.seq[1] = s_seq; }
+      }
+      __syncthreads();
+      if (s_last && threadIdx.x < pd.n_nbr) {
+        const int q = pd.nbr[threadIdx.x];
+        st_release_sys(pd.hflags[q] + pd.rank, s_seq);
+        if (wait_here) p2p_wait(pd.hflags[pd.rank] + q, s_seq, pd.seq + 2, pd.timeout_ns);
+      }
+      if (s_last && threadIdx.x == 0) trace_put(trace, TR_VEC_HALO_PUSHED, st->its);
+      return;
+    }
+    blk -= n_halo_blocks; nblocks -= n_halo_blocks;
+  }
+  double sums[3] = {0.0, 0.0, 0.0};
+  const int i0 = blk * blockDim.x + threadIdx.x, stride = nblocks * blockDim.x;
+  switch (kind) {
+    case PK_INIT: /* r = b, u = M^-1 r, m = u (first SpMV: w0 = A u0); x = p = s = z = 0 */
+      for (int i = i0; i < n; i += stride) {
+        v.r[i] = v.b[i]; v.x[i] = 0.0; v.p[i] = 0.0; v.s[i] = 0.0; v.Z0[i] = 0.0; v.Z1[i] = 0.0;
+        mn[i] = pipe_staged<JACOBI>(v, kind, i, alpha, beta, wo, zo);
+      }
+      return;
+    case PK_TAKE_W: /* w = A u is in the SpMV output: (r,u), (w,u), (u,u); m = M^-1 w */
+      for (int i = i0; i < n; i += stride) {
+        const double wi = nb[i], ri = v.r[i];
+        const double ui = JACOBI ? v.dinv[i] * ri : ri;
+        wn[i] = wi;
+        if (JACOBI) mn[i] = v.dinv[i] * wi;
+        sums[0] += ri * ui; sums[1] += wi * ui; sums[2] += ui * ui;
+      }
+      break;
+    case PK_ITER:
+      for (int i = i0; i < n; i += stride) {
+        const double ro = v.r[i], woi = wo[i];
+        const double ui = JACOBI ? v.dinv[i] * ro : ro;
+        const double zi = fma(beta, zo[i], nb[i]);
+        const double si = fma(beta, v.s[i], woi);
+        const double pi = fma(beta, v.p[i], ui);
+        zn[i] = zi; v.s[i] = si; v.p[i] = pi;
+        v.x[i] = fma(alpha, pi, v.x[i]);
+        const double ri = fma(-alpha, si, ro);
+        const double wi = fma(-alpha, zi, woi);
+        v.r[i] = ri; wn[i] = wi;
+        const double un = JACOBI ? v.dinv[i] * ri : ri;
+        if (JACOBI) mn[i] = v.dinv[i] * wi;
+        sums[0] += ri * un; sums[1] += wi * un; sums[2] += un * un;
+      }
+      break;
+    case PK_PX: /* replacement pass, first launch: p = u + beta p; x += alpha p */
+      for (int i = i0; i < n; i += stride) {
+        const double ro = v.r[i];
+        const double pi = fma(beta, v.p[i], JACOBI ? v.dinv[i] * ro : ro);
+        v.p[i] = pi;
+        v.x[i] = fma(alpha, pi, v.x[i]);
+      }
+      return;
+    case PK_NEW_R: /* r = b - A x (A x is in the SpMV output); m = u = M^-1 r */
+      for (int i = i0; i < n; i += stride) {
+        v.r[i] = v.b[i] - nb[i];
+        mn[i] = pipe_staged<JACOBI>(v, kind, i, alpha, beta, wo, zo);
+      }
+      return;
+    default: /* PK_STAGE_S / _X / _P: copy into the SpMV input buffer */
+      for (int i = i0; i < n; i += stride) mn[i] = pipe_staged<JACOBI>(v, kind, i, alpha, beta, wo, zo);
+      return;
+  }
+  __shared__ double s_red3[3 * 32];
+  block_sum<3>(sums, s_red3);
+  if (threadIdx.x == 0) {
+    vpart[3 * blk] = sums[0]; vpart[3 * blk + 1] = sums[1]; vpart[3 * blk + 2] = sums[2];
+    if (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1 || blockIdx.x == gridDim.x / 2) trace_put(trace, TR_VEC_END, st->its);
+  }
+}
+
+static int pipecg_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o, ohp_ksp_result *res, bool p2p) {
+  ohp_mesh m = A->mesh;
+  ohp_context ctx = m->ctx;
+  cudaStream_t st = ctx->stream;
+  const int n = m->n_owned;
+  const size_t len = (size_t)std::max(1, n + m->n_ghost);
+  const bool jac = (o->pc == OHP_PC_JACOBI);
+  if (!(spmv_use_tma(m) || m->n_tiles == 0) || getenv("OHP_SPMV")) OHP_FAIL(OHP_ERR_SUP, "ohp_ksp_cg (pipelined): needs the TMA-pipelined SpMV (its CTA 0 carries the reducer warp)");
+  auto need = [&](double **ptr) -> int {
+    if (!*ptr) { OHP_CUDA(OHP_MALLOC(ctx, ptr, sizeof(double) * len)); OHP_CUDA(cudaMemsetAsync(*ptr, 0, sizeof(double) * len, st)); }
+    return 0;
+  };
+  OHP_TRY(need(&A->p)); OHP_TRY(need(&A->w)); OHP_TRY(need(&A->s)); OHP_TRY(need(&A->r)); OHP_TRY(need(&A->z)); OHP_TRY(need(&A->z1));
+  static const ohp_p2p_dev no_p2p = {};
+  const ohp_p2p_dev &pd = p2p ? m->p2p->dev : no_p2p;
+  ohp_pipe_vecs v;
+  memset(&v, 0, sizeof(v));
+  if (p2p) { v.M0 = pd.p[0][ctx->rank]; v.M1 = pd.p[1][ctx->rank]; }
+  else { OHP_TRY(need(&A->pm0)); OHP_TRY(need(&A->pm1)); v.M0 = A->pm0; v.M1 = A->pm1; }
+  if (jac) {
+    OHP_TRY(need(&A->pw0)); OHP_TRY(need(&A->pw1)); OHP_TRY(need(&A->dinv));
+    v.W0 = A->pw0; v.W1 = A->pw1;
+    OHP_TRY(ohp_extract_dinv(A));
+  } else { v.W0 = v.M0; v.W1 = v.M1; }
+  v.Z0 = A->z; v.Z1 = A->z1;
+  v.r = A->r; v.s = A->s; v.p = A->p; v.x = x->d; v.nb = A->w; v.b = b->d; v.dinv = A->dinv;
+  double *hist = nullptr;
+  int hist_cap = 0;
+  if (o->history && o->history_cap > 0) {
+    if (A->hist_cap < o->history_cap) {
+      OHP_FREE(ctx, A->hist);
+      OHP_CUDA(OHP_MALLOC(ctx, &A->hist, sizeof(double) * o->history_cap));
+      A->hist_cap = o->history_cap;
+    }
+    hist = A->hist; hist_cap = o->history_cap;
+    OHP_CUDA(cudaMemsetAsync(hist, 0, sizeof(double) * hist_cap, st));
+  }
+  ohp_cg_state init;
+  memset(&init, 0, sizeof(init));
+  init.rtol = o->rtol; init.abstol = o->abstol; init.dtol = o->dtol; init.maxit = o->max_it;
+  *ctx->h_cg = init;
+  OHP_CUDA(cudaMemcpyAsync(ctx->d_cg, ctx->h_cg, sizeof(init), cudaMemcpyHostToDevice, st));
+  const int mode = p2p ? OHP_MODE_P2P : OHP_MODE_SERIAL;
+  /* one resident wave: 48 registers x 256 threads -> 5 blocks per SM (a second wave only adds a tail) */
+  static const char *vps_env = getenv("OHP_VGRID_PER_SM");
+  const int vps = vps_env ? std::max(1, atoi(vps_env)) : 5;
+  const int vgrid = (int)std::min<int64_t>(std::min<int64_t>(nblk(n, 256), (int64_t)ctx->num_sms * vps), kMaxPartials / 3);
+  const int nhalo = p2p ? std::max(1, std::min(16, (pd.soff[pd.n_nbr] + 255) / 256)) : 0;
+  double *vpart = ctx->d_partials + kMaxPartials; /* second half of the scratch */
+  ohp_cgcg_epi epi;
+  memset(&epi, 0, sizeof(epi));
+  epi.vpart = vpart; epi.nvpart = vgrid; epi.jacobi = jac ? 1 : 0; epi.hist = hist; epi.hist_cap = hist_cap;
+  epi.trace = ohp_cg_trace_open(ctx);
+  if (p2p) OHP_TRY(ohp_p2p_entry_barrier(m));
+  static const char *nooverlap = getenv("OHP_NOOVERLAP");
+  const bool overlap = p2p && m->ghost_cta && !nooverlap;
+  const int wait_in_vec = overlap ? 0 : 1;
+  epi.ghost_cta = overlap ? m->ghost_cta : nullptr;
+  static const char *nopdl = getenv("OHP_NOPDL");
+  const bool pdl = !nopdl;
+  static const char *rr_env = getenv("OHP_PIPE_RR"); /* replacement period (A/B runs); 0 = never */
+  const int rr = rr_env ? atoi(rr_env) : kPipeReplaceEvery;
+  const int check_every = o->check_every > 0 ? o->check_every : 50;
+  EventBag bag, profbag;
+  cudaEvent_t ev0, ev1;
+  OHP_CUDA(bag.record(st, &ev0));
+  std::vector<cudaEvent_t> &prof = profbag.ev;
+  const int nprof = std::max(0, o->profile);
+  int pushes = 0; /* halo pushes so far: the next one goes to buffer pushes & 1 */
+  auto vec = [&](int kind, int cur) -> int {
+    if (p2p) {
+      if (jac) OHP_CUDA(ohp_launch(k_pipecg_vec<OHP_MODE_P2P, true>, dim3(vgrid + nhalo), dim3(256), 0, st, pdl, v, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, nhalo, ctx->d_ticket + 2, wait_in_vec, epi.trace, kind, cur));
+      else OHP_CUDA(ohp_launch(k_pipecg_vec<OHP_MODE_P2P, false>, dim3(vgrid + nhalo), dim3(256), 0, st, pdl, v, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, nhalo, ctx->d_ticket + 2, wait_in_vec, epi.trace, kind, cur));
+    } else {
+      if (jac) OHP_CUDA(ohp_launch(k_pipecg_vec<OHP_MODE_SERIAL, true>, dim3(vgrid), dim3(256), 0, st, pdl, v, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, 0, (unsigned *)nullptr, 1, epi.trace, kind, cur));
+      else OHP_CUDA(ohp_launch(k_pipecg_vec<OHP_MODE_SERIAL, false>, dim3(vgrid), dim3(256), 0, st, pdl, v, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, 0, (unsigned *)nullptr, 1, epi.trace, kind, cur));
+    }
+    ctx->launches++;
+    return 0;
+  };
+  /* stage-and-push launch followed by the SpMV of the staged buffer into `out`; reduce = CTA 0's extra warp closes the pass */
+  auto stage_mult = [&](int kind, double *out, bool reduce, bool timed) -> int {
+    const int cur = pushes & 1;
+    OHP_TRY(vec(kind, cur));
+    pushes++;
+    ohp_cgcg_epi e = epi;
+    e.pipe = reduce ? 1 : 2;
+    if (timed) OHP_CUDA(profbag.record(st));
+    OHP_TRY(spmv_enqueue(A, cur ? v.M1 : v.M0, out, ctx->d_cg, ctx->d_scalars, mode, nullptr, pd, e));
+    if (timed) OHP_CUDA(profbag.record(st));
+    return 0;
+  };
+  int pass = 0; /* == the device's pass count while it is not done */
+  for (;;) {
+    for (int it = 0; it < check_every; ++it, ++pass) {
+      const bool timed = (int)prof.size() < 2 * nprof && (pass >= check_every || o->max_it <= check_every);
+      if (pass == 0) OHP_TRY(stage_mult(PK_INIT, A->w, false, false));
+      else if (pass == 1) OHP_TRY(stage_mult(PK_TAKE_W, A->w, true, false));
+      else if (rr > 0 && (pass - 2) > 0 && (pass - 2) % rr == 0) {
+        /* residual replacement in place of iteration pass - 2's recurrences */
+        double *znew = (pass & 1) ? v.Z1 : v.Z0;
+        OHP_TRY(vec(PK_PX, pushes & 1));
+        OHP_TRY(stage_mult(PK_STAGE_P, A->s, false, false));   /* s = A p */
+        OHP_TRY(stage_mult(PK_STAGE_S, znew, false, false));   /* z = A M^-1 s */
+        OHP_TRY(stage_mult(PK_STAGE_X, A->w, false, false));   /* A x */
+        OHP_TRY(stage_mult(PK_NEW_R, A->w, false, false));     /* r = b - A x; w = A M^-1 r (into the SpMV output) */
+        OHP_TRY(stage_mult(PK_TAKE_W, A->w, true, false));     /* w, dot products, m = M^-1 w; n = A m */
+      } else OHP_TRY(stage_mult(PK_ITER, A->w, true, timed));
+    }
+    OHP_CUDA(cudaMemcpyAsync(ctx->h_cg, ctx->d_cg, sizeof(ohp_cg_state), cudaMemcpyDeviceToHost, st));
+    OHP_CUDA(cudaStreamSynchronize(st));
+    if (ctx->h_cg->done) break;
+    if (pass > o->max_it + 3 * check_every) OHP_FAIL(OHP_ERR_LIB, "ohp_ksp_cg (pipelined): iteration control did not terminate");
+  }
+  OHP_CUDA(bag.record(st, &ev1));
+  OHP_CUDA(cudaEventSynchronize(ev1));
+  res->total_ms = 0.f;
+  cudaEventElapsedTime(&res->total_ms, ev0, ev1);
+  res->its = ctx->h_cg->its; res->reason = ctx->h_cg->reason; res->rnorm = ctx->h_cg->dp; res->rnorm0 = ctx->h_cg->rnorm0;
+  res->spmv_ms = 0.f; res->spmv_samples = 0;
+  ohp_cg_trace_dump(ctx, "pipecg");
+  {
+    /* the timed launches are the regular passes from `check_every` on: pass L works while L - 2 < its */
+    double acc = 0.0;
+    int used = 0, L = (o->max_it <= check_every) ? 2 : check_every;
+    for (size_t i = 0; i + 1 < prof.size(); i += 2, ++L) {
+      while (rr > 0 && L > 2 && (L - 2) % rr == 0) ++L; /* replacement passes were not timed */
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, prof[i], prof[i + 1]);
+      if (L - 2 < res->its) { acc += ms; used++; }
+    }
+    if (used) { res->spmv_ms = (float)(acc / used); res->spmv_samples = used; }
+  }
+  if (p2p) OHP_TRY(ohp_p2p_check(m, "ohp_ksp_cg (pipelined)"));
+  if (hist) {
+    const int ncopy = std::min(hist_cap, res->its + 1);
+    OHP_CUDA(cudaMemcpyAsync(o->history, hist, sizeof(double) * ncopy, cudaMemcpyDeviceToHost, st));
+    OHP_CUDA(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+
+/* ------------------------------------------------------------------------------------ */
+/* Pipelined CG, ONE launch per iteration (k_pipecg_fused): the vector update is applied   */
+/* row by row inside the SpMV's consumer loop, while n = (A m)[row] is still in a register. */
+/*   per row:  z = n + beta z;  s = w + beta s;  p = u + beta p;  x += alpha p;            */
+/*             r -= alpha s;  w' = w - alpha z;  m' = M^-1 w'   (w' into the OTHER m buffer)  */
+/* Every update is row-local once n is known, and n only needs the PREVIOUS iteration's m,  */
+/* so the kernel boundary is the only grid-wide synchronisation: no vector kernel, no n in  */
+/* memory (16 B/row less than the two-launch form: 96 B/row of vector traffic), one kernel   */
+/* boundary per iteration instead of two.                                                  */
+/* Scalars.  Each CTA leaves its partial (r,u), (w,u), (u,u) in parts[parity][cta]; at the    */
+/* start of the NEXT launch warp 0 of every CTA adds the G partials in a fixed order (the     */
+/* boundary made them visible: no ticket, no last block on one GPU), adds the other ranks'   */
+/* totals from its local mailboxes in rank order, and runs the scalar recurrences on the      */
+/* CTA's OWN replica of the solver state -- all replicas on all ranks stay bit-identical, CTA  */
+/* 0 mirrors its replica for the host.  Across ranks the total is posted by the last CTA of    */
+/* the rank to finish (ticket) straight into the peers' mailboxes; the poll overlaps the next  */
+/* launch's prologue and TMA prefetch.                                                       */
+/* Halo.  The CTAs that own rows some neighbour ghosts store w' for those rows into the        */
+/* neighbours' vectors when their tiles are done; the last of them (and of the CTAs that read   */
+/* ghost columns: a neighbour must not overwrite a tail somebody here still reads) publishes    */
+/* the flags.                                                                                 */
+/* Set-up passes, the scalar step of a replacement pass and the replacement passes themselves   */
+/* reuse the two-launch pieces above (k_pipecg_vec kinds + plain SpMVs).                        */
+/* ------------------------------------------------------------------------------------ */
+struct ohp_pf_plan {
+  int G = 0, n_contrib = 1;
+  int32_t *hptr = nullptr, *hidx = nullptr; /* CSR over CTAs of the send-list entries whose row the CTA owns */
+  uint8_t *contrib = nullptr;               /* per CTA: takes part in the halo arrival count */
+  ohp_cg_state *rep = nullptr;              /* G replicas of the solver state */
+  double *parts = nullptr;                  /* 2 parities x G x 3 */
+  unsigned *cnt = nullptr;                  /* [0] halo arrivals, [1] rank-total ticket */
+};
+void ohp_pf_plan_free(ohp_context ctx, ohp_pf_plan *pl) {
+  if (!pl) return;
+  OHP_FREE(ctx, pl->hptr); OHP_FREE(ctx, pl->hidx); OHP_FREE(ctx, pl->contrib); OHP_FREE(ctx, pl->rep); OHP_FREE(ctx, pl->parts); OHP_FREE(ctx, pl->cnt);
+  delete pl;
+}
+struct ohp_pf_dev {
+  int G, n_contrib, rpar; /* rpar: parity of the partials this launch READS (it writes the other one) */
+  const int32_t *hptr, *hidx;
+  const uint8_t *contrib, *ghost_cta;
+  ohp_cg_state *rep, *st_host;
+  double *parts;
+  unsigned *cnt;
+  double *hist;
+  int hist_cap, jacobi;
+  ohp_trace trace;
+};
+
+/* G partial triples -> their sum in lane 0..31 (every lane): lane-strided loads, in-lane adds in ascending order, fixed
+ * butterfly.  Used by every consumer of the partials so that all of them get bitwise the same totals. */
+__device__ __forceinline__ void pf_sum_parts(const double *parts, int G, int lane, double (&t)[3]) {
+  t[0] = t[1] = t[2] = 0.0;
+  for (int b0 = 0; b0 < G; b0 += 32 * 8) {
+    double a[8][3];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int b = b0 + j * 32 + lane;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) a[j][k] = b < G ? __ldcg(parts + 3 * b + k) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) t[k] += a[j][k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) t[k] += __shfl_xor_sync(0xffffffffu, t[k], o);
+  }
+}
+/* this rank's total -> the peers' mailboxes (one warp; t valid in every lane) */
+__device__ __forceinline__ void pf_post_total(const ohp_p2p_dev &pd, const double (&t)[3], int lane) {
+  unsigned long long seq = 0;
+  if (lane == 0) { seq = pd.seq[0] + 1; pd.seq[0] = seq; }
+  seq = __shfl_sync(0xffffffffu, seq, 0);
+  if (lane < pd.nranks && lane != pd.rank) {
+    ohp_ar_slot *s = pd.slots[lane] + (int)(seq & 1ull) * kMaxRanks + pd.rank;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) s->v[k] = t[k];
+    st_release_sys(&s->seq, seq);
+  }
+}
+/* own total + the peers' posted totals, added in rank order (one warp; result in every lane) */
+__device__ __forceinline__ void pf_gather_totals(const ohp_p2p_dev &pd, double (&t)[3], int lane) {
+  const unsigned long long seq = pd.seq[0]; /* bumped by the poster of the previous launch */
+  double got[3] = {t[0], t[1], t[2]};
+  if (lane < pd.nranks && lane != pd.rank) {
+    const ohp_ar_slot *r = pd.slots[pd.rank] + (int)(seq & 1ull) * kMaxRanks + lane;
+    p2p_wait(&r->seq, seq, pd.seq + 2, pd.timeout_ns);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) got[k] = r->v[k];
+  }
+  double tot[3] = {0.0, 0.0, 0.0};
+  for (int q = 0; q < pd.nranks; ++q) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) tot[k] += __shfl_sync(0xffffffffu, got[k], q);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) t[k] = tot[k];
+}
+
+/* the per-row update, called by the consumer loop with n = (A m)[row] */
+template <bool JACOBI>
+struct PipeRowUpdate {
+  const double *wo;
+  double *wn, *mn, *z, *s, *p, *r, *x;
+  const double *dinv;
+  double alpha, beta;
+  double g, d, nn;
+  __device__ __forceinline__ void operator()(int i, double n) {
+    const double ro = r[i], woi = wo[i];
+    const double ui = JACOBI ? dinv[i] * ro : ro;
+    const double zi = fma(beta, z[i], n);
+    const double si = fma(beta, s[i], woi);
+    const double pi = fma(beta, p[i], ui);
+    z[i] = zi; s[i] = si; p[i] = pi;
+    x[i] = fma(alpha, pi, x[i]);
+    const double ri = fma(-alpha, si, ro);
+    const double wi = fma(-alpha, zi, woi);
+    r[i] = ri; wn[i] = wi;
+    const double un = JACOBI ? dinv[i] * ri : ri;
+    if (JACOBI) mn[i] = dinv[i] * wi;
+    g += ri * un; d += wi * un; nn += un * un;
+  }
+};
+
+template <int S, int NC, class IDX, bool SPLIT, bool JACOBI, int MODE>
+__global__ void __launch_bounds__(NC + 32, 1)
+k_pipecg_fused(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colidx, const double *__restrict__ vals,
+               const int32_t *__restrict__ tile_row, int n_tiles, const ohp_pipe_vecs v, const ohp_pf_dev f,
+               const ohp_p2p_dev pd, int cur, int pin_tiles) {
+  constexpr int T = kSpmvTile;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *vals_s = reinterpret_cast<double *>(smem_raw);
+  IDX *cols_s = reinterpret_cast<IDX *>(vals_s + S * T);
+  int32_t *rp_s = reinterpret_cast<int32_t *>(cols_s + S * T);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(rp_s + S * kTmaRpStride);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
+  __shared__ double s_scal[2];
+  __shared__ int s_flag[2];          /* [0] done, [1] this CTA took the last rank-total ticket */
+  __shared__ double s_red[3 * 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int t0 = (int)(((int64_t)n_tiles * blockIdx.x) / gridDim.x);
+  const int t1 = (int)(((int64_t)n_tiles * (blockIdx.x + 1)) / gridDim.x);
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 33); mbar_init(empty0 + 8 * s, NC / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const bool is_producer = (warp == NC / 32);
+  int issued = 0;
+  const uint64_t pol_last = l2_policy_evict_last(), pol_first = l2_policy_evict_first();
+  auto issue_tile = [&](int t) {
+    const int i = t - t0, s = i % S;
+    const int rs = __ldg(tile_row + t), re = __ldg(tile_row + t + 1);
+    if (lane == 0) {
+      mbar_expect_tx(full0 + 8 * s, T * (8 + (int)sizeof(IDX)));
+      if (pin_tiles != 0) {
+        const uint64_t pol = (i < pin_tiles) ? pol_last : pol_first;
+        tma_load_1d_hint(smem_u32(vals_s + s * T), vals + (size_t)t * T, T * 8, full0 + 8 * s, pol);
+        tma_load_1d_hint(smem_u32(cols_s + s * T), colidx + (size_t)t * T, T * (int)sizeof(IDX), full0 + 8 * s, pol);
+      } else {
+        tma_load_1d(smem_u32(vals_s + s * T), vals + (size_t)t * T, T * 8, full0 + 8 * s);
+        tma_load_1d(smem_u32(cols_s + s * T), colidx + (size_t)t * T, T * (int)sizeof(IDX), full0 + 8 * s);
+      }
+    }
+    int32_t *rp = rp_s + s * kTmaRpStride;
+    for (int j = lane; j <= re - rs; j += 32) cp_async4(smem_u32(rp + j), rowptr + rs + j);
+    if (lane < 2) cp_async4(smem_u32(rp + kSpmvRowCap + 2 + lane), tile_row + t + lane);
+    cp_async_mbar_arrive_noinc(full0 + 8 * s);
+  };
+  /* the matrix is constant: stream the first stages while the previous launch is still draining */
+  if (is_producer) {
+    for (; issued < S && t0 + issued < t1; ++issued) issue_tile(t0 + issued);
+  }
+  pdl_wait();
+  pdl_launch();
+  /* ---- scalars of this iteration, redundantly in every CTA ---- */
+  ohp_cg_state *me = f.rep + blockIdx.x;
+  if (warp == 0) {
+    int done = me->done;
+    if (!done) {
+      double t[3];
+      pf_sum_parts(f.parts + (size_t)f.rpar * 3 * f.G, f.G, lane, t);
+      if (MODE == OHP_MODE_P2P) pf_gather_totals(pd, t, lane);
+      if (lane == 0) {
+        cgcg_scalars(me, blockIdx.x == 0 ? f.hist : nullptr, f.hist_cap, t[0], t[1], f.jacobi ? t[2] : t[0]);
+        done = me->done;
+        s_scal[0] = me->alpha; s_scal[1] = me->beta;
+        if (blockIdx.x == 0) { *f.st_host = *me; trace_put(f.trace, TR_SPMV_BEGIN, me->its); }
+      }
+    }
+    if (lane == 0) { s_flag[0] = done; s_flag[1] = 0; }
+  }
+  __syncthreads();
+  if (s_flag[0]) {
+    if (is_producer) for (int i = 0; i < issued; ++i) mbar_wait(full0 + 8 * (i % S), 0);
+    return;
+  }
+  if (is_producer) {
+    for (int t = t0 + issued; t < t1; ++t) {
+      const int i = t - t0, s = i % S;
+      mbar_wait(empty0 + 8 * s, ((i / S) & 1) ^ 1);
+      issue_tile(t);
+    }
+    return;
+  }
+  /* ---------------- consumer warps ---------------- */
+  const bool ghost_cta = MODE == OHP_MODE_P2P && f.ghost_cta && f.ghost_cta[blockIdx.x];
+  const bool contrib = MODE == OHP_MODE_P2P && f.contrib[blockIdx.x];
+  unsigned long long halo_seq = 0;
+  if (MODE == OHP_MODE_P2P) halo_seq = pd.seq[1]; /* the neighbours' pushes of the previous launch carry this number */
+  PipeRowUpdate<JACOBI> up;
+  up.wo = cur ? v.W0 : v.W1; up.wn = cur ? v.W1 : v.W0; up.mn = cur ? v.M1 : v.M0;
+  up.z = v.Z0; up.s = v.s; up.p = v.p; up.r = v.r; up.x = v.x; up.dinv = v.dinv;
+  up.alpha = s_scal[0]; up.beta = s_scal[1];
+  up.g = up.d = up.nn = 0.0;
+  const double *xin = cur ? v.M0 : v.M1; /* m of the previous iteration (owned part + ghost tail) */
+  if (ghost_cta) {
+    if (tid < pd.n_nbr) p2p_wait(pd.hflags[pd.rank] + pd.nbr[tid], halo_seq, pd.seq + 2, pd.timeout_ns);
+    asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");
+    spmv_consume_emit<S, NC, IDX, SPLIT, true>(rowptr, colidx, vals, xin, vals_s, cols_s, rp_s, full0, empty0, t0, t1, up);
+  } else {
+    spmv_consume_emit<S, NC, IDX, SPLIT, false>(rowptr, colidx, vals, xin, vals_s, cols_s, rp_s, full0, empty0, t0, t1, up);
+  }
+  /* ---- CTA partials (consumer warps only: named barrier 1) ---- */
+  {
+    double sum[3] = {up.g, up.d, up.nn};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) sum[k] += __shfl_xor_sync(0xffffffffu, sum[k], o);
+      if (lane == 0) s_red[k * 32 + warp] = sum[k];
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");
+    if (warp == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        double t = lane < NC / 32 ? s_red[k * 32 + lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) f.parts[(size_t)(f.rpar ^ 1) * 3 * f.G + 3 * blockIdx.x + k] = t;
+      }
+    }
+  }
+  if (blockIdx.x == 0 && tid == 0) trace_put(f.trace, TR_SPMV_CTA_DONE, me->its);
+  if (MODE != OHP_MODE_P2P) return;
+  /* ---- halo: push w' (m') of the rows the neighbours ghost, publish when every contributor has arrived ---- */
+  if (contrib) {
+    /* a neighbour may still be READING the tail this push overwrites unless its own previous push has been seen */
+    if (tid < pd.n_nbr) p2p_wait(pd.hflags[pd.rank] + pd.nbr[tid], halo_seq, pd.seq + 2, pd.timeout_ns);
+    asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory"); /* also: every row of this CTA is stored */
+    const double *src = up.mn;
+    for (int j = f.hptr[blockIdx.x] + tid; j < f.hptr[blockIdx.x + 1]; j += NC) {
+      const int i = f.hidx[j];
+      const int l = pd.send_ldof[i];
+      int q = 0;
+      while (i >= pd.soff[q + 1]) ++q;
+      pd.p[cur][pd.nbr[q]][pd.dst_off[q] + (i - pd.soff[q])] = ld_weak(src + l);
+    }
+    __threadfence_system();
+    asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");
+    if (warp == 0) {
+      int last = 0;
+      if (lane == 0) last = (atomicInc(f.cnt, (unsigned)(f.n_contrib - 1)) == (unsigned)(f.n_contrib - 1));
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last) {
+        unsigned long long sq = 0;
+        if (lane == 0) { __threadfence(); sq = pd.seq[1] + 1; pd.seq[1] = sq; }
+        sq = __shfl_sync(0xffffffffu, sq, 0);
+        if (lane < pd.n_nbr) st_release_sys(pd.hflags[pd.nbr[lane]] + pd.rank, sq);
+      }
+    }
+  }
+  /* ---- rank total for the other ranks: the last CTA to arrive adds the G partials and posts them ---- */
+  if (warp == 0) {
+    int last = 0;
+    if (lane == 0) { __threadfence(); last = (atomicInc(f.cnt + 1, (unsigned)(f.G - 1)) == (unsigned)(f.G - 1)); }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+      __threadfence();
+      double t[3];
+      pf_sum_parts(f.parts + (size_t)(f.rpar ^ 1) * 3 * f.G, f.G, lane, t);
+      pf_post_total(pd, t, lane);
+      if (lane == 0) trace_put(f.trace, TR_AR_POSTED, me->its);
+    }
+  }
+}
+
+/* after a k_pipecg_vec pass that left vgrid x 3 partials: their sum becomes "CTA 0's partial" of the parity the next
+ * fused launch reads (the other CTAs' entries are zero), and the rank total goes to the peers' mailboxes */
+template <int MODE>
+__global__ void k_pipe_post(const double *vpart, int nvpart, ohp_pf_dev f, const ohp_p2p_dev pd) {
+  pdl_wait();
+  pdl_launch();
+  if (f.st_host->done) return;
+  const int lane = threadIdx.x;
+  double t[3];
+  pf_sum_parts(vpart, nvpart, lane, t);
+  double *dst = f.parts + (size_t)f.rpar * 3 * f.G;
+  for (int i = lane; i < 3 * f.G; i += 32) dst[i] = i < 3 ? t[i] : 0.0;
+  if (MODE == OHP_MODE_P2P) pf_post_total(pd, t, lane);
+}
+/* the scalar step on its own (first launch of a replacement pass): what every CTA of k_pipecg_fused does at its start,
+ * written to the host-visible state and to all replicas */
+template <int MODE>
+__global__ void k_pipe_scalars(ohp_pf_dev f, const ohp_p2p_dev pd) {
+  pdl_wait();
+  pdl_launch();
+  __shared__ ohp_cg_state s_st;
+  if (f.st_host->done) return;
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    double t[3];
+    pf_sum_parts(f.parts + (size_t)f.rpar * 3 * f.G, f.G, lane, t);
+    if (MODE == OHP_MODE_P2P) pf_gather_totals(pd, t, lane);
+    if (lane == 0) {
+      cgcg_scalars(f.st_host, f.hist, f.hist_cap, t[0], t[1], f.jacobi ? t[2] : t[0]);
+      s_st = *f.st_host;
+    }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < f.G; b += blockDim.x) f.rep[b] = s_st;
+}
+__global__ void k_pipe_replicate(const ohp_cg_state *src, ohp_cg_state *rep, int G) {
+  for (int b = threadIdx.x; b < G; b += blockDim.x) rep[b] = *src;
+}
+
+static int pf_plan_build(ohp_mesh m, bool p2p) {
+  ohp_context ctx = m->ctx;
+  cudaStream_t st = ctx->stream;
+  ohp_pf_plan *pl = new ohp_pf_plan();
+  const int G = std::max(1, std::min(m->n_tiles, ctx->num_sms));
+  pl->G = G;
+  std::vector<int32_t> hptr(G + 1, 0), hidx;
+  std::vector<uint8_t> contrib(G, 0);
+  if (p2p) {
+    const ohp_p2p_dev &pd = m->p2p->dev;
+    const int nsend = pd.soff[pd.n_nbr];
+    std::vector<int32_t> tr(m->n_tiles + 1, 0), send(std::max(1, nsend));
+    std::vector<uint8_t> gc(G, 0);
+    if (m->n_tiles > 0) OHP_CUDA(cudaMemcpyAsync(tr.data(), m->tile_row, sizeof(int32_t) * (m->n_tiles + 1), cudaMemcpyDeviceToHost, st));
+    if (nsend > 0) OHP_CUDA(cudaMemcpyAsync(send.data(), pd.send_ldof, sizeof(int32_t) * nsend, cudaMemcpyDeviceToHost, st));
+    if (m->ghost_cta) OHP_CUDA(cudaMemcpyAsync(gc.data(), m->ghost_cta, G, cudaMemcpyDeviceToHost, st));
+    OHP_CUDA(cudaStreamSynchronize(st));
+    std::vector<int32_t> row0(G + 1); /* CTA b owns the rows that start in its tiles */
+    for (int b = 0; b <= G; ++b) row0[b] = tr[(int)(((int64_t)m->n_tiles * b) / G)];
+    std::vector<int32_t> owner(std::max(1, nsend));
+    for (int i = 0; i < nsend; ++i) {
+      const int b = (int)(std::upper_bound(row0.begin(), row0.end(), send[i]) - row0.begin()) - 1;
+      owner[i] = std::min(std::max(b, 0), G - 1);
+      hptr[owner[i] + 1]++;
+    }
+    for (int b = 0; b < G; ++b) hptr[b + 1] += hptr[b];
+    hidx.resize(std::max(1, nsend));
+    std::vector<int32_t> cursor(hptr.begin(), hptr.end() - 1);
+    for (int i = 0; i < nsend; ++i) hidx[cursor[owner[i]]++] = i;
+    pl->n_contrib = 0;
+    for (int b = 0; b < G; ++b) { contrib[b] = (hptr[b + 1] > hptr[b] || gc[b]) ? 1 : 0; pl->n_contrib += contrib[b]; }
+    if (pl->n_contrib == 0) { contrib[0] = 1; pl->n_contrib = 1; } /* the flags still advance in lockstep */
+  }
+  if (hidx.empty()) hidx.push_back(0);
+  OHP_CUDA(OHP_MALLOC(ctx, &pl->hptr, sizeof(int32_t) * (G + 1)));
+  OHP_CUDA(OHP_MALLOC(ctx, &pl->hidx, sizeof(int32_t) * hidx.size()));
+  OHP_CUDA(OHP_MALLOC(ctx, &pl->contrib, G));
+  OHP_CUDA(OHP_MALLOC(ctx, &pl->rep, sizeof(ohp_cg_state) * G));
+  OHP_CUDA(OHP_MALLOC(ctx, &pl->parts, sizeof(double) * 2 * 3 * G));
+  OHP_CUDA(OHP_MALLOC(ctx, &pl->cnt, sizeof(unsigned) * 4));
+  OHP_CUDA(cudaMemcpyAsync(pl->hptr, hptr.data(), sizeof(int32_t) * (G + 1), cudaMemcpyHostToDevice, st));
+  OHP_CUDA(cudaMemcpyAsync(pl->hidx, hidx.data(), sizeof(int32_t) * hidx.size(), cudaMemcpyHostToDevice, st));
+  OHP_CUDA(cudaMemcpyAsync(pl->contrib, contrib.data(), G, cudaMemcpyHostToDevice, st));
+  OHP_CUDA(cudaMemsetAsync(pl->parts, 0, sizeof(double) * 2 * 3 * G, st));
+  OHP_CUDA(cudaMemsetAsync(pl->cnt, 0, sizeof(unsigned) * 4, st));
+  OHP_CUDA(cudaStreamSynchronize(st)); /* the host vectors above go out of scope */
+  m->pfplan = pl;
+  return 0;
+}
+
+template <int S, int NC, class IDX, bool SPLIT, bool JACOBI, int MODE>
+static int pf_launch_t(ohp_mat A, const IDX *cols, const ohp_pipe_vecs &v, const ohp_pf_dev &f, const ohp_p2p_dev &pd, int cur, bool pdl) {
+  ohp_mesh m = A->mesh;
+  ohp_context ctx = m->ctx;
+  constexpr int smem = tma_smem_bytes(S, (int)sizeof(IDX));
+  static unsigned long long configured_devices = 0ull;
+  if (!((configured_devices >> (ctx->device & 63)) & 1ull)) {
+    OHP_CUDA(cudaFuncSetAttribute(k_pipecg_fused<S, NC, IDX, SPLIT, JACOBI, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured_devices |= 1ull << (ctx->device & 63);
+  }
+  OHP_CUDA(ohp_launch(k_pipecg_fused<S, NC, IDX, SPLIT, JACOBI, MODE>, dim3(f.G), dim3(NC + 32), (size_t)smem, ctx->stream, pdl,
+                      (const int32_t *)m->rowptr, cols, (const double *)A->vals, (const int32_t *)m->tile_row, m->n_tiles, v, f, pd, cur,
+                      spmv_pin_tiles(m, f.G, (int)sizeof(IDX))));
+  ctx->launches++;
+  return 0;
+}
+template <bool JACOBI, int MODE>
+static int pf_launch(ohp_mat A, const ohp_pipe_vecs &v, const ohp_pf_dev &f, const ohp_p2p_dev &pd, int cur, bool pdl) {
+  ohp_mesh m = A->mesh;
+  static const char *idx = getenv("OHP_IDX");
+  const bool split = m->nnz > (int64_t)8 * std::max(1, m->n_owned);
+  const bool i16 = m->col16 && !(idx && idx[0] == '3');
+  if (i16) return split ? pf_launch_t<3, 608, int16_t, true, JACOBI, MODE>(A, m->col16, v, f, pd, cur, pdl)
+                        : pf_launch_t<3, 608, int16_t, false, JACOBI, MODE>(A, m->col16, v, f, pd, cur, pdl);
+  return split ? pf_launch_t<3, 608, int32_t, true, JACOBI, MODE>(A, m->colidx, v, f, pd, cur, pdl)
+               : pf_launch_t<3, 608, int32_t, false, JACOBI, MODE>(A, m->colidx, v, f, pd, cur, pdl);
+}
+
+static int pipefused_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o, ohp_ksp_result *res, bool p2p) {
+  ohp_mesh m = A->mesh;
+  ohp_context ctx = m->ctx;
+  cudaStream_t st = ctx->stream;
+  const int n = m->n_owned;
+  const size_t len = (size_t)std::max(1, n + m->n_ghost);
+  const bool jac = (o->pc == OHP_PC_JACOBI);
+  if (!(spmv_use_tma(m) || m->n_tiles == 0) || getenv("OHP_SPMV")) OHP_FAIL(OHP_ERR_SUP, "ohp_ksp_cg (pipelined, fused): needs the TMA-pipelined SpMV");
+  if (!m->pfplan) OHP_TRY(pf_plan_build(m, p2p));
+  ohp_pf_plan *pl = m->pfplan;
+  auto need = [&](double **ptr) -> int {
+    if (!*ptr) { OHP_CUDA(OHP_MALLOC(ctx, ptr, sizeof(double) * len)); OHP_CUDA(cudaMemsetAsync(*ptr, 0, sizeof(double) * len, st)); }
+    return 0;
+  };
+  OHP_TRY(need(&A->p)); OHP_TRY(need(&A->w)); OHP_TRY(need(&A->s)); OHP_TRY(need(&A->r)); OHP_TRY(need(&A->z));
+  static const ohp_p2p_dev no_p2p = {};
+  const ohp_p2p_dev &pd = p2p ? m->p2p->dev : no_p2p;
+  ohp_pipe_vecs v;
+  memset(&v, 0, sizeof(v));
+  if (p2p) { v.M0 = pd.p[0][ctx->rank]; v.M1 = pd.p[1][ctx->rank]; }
+  else { OHP_TRY(need(&A->pm0)); OHP_TRY(need(&A->pm1)); v.M0 = A->pm0; v.M1 = A->pm1; }
+  if (jac) {
+    OHP_TRY(need(&A->pw0)); OHP_TRY(need(&A->pw1)); OHP_TRY(need(&A->dinv));
+    v.W0 = A->pw0; v.W1 = A->pw1;
+    OHP_TRY(ohp_extract_dinv(A));
+  } else { v.W0 = v.M0; v.W1 = v.M1; }
+  v.Z0 = v.Z1 = A->z; /* z is updated in place here (row-local) */
+  v.r = A->r; v.s = A->s; v.p = A->p; v.x = x->d; v.nb = A->w; v.b = b->d; v.dinv = A->dinv;
+  double *hist = nullptr;
+  int hist_cap = 0;
+  if (o->history && o->history_cap > 0) {
+    if (A->hist_cap < o->history_cap) {
+      OHP_FREE(ctx, A->hist);
+      OHP_CUDA(OHP_MALLOC(ctx, &A->hist, sizeof(double) * o->history_cap));
+      A->hist_cap = o->history_cap;
+    }
+    hist = A->hist; hist_cap = o->history_cap;
+    OHP_CUDA(cudaMemsetAsync(hist, 0, sizeof(double) * hist_cap, st));
+  }
+  ohp_cg_state init;
+  memset(&init, 0, sizeof(init));
+  init.rtol = o->rtol; init.abstol = o->abstol; init.dtol = o->dtol; init.maxit = o->max_it;
+  *ctx->h_cg = init;
+  OHP_CUDA(cudaMemcpyAsync(ctx->d_cg, ctx->h_cg, sizeof(init), cudaMemcpyHostToDevice, st));
+  k_pipe_replicate<<<1, 256, 0, st>>>(ctx->d_cg, pl->rep, pl->G); OHP_CHECK_LAUNCH(ctx);
+  const int mode = p2p ? OHP_MODE_P2P : OHP_MODE_SERIAL;
+  const int vgrid = (int)std::min<int64_t>(std::min<int64_t>(nblk(n, 256), (int64_t)ctx->num_sms * 5), kMaxPartials / 3);
+  const int nhalo = p2p ? std::max(1, std::min(16, (pd.soff[pd.n_nbr] + 255) / 256)) : 0;
+  double *vpart = ctx->d_partials + kMaxPartials;
+  ohp_cgcg_epi epi;
+  memset(&epi, 0, sizeof(epi));
+  epi.vpart = vpart; epi.nvpart = vgrid; epi.jacobi = jac ? 1 : 0; epi.hist = hist; epi.hist_cap = hist_cap; epi.pipe = 2;
+  epi.trace = ohp_cg_trace_open(ctx);
+  if (p2p) OHP_TRY(ohp_p2p_entry_barrier(m));
+  static const char *nooverlap = getenv("OHP_NOOVERLAP");
+  const bool overlap = p2p && m->ghost_cta && !nooverlap;
+  const int wait_in_vec = overlap ? 0 : 1;
+  epi.ghost_cta = overlap ? m->ghost_cta : nullptr;
+  static const char *nopdl = getenv("OHP_NOPDL");
+  const bool pdl = !nopdl;
+  static const char *rr_env = getenv("OHP_PIPE_RR");
+  const int rr = rr_env ? atoi(rr_env) : kPipeReplaceEvery;
+  const int check_every = o->check_every > 0 ? o->check_every : 50;
+  ohp_pf_dev f;
+  memset(&f, 0, sizeof(f));
+  f.G = pl->G; f.n_contrib = pl->n_contrib; f.hptr = pl->hptr; f.hidx = pl->hidx; f.contrib = pl->contrib;
+  f.ghost_cta = p2p ? m->ghost_cta : nullptr; /* without the flags table every CTA of a partitioned run would have to wait: see below */
+  f.rep = pl->rep; f.st_host = ctx->d_cg; f.parts = pl->parts; f.cnt = pl->cnt; f.hist = hist; f.hist_cap = hist_cap; f.jacobi = jac ? 1 : 0;
+  f.trace = epi.trace;
+  if (p2p && !m->ghost_cta && m->n_tiles > 0) OHP_FAIL(OHP_ERR_LIB, "ohp_ksp_cg (pipelined, fused): ghost-column table missing");
+  EventBag bag, profbag;
+  cudaEvent_t ev0, ev1;
+  OHP_CUDA(bag.record(st, &ev0));
+  std::vector<cudaEvent_t> &prof = profbag.ev;
+  const int nprof = std::max(0, o->profile);
+  int pushes = 0, rpar = 0; /* next push goes to buffer pushes & 1; the next consumer of partials reads parity rpar */
+  auto vec = [&](int kind, int cur) -> int {
+    if (p2p) {
+      if (jac) OHP_CUDA(ohp_launch(k_pipecg_vec<OHP_MODE_P2P, true>, dim3(vgrid + nhalo), dim3(256), 0, st, pdl, v, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, nhalo, ctx->d_ticket + 2, wait_in_vec, epi.trace, kind, cur));
+      else OHP_CUDA(ohp_launch(k_pipecg_vec<OHP_MODE_P2P, false>, dim3(vgrid + nhalo), dim3(256), 0, st, pdl, v, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, nhalo, ctx->d_ticket + 2, wait_in_vec, epi.trace, kind, cur));
+    } else {
+      if (jac) OHP_CUDA(ohp_launch(k_pipecg_vec<OHP_MODE_SERIAL, true>, dim3(vgrid), dim3(256), 0, st, pdl, v, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, 0, (unsigned *)nullptr, 1, epi.trace, kind, cur));
+      else OHP_CUDA(ohp_launch(k_pipecg_vec<OHP_MODE_SERIAL, false>, dim3(vgrid), dim3(256), 0, st, pdl, v, n, (const ohp_cg_state *)ctx->d_cg, vpart, pd, 0, (unsigned *)nullptr, 1, epi.trace, kind, cur));
+    }
+    ctx->launches++;
+    return 0;
+  };
+  auto stage = [&](int kind) -> int { const int cur = pushes & 1; OHP_TRY(vec(kind, cur)); pushes++; return 0; };
+  auto stage_mult = [&](int kind, double *out) -> int {
+    const int cur = pushes & 1;
+    OHP_TRY(stage(kind));
+    OHP_TRY(spmv_enqueue(A, cur ? v.M1 : v.M0, out, ctx->d_cg, ctx->d_scalars, mode, nullptr, pd, epi));
+    return 0;
+  };
+  auto post = [&]() -> int { /* vpart -> parts[rpar] (+ mailboxes) for the next consumer */
+    f.rpar = rpar;
+    if (p2p) OHP_CUDA(ohp_launch(k_pipe_post<OHP_MODE_P2P>, dim3(1), dim3(32), 0, st, pdl, (const double *)vpart, vgrid, f, pd));
+    else OHP_CUDA(ohp_launch(k_pipe_post<OHP_MODE_SERIAL>, dim3(1), dim3(32), 0, st, pdl, (const double *)vpart, vgrid, f, pd));
+    ctx->launches++;
+    return 0;
+  };
+  /* set-up: r = b, u, m = u; w = A u; partials of (r,u), (w,u), (u,u) */
+  OHP_TRY(stage_mult(PK_INIT, A->w));
+  OHP_TRY(stage(PK_TAKE_W));
+  OHP_TRY(post());
+  int iter = 0; /* == the device's iteration count while it is not done */
+  for (;;) {
+    for (int it = 0; it < check_every; ++it, ++iter) {
+      f.rpar = rpar;
+      if (rr > 0 && iter > 0 && iter % rr == 0) {
+        /* residual replacement in place of iteration `iter`'s recurrences */
+        if (p2p) OHP_CUDA(ohp_launch(k_pipe_scalars<OHP_MODE_P2P>, dim3(1), dim3(256), 0, st, pdl, f, pd));
+        else OHP_CUDA(ohp_launch(k_pipe_scalars<OHP_MODE_SERIAL>, dim3(1), dim3(256), 0, st, pdl, f, pd));
+        ctx->launches++;
+        OHP_TRY(vec(PK_PX, pushes & 1));
+        OHP_TRY(stage_mult(PK_STAGE_P, A->s));   /* s = A p */
+        OHP_TRY(stage_mult(PK_STAGE_S, A->z));   /* z = A M^-1 s */
+        OHP_TRY(stage_mult(PK_STAGE_X, A->w));   /* A x */
+        OHP_TRY(stage_mult(PK_NEW_R, A->w));     /* r = b - A x; A M^-1 r */
+        OHP_TRY(stage(PK_TAKE_W));               /* w, partials, m = M^-1 w */
+        OHP_TRY(post());                         /* (rpar unchanged: the scalar step consumed it, the post refills it) */
+      } else {
+        const bool timed = (int)prof.size() < 2 * nprof && (iter >= check_every || o->max_it <= check_every);
+        const int cur = pushes & 1;
+        if (timed) OHP_CUDA(profbag.record(st));
+        if (p2p) { if (jac) OHP_TRY((pf_launch<true, OHP_MODE_P2P>(A, v, f, pd, cur, pdl))); else OHP_TRY((pf_launch<false, OHP_MODE_P2P>(A, v, f, pd, cur, pdl))); }
+        else { if (jac) OHP_TRY((pf_launch<true, OHP_MODE_SERIAL>(A, v, f, pd, cur, pdl))); else OHP_TRY((pf_launch<false, OHP_MODE_SERIAL>(A, v, f, pd, cur, pdl))); }
+        if (timed) OHP_CUDA(profbag.record(st));
+        pushes++;
+        rpar ^= 1;
+      }
+    }
+    OHP_CUDA(cudaMemcpyAsync(ctx->h_cg, ctx->d_cg, sizeof(ohp_cg_state), cudaMemcpyDeviceToHost, st));
+    OHP_CUDA(cudaStreamSynchronize(st));
+    if (ctx->h_cg->done) break;
+    if (iter > o->max_it + 3 * check_every) OHP_FAIL(OHP_ERR_LIB, "ohp_ksp_cg (pipelined, fused): iteration control did not terminate");
+  }
+  OHP_CUDA(bag.record(st, &ev1));
+  OHP_CUDA(cudaEventSynchronize(ev1));
+  res->total_ms = 0.f;
+  cudaEventElapsedTime(&res->total_ms, ev0, ev1);
+  res->its = ctx->h_cg->its; res->reason = ctx->h_cg->reason; res->rnorm = ctx->h_cg->dp; res->rnorm0 = ctx->h_cg->rnorm0;
+  res->spmv_ms = 0.f; res->spmv_samples = 0;
+  ohp_cg_trace_dump(ctx, "pipecg-fused");
+  {
+    double acc = 0.0;
+    int used = 0, L = (o->max_it <= check_every) ? 0 : check_every;
+    for (size_t i = 0; i + 1 < prof.size(); i += 2, ++L) {
+      while (rr > 0 && L > 0 && L % rr == 0) ++L;
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, prof[i], prof[i + 1]);
+      if (L < res->its) { acc += ms; used++; }
+    }
+    if (used) { res->spmv_ms = (float)(acc / used); res->spmv_samples = used; }
+  }
+  if (p2p) OHP_TRY(ohp_p2p_check(m, "ohp_ksp_cg (pipelined, fused)"));
+  if (hist) {
+    const int ncopy = std::min(hist_cap, res->its + 1);
+    OHP_CUDA(cudaMemcpyAsync(o->history, hist, sizeof(double) * ncopy, cudaMemcpyDeviceToHost, st));
+    OHP_CUDA(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
 extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o, ohp_ksp_result *res) {
   if (!A || !b || !x || !o || !res) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_ksp_cg: null argument");
   ohp_mesh m = A->mesh;
@@ -1015,9 +2018,16 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
     const bool feasible = spmv_use_tma(m) && n > 0 && (ctx->nranks == 1 || can_p2p);
     bool persistent = feasible && ctx->nranks == 1 && n < kPersistentBelowRows; /* measured: see DESIGN.md section 5 */
     if (force && force[0] == 'c') persistent = false; /* classic or cgcg */
-    if (force && force[0] == 'p') persistent = feasible;
+    if (force && force[0] == 'p' && force[1] == 'e') persistent = feasible;
     /* OHP_CG=fused: the one-synchronisation persistent kernel (ohp_cg_fused.cu) */
     if (force && force[0] == 'f' && feasible) return ohp_cg_fused_solve(A, b, x, o, res, can_p2p);
+    /* OHP_CG=pipecg: the pipelined recurrence (reduction and all-reduce overlapped with the SpMV) */
+    const bool feasible_pipe = (spmv_use_tma(m) || m->n_tiles == 0) && (ctx->nranks == 1 ? n > 0 : can_p2p);
+    if (o->ksp_type == OHP_KSP_PIPECG && n == 0 && ctx->nranks == 1) { res->its = 0; res->reason = 3; res->rnorm = res->rnorm0 = 0.0; res->spmv_ms = res->total_ms = 0.f; res->spmv_samples = 0; return 0; }
+    if (o->ksp_type == OHP_KSP_PIPECG && !feasible_pipe) OHP_FAIL(OHP_ERR_SUP, "ohp_ksp_cg: -ksp_type pipecg needs the TMA SpMV and, on a partitioned run, the NVLink peer transport");
+    /* OHP_CG=pipecg2: the two-launch form of the pipelined recurrence (A/B runs); pipecg / -ksp_type pipecg: one launch per iteration */
+    if (force && !strcmp(force, "pipecg2") && feasible_pipe) return pipecg_solve(A, b, x, o, res, can_p2p);
+    if ((o->ksp_type == OHP_KSP_PIPECG || (force && force[0] == 'p' && force[1] == 'i')) && feasible_pipe) return pipefused_solve(A, b, x, o, res, can_p2p);
     if (persistent) return ohp_cg_persistent_solve(A, b, x, o, res, can_p2p);
     /* single-reduction recurrence in two launches: default for partitioned runs over NVLink peer memory (one
      * all-reduce and one kernel boundary fewer per iteration); OHP_CG=cgcg forces it on one GPU */

@@ -182,6 +182,19 @@ def main():
     assert abs(res["ksp_its"] - ref["ksp_its"]) <= max(2, ref["ksp_its"] // 40), (res["ksp_its"], ref["ksp_its"])
     uref = ref["u"][gidx[dof2vert[start:start + info.n_owned]]]
     assert np.abs(u.to_host() - uref).max(initial=0.0) <= 1e-7 * np.abs(ref["u"]).max(), "solution"
+    # the same solve with -ksp_type pipecg (pipelined recurrence: halo push, mailbox all-reduce and the residual
+    # replacement passes all cross the ranks) and with the Jacobi preconditioner
+    for kt, pc in ((ohp.KSP_PIPECG, ohp.PC_NONE), (ohp.KSP_PIPECG, ohp.PC_JACOBI), (ohp.KSP_CG, ohp.PC_JACOBI)):
+        if os.environ.get("OHP_COMM", "p2p") == "nccl" and kt == ohp.KSP_PIPECG:
+            continue  # pipecg needs the NVLink peer transport
+        u2 = m.create_global_vector()
+        m.project(0, 0, u2)
+        res2 = m.snes_solve(0, J, u2, ksp=ohp.ksp_options(rtol=1e-9, max_it=100000, ksp_type=kt, pc=pc))
+        assert (res2["its"], res2["reason"]) == (1, 3), (kt, pc, res2)
+        if pc == ohp.PC_NONE:  # pipecg on the ill-conditioned XGC mesh: up to 7 % more iterations than CG (539 against 505 at 2 GPUs)
+            assert abs(res2["ksp_its"] - ref["ksp_its"]) <= max(2, ref["ksp_its"] // 10), (kt, res2["ksp_its"], ref["ksp_its"])
+        assert np.abs(u2.to_host() - uref).max(initial=0.0) <= 1e-6 * np.abs(ref["u"]).max(), "solution (ksp_type %d pc %d)" % (kt, pc)
+        u2.destroy()
     # DMComputeL2Diff across ranks: every cell integrated once (by the owner of its first corner)
     xi, wq = oracle.quadrature(coords.shape[1])
     full = (coords ** 2).sum(axis=1) * (1.0 if coords.shape[1] == 2 else 2.0 / 3.0)

@@ -77,13 +77,18 @@ def test_run_type_test_and_perf_and_analytic():
                        capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stdout + p.stderr
     assert float(re.search(r"L_2 Error: ([0-9.e+-]+)", p.stdout).group(1)) < 2e-3
+    # -ksp_type pipecg (KSPPIPECG): the pipelined recurrence through the facade, same answer
+    p = subprocess.run([EXE, "-mesh", "box", "-cells", "32,32", "-variable_coefficient", "analytic", "-ksp_rtol", "1e-10", "-ksp_type", "pipecg"],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert float(re.search(r"L_2 Error: ([0-9.e+-]+)", p.stdout).group(1)) < 2e-3
 
 
 @pytest.mark.gpu
 def test_unsupported_requests_fail_loudly():
     build()
     p = subprocess.run([EXE, "-mesh", "box", "-cells", "8,8", "-ksp_type", "gmres"], capture_output=True, text=True, timeout=120)
-    assert p.returncode != 0 and "only cg is built" in p.stderr
+    assert p.returncode != 0 and "only cg and pipecg are built" in p.stderr
     p = subprocess.run([EXE, "-mesh", "/nonexistent.osh"], capture_output=True, text=True, timeout=120)
     assert p.returncode != 0
 

@@ -157,9 +157,11 @@ def test_spmv_and_vec_ops(ctx, oracle_mod, name):
     m.destroy()
 
 
+@pytest.mark.parametrize("ksp_type", [ohp.KSP_CG, ohp.KSP_PIPECG])
 @pytest.mark.parametrize("pc", [0, 1])
 @pytest.mark.parametrize("name", ["T23", "box2d_33x17", "sheared_21x13", "T24k", "box3d_12x11x10"])
-def test_cg_matches_oracle(ctx, oracle_mod, name, pc):
+def test_cg_matches_oracle(ctx, oracle_mod, name, pc, ksp_type):
+    """-ksp_type cg and pipecg (the pipelined recurrence: same iterates in exact arithmetic) against the oracle's CG."""
     cells, coords = get_mesh(name)
     bnd, gidx, N, rowptr, colidx = oracle_setup(oracle_mod, cells, coords)
     m = ohp.Mesh(ctx, cells, coords).setup()
@@ -167,10 +169,12 @@ def test_cg_matches_oracle(ctx, oracle_mod, name, pc):
     u, b, x = (m.create_global_vector() for _ in range(3))
     m.jacobian(0, u, J)
     m.residual(0, u, b)
-    out = ohp.ksp_cg(J, b, x, ohp.ksp_options(rtol=1e-9, max_it=20000, pc=pc), history=True)
+    out = ohp.ksp_cg(J, b, x, ohp.ksp_options(rtol=1e-9, max_it=20000, pc=pc, ksp_type=ksp_type), history=True)
     ref = oracle_mod.cg(rowptr, colidx, J.values(), b.to_host(), rtol=1e-9, maxit=20000, pc=pc, history=True)
     assert out["reason"] == ref["reason"] == 2
-    assert abs(out["its"] - ref["its"]) <= max(2, ref["its"] // 40)  # rounding-order sensitivity of CG
+    # rounding-order sensitivity of CG; the pipelined recurrence (more recurred vectors) loses a little more on the
+    # ill-conditioned XGC mesh: 526 against 506 iterations
+    assert abs(out["its"] - ref["its"]) <= max(2, ref["its"] // (40 if ksp_type == ohp.KSP_CG else 20))
     # CG amplifies rounding differences (summation order, FMA contraction) exponentially on an
     # ill-conditioned operator: the monitored norms agree to many digits only for the first iterations
     k = min(out["its"], ref["its"], 8)
@@ -196,6 +200,12 @@ def test_cg_limits(ctx, oracle_mod):
     out = ohp.ksp_cg(J, b, x, ohp.ksp_options(rtol=1e-9, max_it=37, check_every=7))
     assert (out["its"], out["reason"]) == (37, -3)
     out = ohp.ksp_cg(J, b.set(0.0), x, ohp.ksp_options(rtol=1e-9))
+    assert (out["its"], out["reason"]) == (0, 3)
+    # the same limits through the pipelined recurrence
+    m.residual(0, u, b)
+    out = ohp.ksp_cg(J, b, x, ohp.ksp_options(rtol=1e-9, max_it=37, check_every=7, ksp_type=ohp.KSP_PIPECG))
+    assert (out["its"], out["reason"]) == (37, -3)
+    out = ohp.ksp_cg(J, b.set(0.0), x, ohp.ksp_options(rtol=1e-9, ksp_type=ohp.KSP_PIPECG))
     assert (out["its"], out["reason"]) == (0, 3)
     m.destroy()
 
