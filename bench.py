@@ -471,14 +471,26 @@ def measure_workload(job, args, workload, steps, warmup, e2e_steps, sampler, wit
     ab = algorithmic_bytes(dim, info.n_cells, info.n_verts, info.n_owned, info.nnz)
     spmv_ms = float(np.mean(phase["spmv_ms"])) if phase["spmv_ms"] else None
     roof = None
+    algo = int(res.get("algo", 0))
     if spmv_ms:
-        ach = ab["spmv"] / (spmv_ms * 1e-3) / 1e9
-        roof = {"kernel": "k_spmv_tma<true> (persistent TMA-pipelined CSR SpMV + fused (p,Ap))", "bound": "hbm", "achieved": ach, "peak": peak,
+        # which kernel the solver bracketed with CUDA events (ohp_ksp_result.algo)
+        if algo == 4:   # one launch per iteration: SpMV + the whole pipelined-CG vector update of the row
+            kname, kbytes = "k_pipecg_fused (persistent TMA-pipelined CSR SpMV with the pipelined-CG vector update fused per row)", ab["spmv"] - 16 * info.n_owned + 96 * info.n_owned
+        elif algo == 3:
+            kname, kbytes = "k_spmv_tma<true> (persistent TMA-pipelined CSR SpMV; pipelined CG, reducer warp)", ab["spmv"]
+        else:
+            kname, kbytes = "k_spmv_tma<true> (persistent TMA-pipelined CSR SpMV + fused (p,Ap))", ab["spmv"]
+        ach = kbytes / (spmv_ms * 1e-3) / 1e9
+        roof = {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": peak,
                 "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                "bytes_per_launch": ab["spmv"], "ms_per_launch": spmv_ms, "launches_timed": int(res["spmv_samples"]),
+                "bytes_per_launch": kbytes, "ms_per_launch": spmv_ms, "launches_timed": int(res["spmv_samples"]),
+                "cg_recurrence": {0: "classic (3 launches)", 1: "single-reduction (2 launches)", 2: "persistent cooperative kernel",
+                                  3: "pipelined (2 launches)", 4: "pipelined (1 launch)"}.get(algo, str(algo)),
                 "scope": "rank 0's share of the matrix" if world > 1 else "whole matrix"}
+        if world > 1 and 12 * info.nnz + 100 * info.n_owned < 200e6:
+            roof["note"] = "rank 0's share (%.0f MB) is of the order of the 126 MB L2: the vectors are L2-resident, achieved may exceed the HBM line" % ((12 * info.nnz + 100 * info.n_owned) / 1e6)
         tr = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tr) and world == 1 and not args.n:  # ncu capture of the full matrix on one GPU (profiles/)
+        if os.path.exists(tr) and world == 1 and not args.n and algo != 4:  # ncu capture of the full matrix on one GPU (profiles/)
             with open(tr) as f:
                 roof["traffic"] = json.load(f).get("%s:spmv" % workload)
                 roof["traffic_source"] = "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel on this workload (profiles/), not re-measured in this run"

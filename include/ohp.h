@@ -324,6 +324,9 @@ typedef struct {
   int32_t profile;           /* >0: bracket up to this many SpMV launches with CUDA events (-log_view analogue) */
   int32_t ksp_type;          /* OHP_KSP_CG (default) | OHP_KSP_PIPECG */
 } ohp_ksp_options;
+/* the kernel the profiled launches belong to: k_spmv_tma (classic three-launch CG, single-reduction two-launch CG, two-launch
+ * pipelined CG), the persistent cooperative kernel, or k_pipecg_fused (SpMV + the whole vector update in one launch) */
+enum { OHP_ALGO_CLASSIC = 0, OHP_ALGO_SINGLE_REDUCTION = 1, OHP_ALGO_PERSISTENT = 2, OHP_ALGO_PIPELINED_2L = 3, OHP_ALGO_PIPELINED_FUSED = 4, OHP_ALGO_FUSED_PERSISTENT = 5 };
 typedef struct {
   int32_t its;
   int32_t reason; /* KSPConvergedReason: 2 RTOL, 3 ATOL, -3 ITS, -4 DTOL, -8 INDEFINITE_MAT, -9 NANORINF */
@@ -332,6 +335,7 @@ typedef struct {
   float spmv_ms;        /* mean device time of the profiled SpMV launches (0 if profile == 0) */
   int32_t spmv_samples; /* how many launches that mean is over */
   float total_ms;       /* device time of the whole solve (CUDA events) */
+  int32_t algo;         /* which recurrence ran (OHP_ALGO_*): names the kernel that `spmv_ms` times */
 } ohp_ksp_result;
 int ohp_ksp_default_options(ohp_ksp_options *o);
 int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *opts, ohp_ksp_result *res);
@@ -362,6 +366,7 @@ typedef struct {
   float ms_residual, ms_jacobian, ms_ksp; /* device time per phase (CUDA events), summed */
   float spmv_ms;        /* from the last linear solve, see ohp_ksp_result */
   int32_t spmv_samples;
+  int32_t algo;         /* of the last linear solve */
 } ohp_snes_result;
 int ohp_snes_default_options(ohp_snes_options *o);
 int ohp_snes_solve(ohp_mesh mesh, int problem, ohp_mat J, ohp_vec u, const ohp_snes_options *opts,

@@ -54,7 +54,7 @@ class KspOptions(ctypes.Structure):
 class KspResult(ctypes.Structure):
     _fields_ = [("its", ctypes.c_int32), ("reason", ctypes.c_int32), ("rnorm", ctypes.c_double),
                 ("rnorm0", ctypes.c_double), ("spmv_ms", ctypes.c_float), ("spmv_samples", ctypes.c_int32),
-                ("total_ms", ctypes.c_float)]
+                ("total_ms", ctypes.c_float), ("algo", ctypes.c_int32)]
 
 
 SNES_MONITOR_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int32, ctypes.c_double)
@@ -71,7 +71,8 @@ class SnesResult(ctypes.Structure):
     _fields_ = [("its", ctypes.c_int32), ("ksp_its", ctypes.c_int32), ("reason", ctypes.c_int32),
                 ("n_residual", ctypes.c_int32), ("n_jacobian", ctypes.c_int32), ("fnorm0", ctypes.c_double),
                 ("fnorm", ctypes.c_double), ("ms_residual", ctypes.c_float), ("ms_jacobian", ctypes.c_float),
-                ("ms_ksp", ctypes.c_float), ("spmv_ms", ctypes.c_float), ("spmv_samples", ctypes.c_int32)]
+                ("ms_ksp", ctypes.c_float), ("spmv_ms", ctypes.c_float), ("spmv_samples", ctypes.c_int32),
+                ("algo", ctypes.c_int32)]
 
 
 _lib = None

@@ -584,7 +584,7 @@ int ohp_cg_fused_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o
   res->total_ms = 0.f;
   cudaEventElapsedTime(&res->total_ms, e0.e, e1.e);
   res->its = ctx->h_cg->its; res->reason = ctx->h_cg->reason; res->rnorm = ctx->h_cg->dp; res->rnorm0 = ctx->h_cg->rnorm0;
-  res->spmv_ms = 0.f; res->spmv_samples = 0;
+  res->spmv_ms = 0.f; res->spmv_samples = 0; res->algo = OHP_ALGO_FUSED_PERSISTENT;
   ohp_cg_trace_dump(ctx, "fused");
   if (p2p) OHP_TRY(ohp_p2p_check(m, "ohp_ksp_cg (fused)"));
   else {

@@ -389,7 +389,7 @@ int ohp_cg_persistent_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_optio
   res->total_ms = 0.f;
   cudaEventElapsedTime(&res->total_ms, ev0, ev1);
   res->its = ctx->h_cg->its; res->reason = ctx->h_cg->reason; res->rnorm = ctx->h_cg->dp; res->rnorm0 = ctx->h_cg->rnorm0;
-  res->spmv_ms = 0.f; res->spmv_samples = 0;
+  res->spmv_ms = 0.f; res->spmv_samples = 0; res->algo = OHP_ALGO_PERSISTENT;
   if (p2p) OHP_TRY(ohp_p2p_check(m, "ohp_ksp_cg (persistent)"));
   if (hist) {
     const int ncopy = std::min(o->history_cap, res->its + 1);

@@ -338,6 +338,46 @@ __device__ __forceinline__ void spmv_consume_emit(const int32_t *__restrict__ ro
   }
 }
 
+
+/* The same consumer loop with the consumer warps split into GR groups that work on DIFFERENT tiles (group g takes the
+ * CTA's tiles g, g + GR, ...): one tile's dependency chain (mbarrier -> rowptr -> columns -> gather -> FMA -> vector
+ * loads -> stores, ~2 us in the fused pipelined-CG kernel against 0.9 us per tile at HBM rate) no longer bounds the CTA.
+ * A row that runs past its tile is finished by the thread that started it straight from global memory (at most one row
+ * per tile), so the next tile's group never waits for a carry and the summation order stays the serial CSR order.  emit.load(row) issues the row's vector operands
+ * before the row is summed, emit.store(row, sum, operands) applies the update. */
+template <int S, int NCT, int GR, class IDX, bool COHERENT, class Emit>
+__device__ __forceinline__ void spmv_consume_groups(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colidx,
+                                                    const double *__restrict__ vals, const double *x, const double *vals_s,
+                                                    const IDX *cols_s, const int32_t *rp_s, uint32_t full0, uint32_t empty0,
+                                                    int t0, int t1, Emit &emit) {
+  constexpr int T = kSpmvTile, NG = NCT / GR;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int grp = tid / NG, gtid = tid - grp * NG;
+  for (int t = t0 + grp; t < t1; t += GR) {
+    const int i = t - t0, s = i % S;
+    mbar_wait(full0 + 8 * s, (i / S) & 1);
+    const int32_t *rp = rp_s + s * kTmaRpStride;
+    const double *vs = vals_s + s * T;
+    const IDX *cs = cols_s + s * T;
+    const int rs = rp[kSpmvRowCap + 2], re = rp[kSpmvRowCap + 3];
+    const int base = t * T, lim = base + T;
+    for (int r = rs + gtid; r < re; r += NG) {
+      const int a = rp[r - rs], b = rp[r - rs + 1];
+      auto opnd = emit.load(r);
+      double sum;
+      if (b <= lim) sum = row_dot<IDX, COHERENT>(vs, cs, a - base, b - base, x, 0.0, r);
+      else {
+        /* the row's tail lies in the next tile (another group's): add it in order straight from global memory */
+        sum = row_dot<IDX, COHERENT>(vs, cs, a - base, lim - base, x, 0.0, r);
+        sum = row_dot<IDX, COHERENT>(vals + lim, colidx + lim, 0, b - lim, x, sum, r);
+      }
+      emit.store(r, sum, opnd);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty0 + 8 * s);
+  }
+}
+
 template <bool CG, int kTmaStages, int kTmaConsumers, class IDX, bool SPLIT, int MINB = 1>
 __global__ void __launch_bounds__(kTmaConsumers + 64, MINB)
 k_spmv_tma(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colidx, const double *__restrict__ vals, const double *x, double *__restrict__ y, const int32_t *__restrict__ tile_row, int n_tiles,
@@ -1093,6 +1133,7 @@ static int cgcg_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o,
   res->its = ctx->h_cg->its; res->reason = ctx->h_cg->reason; res->rnorm = ctx->h_cg->dp; res->rnorm0 = ctx->h_cg->rnorm0;
   res->spmv_ms = 0.f; res->spmv_samples = 0;
   ohp_cg_trace_dump(ctx, "cgcg");
+  res->algo = OHP_ALGO_SINGLE_REDUCTION;
   {
     /* SpMV launch number j closes iteration j - 1 (launch 0 is the initial pass): count the ones that did real work */
     double acc = 0.0;
@@ -1401,6 +1442,7 @@ static int pipecg_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *
   res->its = ctx->h_cg->its; res->reason = ctx->h_cg->reason; res->rnorm = ctx->h_cg->dp; res->rnorm0 = ctx->h_cg->rnorm0;
   res->spmv_ms = 0.f; res->spmv_samples = 0;
   ohp_cg_trace_dump(ctx, "pipecg");
+  res->algo = OHP_ALGO_PIPELINED_2L;
   {
     /* the timed launches are the regular passes from `check_every` on: pass L works while L - 2 < its */
     double acc = 0.0;
@@ -1527,7 +1569,8 @@ __device__ __forceinline__ void pf_gather_totals(const ohp_p2p_dev &pd, double (
   for (int k = 0; k < 3; ++k) t[k] = tot[k];
 }
 
-/* the per-row update, called by the consumer loop with n = (A m)[row] */
+/* the per-row update of the consumer loop: load(row) issues the row's vector operands (before the row is summed, so
+ * that their latency overlaps the gather), store(row, n, operands) applies the update with n = (A m)[row] */
 template <bool JACOBI>
 struct PipeRowUpdate {
   const double *wo;
@@ -1535,24 +1578,31 @@ struct PipeRowUpdate {
   const double *dinv;
   double alpha, beta;
   double g, d, nn;
-  __device__ __forceinline__ void operator()(int i, double n) {
-    const double ro = r[i], woi = wo[i];
-    const double ui = JACOBI ? dinv[i] * ro : ro;
-    const double zi = fma(beta, z[i], n);
-    const double si = fma(beta, s[i], woi);
-    const double pi = fma(beta, p[i], ui);
+  struct Opnd { double ro, wo, z, s, p, x, di; };
+  __device__ __forceinline__ Opnd load(int i) const {
+    Opnd o;
+    o.ro = r[i]; o.wo = wo[i]; o.z = z[i]; o.s = s[i]; o.p = p[i]; o.x = x[i];
+    o.di = JACOBI ? dinv[i] : 1.0;
+    return o;
+  }
+  __device__ __forceinline__ void store(int i, double n, const Opnd &o) {
+    const double ui = JACOBI ? o.di * o.ro : o.ro;
+    const double zi = fma(beta, o.z, n);
+    const double si = fma(beta, o.s, o.wo);
+    const double pi = fma(beta, o.p, ui);
     z[i] = zi; s[i] = si; p[i] = pi;
-    x[i] = fma(alpha, pi, x[i]);
-    const double ri = fma(-alpha, si, ro);
-    const double wi = fma(-alpha, zi, woi);
+    x[i] = fma(alpha, pi, o.x);
+    const double ri = fma(-alpha, si, o.ro);
+    const double wi = fma(-alpha, zi, o.wo);
     r[i] = ri; wn[i] = wi;
-    const double un = JACOBI ? dinv[i] * ri : ri;
-    if (JACOBI) mn[i] = dinv[i] * wi;
+    const double un = JACOBI ? o.di * ri : ri;
+    if (JACOBI) mn[i] = o.di * wi;
     g += ri * un; d += wi * un; nn += un * un;
   }
+  __device__ __forceinline__ void operator()(int i, double n) { const Opnd o = load(i); store(i, n, o); }
 };
 
-template <int S, int NC, class IDX, bool SPLIT, bool JACOBI, int MODE>
+template <int S, int NC, int GR, class IDX, bool SPLIT, bool JACOBI, int MODE>
 __global__ void __launch_bounds__(NC + 32, 1)
 k_pipecg_fused(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colidx, const double *__restrict__ vals,
                const int32_t *__restrict__ tile_row, int n_tiles, const ohp_pipe_vecs v, const ohp_pf_dev f,
@@ -1572,7 +1622,7 @@ k_pipecg_fused(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colid
   const int t1 = (int)(((int64_t)n_tiles * (blockIdx.x + 1)) / gridDim.x);
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 33); mbar_init(empty0 + 8 * s, NC / 32); }
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 33); mbar_init(empty0 + 8 * s, NC / 32 / GR); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -1613,10 +1663,12 @@ k_pipecg_fused(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colid
       pf_sum_parts(f.parts + (size_t)f.rpar * 3 * f.G, f.G, lane, t);
       if (MODE == OHP_MODE_P2P) pf_gather_totals(pd, t, lane);
       if (lane == 0) {
-        cgcg_scalars(me, blockIdx.x == 0 ? f.hist : nullptr, f.hist_cap, t[0], t[1], f.jacobi ? t[2] : t[0]);
-        done = me->done;
-        s_scal[0] = me->alpha; s_scal[1] = me->beta;
-        if (blockIdx.x == 0) { *f.st_host = *me; trace_put(f.trace, TR_SPMV_BEGIN, me->its); }
+        ohp_cg_state loc = *me; /* one round trip for the whole replica, the recurrences then run in registers */
+        cgcg_scalars(&loc, blockIdx.x == 0 ? f.hist : nullptr, f.hist_cap, t[0], t[1], f.jacobi ? t[2] : t[0]);
+        *me = loc;
+        done = loc.done;
+        s_scal[0] = loc.alpha; s_scal[1] = loc.beta;
+        if (blockIdx.x == 0) { *f.st_host = loc; trace_put(f.trace, TR_SPMV_BEGIN, loc.its); }
       }
     }
     if (lane == 0) { s_flag[0] = done; s_flag[1] = 0; }
@@ -1648,9 +1700,11 @@ k_pipecg_fused(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colid
   if (ghost_cta) {
     if (tid < pd.n_nbr) p2p_wait(pd.hflags[pd.rank] + pd.nbr[tid], halo_seq, pd.seq + 2, pd.timeout_ns);
     asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");
-    spmv_consume_emit<S, NC, IDX, SPLIT, true>(rowptr, colidx, vals, xin, vals_s, cols_s, rp_s, full0, empty0, t0, t1, up);
+    if (GR > 1) spmv_consume_groups<S, NC, GR, IDX, true>(rowptr, colidx, vals, xin, vals_s, cols_s, rp_s, full0, empty0, t0, t1, up);
+    else spmv_consume_emit<S, NC, IDX, SPLIT, true>(rowptr, colidx, vals, xin, vals_s, cols_s, rp_s, full0, empty0, t0, t1, up);
   } else {
-    spmv_consume_emit<S, NC, IDX, SPLIT, false>(rowptr, colidx, vals, xin, vals_s, cols_s, rp_s, full0, empty0, t0, t1, up);
+    if (GR > 1) spmv_consume_groups<S, NC, GR, IDX, false>(rowptr, colidx, vals, xin, vals_s, cols_s, rp_s, full0, empty0, t0, t1, up);
+    else spmv_consume_emit<S, NC, IDX, SPLIT, false>(rowptr, colidx, vals, xin, vals_s, cols_s, rp_s, full0, empty0, t0, t1, up);
   }
   /* ---- CTA partials (consumer warps only: named barrier 1) ---- */
   {
@@ -1805,17 +1859,17 @@ static int pf_plan_build(ohp_mesh m, bool p2p) {
   return 0;
 }
 
-template <int S, int NC, class IDX, bool SPLIT, bool JACOBI, int MODE>
+template <int S, int NC, int GR, class IDX, bool SPLIT, bool JACOBI, int MODE>
 static int pf_launch_t(ohp_mat A, const IDX *cols, const ohp_pipe_vecs &v, const ohp_pf_dev &f, const ohp_p2p_dev &pd, int cur, bool pdl) {
   ohp_mesh m = A->mesh;
   ohp_context ctx = m->ctx;
   constexpr int smem = tma_smem_bytes(S, (int)sizeof(IDX));
   static unsigned long long configured_devices = 0ull;
   if (!((configured_devices >> (ctx->device & 63)) & 1ull)) {
-    OHP_CUDA(cudaFuncSetAttribute(k_pipecg_fused<S, NC, IDX, SPLIT, JACOBI, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    OHP_CUDA(cudaFuncSetAttribute(k_pipecg_fused<S, NC, GR, IDX, SPLIT, JACOBI, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured_devices |= 1ull << (ctx->device & 63);
   }
-  OHP_CUDA(ohp_launch(k_pipecg_fused<S, NC, IDX, SPLIT, JACOBI, MODE>, dim3(f.G), dim3(NC + 32), (size_t)smem, ctx->stream, pdl,
+  OHP_CUDA(ohp_launch(k_pipecg_fused<S, NC, GR, IDX, SPLIT, JACOBI, MODE>, dim3(f.G), dim3(NC + 32), (size_t)smem, ctx->stream, pdl,
                       (const int32_t *)m->rowptr, cols, (const double *)A->vals, (const int32_t *)m->tile_row, m->n_tiles, v, f, pd, cur,
                       spmv_pin_tiles(m, f.G, (int)sizeof(IDX))));
   ctx->launches++;
@@ -1825,12 +1879,24 @@ template <bool JACOBI, int MODE>
 static int pf_launch(ohp_mat A, const ohp_pipe_vecs &v, const ohp_pf_dev &f, const ohp_p2p_dev &pd, int cur, bool pdl) {
   ohp_mesh m = A->mesh;
   static const char *idx = getenv("OHP_IDX");
-  const bool split = m->nnz > (int64_t)8 * std::max(1, m->n_owned);
+  static const char *grp = getenv("OHP_PF_GROUPS"); /* "2" / "3": consumer groups on different tiles (A/B runs) */
   const bool i16 = m->col16 && !(idx && idx[0] == '3');
-  if (i16) return split ? pf_launch_t<3, 608, int16_t, true, JACOBI, MODE>(A, m->col16, v, f, pd, cur, pdl)
-                        : pf_launch_t<3, 608, int16_t, false, JACOBI, MODE>(A, m->col16, v, f, pd, cur, pdl);
-  return split ? pf_launch_t<3, 608, int32_t, true, JACOBI, MODE>(A, m->colidx, v, f, pd, cur, pdl)
-               : pf_launch_t<3, 608, int32_t, false, JACOBI, MODE>(A, m->colidx, v, f, pd, cur, pdl);
+  /* Consumer groups on different tiles: the number of stages must be a multiple of the number of groups, so that the
+   * tile that used a stage before (i - S) belongs to the SAME group -- a group that waited for phase k of a stage's
+   * `full` barrier while the barrier was still in phase k - 1 would pass on the parity of phase k - 2.
+   * Measured (1.05 M rows): one group 29.0 us per iteration, two groups 30.7: once the row's vector operands are loaded
+   * before the row is summed the tile loop runs at the L2 throughput limit (~10 TB/s), not at the per-tile latency
+   * chain, so the default stays one group. */
+  if (grp && grp[0] == '2' && i16) return pf_launch_t<4, 576, 2, int16_t, false, JACOBI, MODE>(A, m->col16, v, f, pd, cur, pdl);
+  if (grp && grp[0] == '3') {
+    if (i16) return pf_launch_t<3, 576, 3, int16_t, false, JACOBI, MODE>(A, m->col16, v, f, pd, cur, pdl);
+    return pf_launch_t<3, 576, 3, int32_t, false, JACOBI, MODE>(A, m->colidx, v, f, pd, cur, pdl);
+  }
+  const bool split = m->nnz > (int64_t)8 * std::max(1, m->n_owned);
+  if (i16) return split ? pf_launch_t<3, 608, 1, int16_t, true, JACOBI, MODE>(A, m->col16, v, f, pd, cur, pdl)
+                        : pf_launch_t<3, 608, 1, int16_t, false, JACOBI, MODE>(A, m->col16, v, f, pd, cur, pdl);
+  return split ? pf_launch_t<3, 608, 1, int32_t, true, JACOBI, MODE>(A, m->colidx, v, f, pd, cur, pdl)
+               : pf_launch_t<3, 608, 1, int32_t, false, JACOBI, MODE>(A, m->colidx, v, f, pd, cur, pdl);
 }
 
 static int pipefused_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o, ohp_ksp_result *res, bool p2p) {
@@ -1977,6 +2043,7 @@ static int pipefused_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_option
   res->its = ctx->h_cg->its; res->reason = ctx->h_cg->reason; res->rnorm = ctx->h_cg->dp; res->rnorm0 = ctx->h_cg->rnorm0;
   res->spmv_ms = 0.f; res->spmv_samples = 0;
   ohp_cg_trace_dump(ctx, "pipecg-fused");
+  res->algo = OHP_ALGO_PIPELINED_FUSED;
   {
     double acc = 0.0;
     int used = 0, L = (o->max_it <= check_every) ? 0 : check_every;
@@ -2150,6 +2217,7 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
   cudaEventElapsedTime(&res->total_ms, ev_t0, ev_t1);
   res->spmv_ms = 0.f; res->spmv_samples = 0;
   ohp_cg_trace_dump(ctx, "classic");
+  res->algo = OHP_ALGO_CLASSIC;
   {
     /* only launches that ran before convergence did real work: iteration k is sample k - first_timed */
     double acc = 0.0;

@@ -324,7 +324,7 @@ extern "C" int ohp_snes_solve(ohp_mesh m, int problem, ohp_mat J, ohp_vec u, con
     tm.end(2);
     if (o->ksp_monitor) o->ksp_monitor(o->monitor_ctx, its, std::min(kr.its, ko.history_cap - 1), ko.history, kr.reason);
     kits += kr.its;
-    res->spmv_ms = kr.spmv_ms; res->spmv_samples = kr.spmv_samples;
+    res->spmv_ms = kr.spmv_ms; res->spmv_samples = kr.spmv_samples; res->algo = kr.algo;
     if (kr.reason < 0) { reason = -3; break; }
     /* bt line search: accept lambda when 0.5 g^2 <= 0.5 f^2 + lambda * 1e-4 * initslope */
     SN_TRY(ohp_mat_mult(J, y, w));
