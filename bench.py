@@ -373,14 +373,30 @@ def measure_workload(job, args, workload, steps, warmup, e2e_steps, sampler, wit
     else:
         part, lcells, lcoords = None, cells, coords
 
+    breakdown = {} if os.environ.get("OHP_BENCH_E2E_BREAKDOWN") else None
+
+    def lap(name, t_prev):
+        """opt-in phase timing of the e2e path (synchronises after every phase: diagnostic only, never the reported e2e)"""
+        if breakdown is None:
+            return t_prev
+        ctx.sync()
+        now = time.perf_counter()
+        breakdown[name] = breakdown.get(name, 0.0) + (now - t_prev) * 1e3
+        return now
+
     def build_mesh():
+        t = time.perf_counter()
         m = ohp.Mesh(ctx, lcells, lcoords)
+        t = lap("mesh_create_h2d", t)
         if part is not None:
             # A6 behind the C-ABI: ghost roots from global vertex ids on the device (ohp_ghost_roots_from_gids)
             m.set_ghosts_from_gids(part["ghost_local"], part["ghost_owner"], part["gverts"], vo[part["gverts"]] == rank)
+            t = lap("ghost_roots_from_gids", t)
         m.setup()
+        t = lap("mesh_setup", t)
         if part is not None and os.environ.get("OHP_COMM", "p2p") != "nccl":
-            m.p2p_enable(dist.all_gather_object, world)
+            m.p2p_enable_native()   # CUDA IPC handles all-gathered over the library's own communicator
+            t = lap("p2p_enable", t)
         return m
 
     t0 = time.perf_counter()
@@ -452,18 +468,23 @@ def measure_workload(job, args, workload, steps, warmup, e2e_steps, sampler, wit
         for _ in range(e2e_steps):
             t_one = time.perf_counter()
             m2 = build_mesh()
+            t = time.perf_counter()
             J2, u2 = m2.create_matrix(), m2.create_global_vector()
             m2.project(0, 0, u2)
             r2 = m2.snes_solve(0, J2, u2, ksp=ksp)
+            t = lap("solve", t)
             uh2 = u2.to_host()
             assert r2["reason"] == 3 and np.isfinite(uh2[:8]).all()
+            t = lap("d2h", t)
             J2.destroy(); u2.destroy(); m2.destroy()
+            t = lap("destroy", t)
             e2e_each.append((time.perf_counter() - t_one) * 1e3)
         job.barrier()
         t_e2e = job.max_over_ranks((time.perf_counter() - t0) / e2e_steps)
         e2e = {"value": N / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(lcells.nbytes + lcoords.nbytes),
                "d2h_bytes_per_step": int(info.n_owned * 8), "ms_per_step": t_e2e * 1e3, "steps": e2e_steps,
                "each_step_ms_rank0": e2e_each,
+               **({"breakdown_ms_total_rank0_diagnostic": breakdown} if breakdown else {}),
                "includes": "ohp_mesh_create (H2D of cells+coords from pinned host memory), device numbering + CSR build, "
                            "Newton step, D2H of the solution"}
 

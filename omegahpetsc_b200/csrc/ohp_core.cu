@@ -270,7 +270,7 @@ extern "C" int ohp_mesh_destroy(ohp_mesh m) {
   ohp_pf_plan_free(m->ctx, m->pfplan);
   ohp_halo_free(m->ctx, m->halo);
   ohp_p2p_free(m->ctx, m->p2p);
-  OHP_FREE(m->ctx, m->ghost_cta);
+  OHP_FREE(m->ctx, m->ghost_cta); OHP_FREE(m->ctx, m->ghost_tile); OHP_FREE(m->ctx, m->ghost_cta_w); OHP_FREE(m->ctx, m->cta_tile0);
   delete m;
   return 0;
 }
@@ -489,11 +489,25 @@ __global__ void k_col16(const int32_t *rowptr, const int32_t *colidx, int n_rows
   if (bad) atomicExch(overflow, 1);
 }
 
-/* which CTAs of the persistent SpMV (CTA b owns tiles [n_tiles*b/G, n_tiles*(b+1)/G)) touch ghost columns */
-__global__ void k_ghost_cta(const int32_t *colidx, int64_t nnz, int n_owned, int n_tiles, int tile, uint8_t *flag) {
-  const int64_t k0 = (int64_t)(((int64_t)n_tiles * blockIdx.x) / gridDim.x) * tile;
-  const int64_t k1 = std::min<int64_t>(nnz, (int64_t)(((int64_t)n_tiles * (blockIdx.x + 1)) / gridDim.x) * tile + 8192);
+/* which CTAs of the persistent SpMV touch ghost columns.  CTA b owns tiles [n_tiles*b/G, n_tiles*(b+1)/G), or
+ * [tile0[b], tile0[b+1]) when a partition table is given */
+__global__ void k_ghost_cta(const int32_t *colidx, int64_t nnz, int n_owned, int n_tiles, int tile, uint8_t *flag, const int32_t *tile0) {
+  const int64_t ta = tile0 ? tile0[blockIdx.x] : (((int64_t)n_tiles * blockIdx.x) / gridDim.x);
+  const int64_t tb = tile0 ? tile0[blockIdx.x + 1] : (((int64_t)n_tiles * (blockIdx.x + 1)) / gridDim.x);
+  const int64_t k0 = ta * tile;
+  const int64_t k1 = std::min<int64_t>(nnz, tb * tile + 8192);
   int any = 0; /* + 8192: a row started in the last tile may run on into the next CTA's first tile */
+  for (int64_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) any |= (colidx[k] >= n_owned);
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) flag[blockIdx.x] = any ? 1 : 0;
+}
+
+/* per SpMV tile: does it (or the tail of a row it starts) reference a ghost column?  Used by the dynamically scheduled
+ * SpMV, where the CTA that gets a tile is not known in advance */
+__global__ void k_ghost_tile(const int32_t *colidx, int64_t nnz, int n_owned, int tile, uint8_t *flag) {
+  const int64_t k0 = (int64_t)blockIdx.x * tile;
+  const int64_t k1 = std::min<int64_t>(nnz, k0 + tile + 8192);
+  int any = 0;
   for (int64_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) any |= (colidx[k] >= n_owned);
   any = __syncthreads_or(any);
   if (threadIdx.x == 0) flag[blockIdx.x] = any ? 1 : 0;
@@ -864,7 +878,35 @@ extern "C" int ohp_mesh_setup(ohp_mesh m) {
     const int G = std::max(1, std::min(m->n_tiles, ctx->num_sms));
     OHP_CUDA(OHP_MALLOC(ctx, &m->ghost_cta, ctx->num_sms));
     OHP_CUDA(cudaMemsetAsync(m->ghost_cta, 1, ctx->num_sms, st));
-    k_ghost_cta<<<G, 256, 0, st>>>(m->colidx, m->nnz, m->n_owned, m->n_tiles, kSpmvTile, m->ghost_cta); OHP_CHECK_LAUNCH(ctx);
+    k_ghost_cta<<<G, 256, 0, st>>>(m->colidx, m->nnz, m->n_owned, m->n_tiles, kSpmvTile, m->ghost_cta, nullptr); OHP_CHECK_LAUNCH(ctx);
+    {
+      /* Weighted tile partition for the SpMV of the partitioned CG loops: a CTA that reads ghost columns waits for the
+       * neighbours' halo flags and loads x coherently, which made the strips' first and last CTAs the slowest of every
+       * launch (device timeline at 8 GPUs: 25-29 us against a median of 23); they get kGhostCtaShare of a full share.
+       * The flags are then recomputed for the shifted partition. */
+      static const char *sh_env = getenv("OHP_GHOST_CTA_SHARE"); /* percent (A/B runs); 100 = uniform */
+      const double share = sh_env ? atof(sh_env) / 100.0 : 0.85;
+      std::vector<uint8_t> gc(G);
+      OHP_CUDA(cudaMemcpyAsync(gc.data(), m->ghost_cta, G, cudaMemcpyDeviceToHost, st));
+      OHP_CUDA(cudaStreamSynchronize(st));
+      double total = 0.0;
+      for (int b = 0; b < G; ++b) total += gc[b] ? share : 1.0;
+      std::vector<int32_t> t0(G + 1, 0);
+      double acc = 0.0;
+      for (int b = 0; b < G; ++b) {
+        acc += gc[b] ? share : 1.0;
+        t0[b + 1] = std::max(t0[b], std::min(m->n_tiles, (int)llround((double)m->n_tiles * acc / total)));
+      }
+      t0[G] = m->n_tiles;
+      OHP_CUDA(OHP_MALLOC(ctx, &m->cta_tile0, sizeof(int32_t) * (G + 1)));
+      OHP_CUDA(cudaMemcpyAsync(m->cta_tile0, t0.data(), sizeof(int32_t) * (G + 1), cudaMemcpyHostToDevice, st));
+      OHP_CUDA(OHP_MALLOC(ctx, &m->ghost_cta_w, ctx->num_sms));
+      OHP_CUDA(cudaMemsetAsync(m->ghost_cta_w, 1, ctx->num_sms, st));
+      k_ghost_cta<<<G, 256, 0, st>>>(m->colidx, m->nnz, m->n_owned, m->n_tiles, kSpmvTile, m->ghost_cta_w, m->cta_tile0); OHP_CHECK_LAUNCH(ctx);
+      OHP_CUDA(cudaStreamSynchronize(st)); /* t0 goes out of scope */
+    }
+    OHP_CUDA(OHP_MALLOC(ctx, &m->ghost_tile, m->n_tiles));
+    k_ghost_tile<<<m->n_tiles, 256, 0, st>>>(m->colidx, m->nnz, m->n_owned, kSpmvTile, m->ghost_tile); OHP_CHECK_LAUNCH(ctx);
   }
   {
     std::vector<int32_t> tr(m->n_tiles + 1);
@@ -872,6 +914,18 @@ extern "C" int ohp_mesh_setup(ohp_mesh m) {
     OHP_CUDA(cudaStreamSynchronize(st));
     m->max_tile_rows = 0;
     for (int t = 0; t < m->n_tiles; ++t) m->max_tile_rows = std::max(m->max_tile_rows, tr[t + 1] - tr[t]);
+  }
+  /* can EVERY rank run the TMA-pipelined SpMV?  The CG variants built on it are selected from this global answer, so
+   * that all ranks take the same branch (one all-reduce at set-up) */
+  m->all_tma = m->max_tile_rows <= kSpmvRowCap - 1;
+  if (ctx->nranks > 1 && ctx->comm) {
+    const double bad = m->all_tma ? 0.0 : 1.0;
+    double sum = 0.0;
+    OHP_CUDA(cudaMemcpyAsync(ctx->d_scalars + 12, &bad, sizeof(double), cudaMemcpyHostToDevice, st));
+    OHP_TRY(ohp_allreduce_sum(ctx, ctx->d_scalars + 12, 1));
+    OHP_CUDA(cudaMemcpyAsync(&sum, ctx->d_scalars + 12, sizeof(double), cudaMemcpyDeviceToHost, st));
+    OHP_CUDA(cudaStreamSynchronize(st));
+    m->all_tma = (sum == 0.0);
   }
   m->setup_done = true;
   return 0;

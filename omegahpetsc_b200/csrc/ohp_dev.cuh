@@ -291,6 +291,7 @@ struct ohp_cgcg_epi {
   int nvpart, jacobi, hist_cap;
   double *hist;
   const uint8_t *ghost_cta; /* non-NULL: the SpMV itself waits for the halo, and only in the CTAs flagged here */
+  const int32_t *cta_tile0; /* non-NULL: CTA b owns tiles [cta_tile0[b], cta_tile0[b+1]) instead of the uniform split (the flags above belong to it) */
   int pipe;                 /* pipelined recurrence: no dot product here, the host names the input buffer.  1: an extra
                              * warp of CTA 0 reduces the vector kernel's partials (nvpart x 3), all-reduces them and
                              * advances the scalars WHILE the other warps stream the matrix; 2: nothing to reduce */

@@ -146,6 +146,7 @@ struct ohp_mesh_s {
   int32_t *tile_row; /* n_tiles+1: first row of each nnz tile */
   int32_t n_tiles;
   int32_t max_tile_rows; /* most rows starting inside one tile */
+  bool all_tma;          /* every rank's matrix fits the TMA-pipelined SpMV (max_tile_rows below its row cap) */
   ohp_halo *halo;    /* dof-level halo plan (NULL when serial) */
   ohp_p2p *p2p;      /* NVLink peer mapping (NULL until ohp_mesh_p2p_attach) */
   /* facets (DMPlexInterpolate's edges / faces), built on demand for Plex queries */
@@ -156,6 +157,9 @@ struct ohp_mesh_s {
   std::vector<int32_t> user_label;
   struct ohp_pf_plan *pfplan;   /* tables of the one-launch pipelined CG (ohp_linalg.cu), built on first use */
   struct ohp_fused_plan *fused; /* tables of the fused persistent CG kernel, built on first use (ohp_cg_fused.cu) */
+  int32_t *cta_tile0;  /* weighted tile partition of the SpMV CTAs (G + 1 entries; NULL when serial), with its own ghost flags: */
+  uint8_t *ghost_cta_w;
+  uint8_t *ghost_tile; /* per SpMV tile: 1 if it references ghost columns (NULL when serial) */
   uint8_t *ghost_cta; /* per persistent-SpMV CTA: 1 if its tiles reference ghost columns (NULL when serial) */
 };
 

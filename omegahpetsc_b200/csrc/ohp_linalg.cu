@@ -297,9 +297,12 @@ __device__ __forceinline__ void spmv_consume_emit(const int32_t *__restrict__ ro
     if (!SPLIT) {
       for (int r = rs + tid; r < re; r += NC) {
         const int a = rp[r - rs], b = rp[r - rs + 1];
-        const double sum = row_dot<IDX, COHERENT>(vs, cs, a - base, min(b, lim) - base, x, 0.0, r);
-        if (b > lim) { carry = sum; pend = r; }
-        else emit(r, sum);
+        if (b > lim) { carry = row_dot<IDX, COHERENT>(vs, cs, a - base, lim - base, x, 0.0, r); pend = r; }
+        else {
+          auto opnd = emit.load(r); /* the row's vector operands travel while the row is summed */
+          const double sum = row_dot<IDX, COHERENT>(vs, cs, a - base, b - base, x, 0.0, r);
+          emit.store(r, sum, opnd);
+        }
       }
     } else {
       const int nrows = re - rs;
@@ -391,8 +394,8 @@ k_spmv_tma(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colidx, c
   uint64_t *bars = reinterpret_cast<uint64_t *>(rp_s + S * kTmaRpStride);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int t0 = (int)(((int64_t)n_tiles * blockIdx.x) / gridDim.x);
-  const int t1 = (int)(((int64_t)n_tiles * (blockIdx.x + 1)) / gridDim.x);
+  const int t0 = epi.cta_tile0 ? __ldg(epi.cta_tile0 + blockIdx.x) : (int)(((int64_t)n_tiles * blockIdx.x) / gridDim.x);
+  const int t1 = epi.cta_tile0 ? __ldg(epi.cta_tile0 + blockIdx.x + 1) : (int)(((int64_t)n_tiles * (blockIdx.x + 1)) / gridDim.x);
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 33); mbar_init(empty0 + 8 * s, NC / 32); }
@@ -476,8 +479,153 @@ k_spmv_tma(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colidx, c
   }
 }
 
+
+/* ------------------------------------------------------------------------------------ */
+/* The same SpMV with DYNAMIC tile scheduling (pipelined CG and plain MatMult: no dot      */
+/* product here, so which CTA sums which rows cannot change a rounding).  A device-side     */
+/* timeline of the static kernel at 12 tiles per CTA showed CTAs finishing between 14.0 and   */
+/* 17.3 us with the SAME CTAs slow in every launch (die position, L2 distance): the launch     */
+/* ends with its slowest SM.  Here every CTA starts on a static run of tiles (so that the       */
+/* producer can prefetch before griddepcontrol.wait, as before) worth ~70 % of its share; the    */
+/* rest is handed out in chunks of `chunk` tiles from a counter in HBM that the PRECEDING        */
+/* kernel re-arms.  The producer writes the tile number next to the staged rowptr slice; a        */
+/* negative number ends the CTA.  A row that runs past the last tile of a run is finished from    */
+/* global memory by the thread that carried it (serial CSR order as always).  Halo: a tile that   */
+/* references ghost columns (table built at set-up) makes its CTA wait for the neighbours' flags   */
+/* once and read x coherently for that tile.                                                    */
+/* ------------------------------------------------------------------------------------ */
+struct ohp_dyn_sched { unsigned *counter; int static_tiles, chunk; const uint8_t *ghost_tile; };
+
+template <class IDX, bool COHERENT, int NC>
+__device__ __forceinline__ void spmv_dyn_tile(const int32_t *rp, const double *vs, const IDX *cs, const double *x, double *__restrict__ y,
+                                              int t, double &carry, int &pend) {
+  constexpr int T = kSpmvTile;
+  const int tid = threadIdx.x;
+  const int rs = rp[kSpmvRowCap + 2], re = rp[kSpmvRowCap + 3];
+  const int base = t * T, lim = base + T;
+  if (pend >= 0) {
+    const int end = rp[0];
+    carry = row_dot<IDX, COHERENT>(vs, cs, 0, min(end, lim) - base, x, carry, pend);
+    if (end <= lim) { y[pend] = carry; pend = -1; }
+  }
+  for (int r = rs + tid; r < re; r += NC) {
+    const int a = rp[r - rs], b = rp[r - rs + 1];
+    const double sum = row_dot<IDX, COHERENT>(vs, cs, a - base, min(b, lim) - base, x, 0.0, r);
+    if (b > lim) { carry = sum; pend = r; }
+    else y[r] = sum;
+  }
+}
+
+template <int S, int NC, class IDX>
+__global__ void __launch_bounds__(NC + 64, 1)
+k_spmv_dyn(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colidx, const double *__restrict__ vals, const double *x,
+           double *__restrict__ y, const int32_t *__restrict__ tile_row, int n_tiles, ohp_cg_state *st, int mode,
+           const ohp_p2p_dev pd, const ohp_cgcg_epi epi, const ohp_dyn_sched ds) {
+  constexpr int T = kSpmvTile;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *vals_s = reinterpret_cast<double *>(smem_raw);
+  IDX *cols_s = reinterpret_cast<IDX *>(vals_s + S * T);
+  int32_t *rp_s = reinterpret_cast<int32_t *>(cols_s + S * T);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(rp_s + S * kTmaRpStride);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 33); mbar_init(empty0 + 8 * s, NC / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const bool is_producer = (warp == NC / 32), is_reducer = (warp == NC / 32 + 1);
+  const uint64_t pol_first = l2_policy_evict_first();
+  /* stage i % S of this CTA's i-th tile; t < 0 ends the CTA */
+  auto issue = [&](int i, int t) {
+    const int s = i % S;
+    int32_t *rp = rp_s + s * kTmaRpStride;
+    if (t < 0) {
+      if (lane == 0) { rp[kSpmvRowCap] = -1; mbar_arrive(full0 + 8 * s); }
+      cp_async_mbar_arrive_noinc(full0 + 8 * s);
+      return;
+    }
+    const int rs = __ldg(tile_row + t), re = __ldg(tile_row + t + 1);
+    if (lane == 0) {
+      rp[kSpmvRowCap] = t;
+      mbar_expect_tx(full0 + 8 * s, T * (8 + (int)sizeof(IDX)));
+      tma_load_1d_hint(smem_u32(vals_s + s * T), vals + (size_t)t * T, T * 8, full0 + 8 * s, pol_first);
+      tma_load_1d_hint(smem_u32(cols_s + s * T), colidx + (size_t)t * T, T * (int)sizeof(IDX), full0 + 8 * s, pol_first);
+    }
+    for (int j = lane; j <= re - rs; j += 32) cp_async4(smem_u32(rp + j), rowptr + rs + j);
+    if (lane < 2) cp_async4(smem_u32(rp + kSpmvRowCap + 2 + lane), tile_row + t + lane);
+    cp_async_mbar_arrive_noinc(full0 + 8 * s);
+  };
+  /* static run of this CTA: [ts0, ts1) */
+  const int ts0 = min(n_tiles, (int)blockIdx.x * ds.static_tiles), ts1 = min(n_tiles, ts0 + ds.static_tiles);
+  int issued = 0;
+  if (is_producer) {
+    for (; issued < S && ts0 + issued < ts1; ++issued) issue(issued, ts0 + issued); /* stages are free at kernel start */
+  }
+  pdl_wait();
+  pdl_launch();
+  if (st && st->done) {
+    if (is_producer) for (int i = 0; i < issued; ++i) mbar_wait(full0 + 8 * (i % S), 0);
+    return;
+  }
+  if (is_reducer) {
+    if (st && epi.pipe == 1 && blockIdx.x == 0) pipe_reduce(st, mode, pd, epi, lane);
+    return;
+  }
+  if (is_producer) {
+    int i = issued;
+    for (int t = ts0 + issued; t < ts1; ++t, ++i) {
+      mbar_wait(empty0 + 8 * (i % S), ((i / S) & 1) ^ 1);
+      issue(i, t);
+    }
+    for (;;) {
+      int c0 = 0;
+      if (lane == 0) c0 = (int)atomicAdd(ds.counter, (unsigned)ds.chunk);
+      c0 = __shfl_sync(0xffffffffu, c0, 0);
+      if (c0 >= n_tiles) break;
+      for (int t = c0; t < min(n_tiles, c0 + ds.chunk); ++t, ++i) {
+        mbar_wait(empty0 + 8 * (i % S), ((i / S) & 1) ^ 1);
+        issue(i, t);
+      }
+    }
+    mbar_wait(empty0 + 8 * (i % S), ((i / S) & 1) ^ 1);
+    issue(i, -1);
+    return;
+  }
+  /* ---------------- consumer warps ---------------- */
+  double carry = 0.0;
+  int pend = -1, prev = -2;
+  bool halo_ready = false;
+  for (int i = 0;; ++i) {
+    const int s = i % S;
+    mbar_wait(full0 + 8 * s, (i / S) & 1);
+    const int32_t *rp = rp_s + s * kTmaRpStride;
+    const int t = rp[kSpmvRowCap];
+    if (pend >= 0 && t != prev + 1) { /* the run ended: the carried row's tail is not coming through shared memory */
+      const int end = __ldg(rowptr + pend + 1);
+      carry = row_dot<IDX, true>(vals + (size_t)(prev + 1) * T, colidx + (size_t)(prev + 1) * T, 0, end - (prev + 1) * T, x, carry, pend);
+      y[pend] = carry;
+      pend = -1;
+    }
+    if (t < 0) break;
+    const bool ghost = mode == OHP_MODE_P2P && ds.ghost_tile && ds.ghost_tile[t];
+    if (ghost && !halo_ready) { /* uniform over the consumer warps: the tile number is */
+      if (tid < pd.n_nbr) p2p_wait(pd.hflags[pd.rank] + pd.nbr[tid], pd.seq[1], pd.seq + 2, pd.timeout_ns);
+      asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");
+      halo_ready = true;
+    }
+    if (ghost) spmv_dyn_tile<IDX, true, NC>(rp, vals_s + s * T, cols_s + s * T, x, y, t, carry, pend);
+    else spmv_dyn_tile<IDX, false, NC>(rp, vals_s + s * T, cols_s + s * T, x, y, t, carry, pend);
+    prev = t;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty0 + 8 * s);
+  }
+}
+
 constexpr int kPersistentBelowRows = 400000;
 constexpr int kSingleReductionBelowRows = 1600000;
+constexpr int kPipelinedBelowRows = 1600000;
 static bool spmv_use_tma(ohp_mesh m) { return m->max_tile_rows <= kSpmvRowCap - 1 && m->n_tiles > 0; }
 
 static int spmv_smem_bytes(ohp_mesh m) { return (int)sizeof(double) * (kSpmvTile + std::max(1, m->max_row)); }
@@ -557,6 +705,49 @@ static int spmv_tma_launch(ohp_mat A, const double *x, double *y, ohp_cg_state *
   return spmv_tma_launch_t<S, NC, int32_t>(A, m->colidx, x, y, st, sums, mode, x_alt, pd, epi);
 }
 
+
+/* dynamic schedule of k_spmv_dyn: ~70 % of every CTA's share as a static run, the rest in chunks from the counter */
+static void dyn_sched_params(ohp_mesh m, int num_sms, int *G, int *static_tiles, int *chunk) {
+  *G = std::max(1, std::min(m->n_tiles, num_sms));
+  static const char *fr = getenv("OHP_DYN_STATIC"); /* static share in percent (A/B runs) */
+  const double share = fr ? atof(fr) / 100.0 : 0.7;
+  *static_tiles = (int)(share * (double)m->n_tiles / (double)*G);
+  const int rest = m->n_tiles - *static_tiles * *G;
+  *chunk = std::max(1, std::min(4, rest / (*G * 4)));
+}
+template <int S, int NC, class IDX>
+static int spmv_dyn_launch_t(ohp_mat A, const IDX *cols, const double *x, double *y, ohp_cg_state *st, int mode, const ohp_p2p_dev &pd,
+                             const ohp_cgcg_epi &epi) {
+  ohp_mesh m = A->mesh;
+  ohp_context ctx = m->ctx;
+  constexpr int smem = tma_smem_bytes(S, (int)sizeof(IDX));
+  static unsigned long long configured_devices = 0ull;
+  if (!((configured_devices >> (ctx->device & 63)) & 1ull)) {
+    OHP_CUDA(cudaFuncSetAttribute(k_spmv_dyn<S, NC, IDX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured_devices |= 1ull << (ctx->device & 63);
+  }
+  ohp_dyn_sched ds;
+  int G;
+  dyn_sched_params(m, ctx->num_sms, &G, &ds.static_tiles, &ds.chunk);
+  ds.counter = ctx->d_ticket + 3;
+  ds.ghost_tile = (mode == OHP_MODE_P2P && epi.ghost_cta) ? m->ghost_tile : nullptr;
+  static const char *nopdl = getenv("OHP_NOPDL");
+  if (!st) { /* plain MatMult: nobody armed the counter -> everything comes from it */
+    OHP_CUDA(cudaMemsetAsync(ds.counter, 0, sizeof(unsigned), ctx->stream));
+    ds.static_tiles = 0;
+  }
+  OHP_CUDA(ohp_launch(k_spmv_dyn<S, NC, IDX>, dim3(G), dim3(NC + 64), (size_t)smem, ctx->stream, st != nullptr && mode != OHP_MODE_NCCL && !nopdl,
+                      (const int32_t *)m->rowptr, cols, (const double *)A->vals, x, y, (const int32_t *)m->tile_row, m->n_tiles, st, mode, pd, epi, ds));
+  OHP_CHECK_LAUNCH(ctx);
+  return 0;
+}
+static int spmv_dyn_launch(ohp_mat A, const double *x, double *y, ohp_cg_state *st, int mode, const ohp_p2p_dev &pd, const ohp_cgcg_epi &epi) {
+  ohp_mesh m = A->mesh;
+  static const char *idx = getenv("OHP_IDX");
+  if (m->col16 && !(idx && idx[0] == '3')) return spmv_dyn_launch_t<3, 608, int16_t>(A, m->col16, x, y, st, mode, pd, epi);
+  return spmv_dyn_launch_t<3, 608, int32_t>(A, m->colidx, x, y, st, mode, pd, epi);
+}
+
 /* y = A x on the context stream; with `st` the (x, y) dot and the CG scalar update are fused in */
 static int spmv_enqueue(ohp_mat A, const double *x, double *y, ohp_cg_state *st, double *sums, int mode,
                         const double *x_alt, const ohp_p2p_dev &pd, const ohp_cgcg_epi &epi = ohp_cgcg_epi{}) {
@@ -565,6 +756,11 @@ static int spmv_enqueue(ohp_mat A, const double *x, double *y, ohp_cg_state *st,
   static const char *force = getenv("OHP_SPMV"); /* "stream" forces the fallback kernel; "0".."5" pick a TMA config (A/B runs) */
   /* a rank that owns no rows still runs the pipelined solver's reducer warp, which lives in the TMA kernel's CTA 0 */
   const bool tma = (spmv_use_tma(m) || (epi.pipe && m->n_tiles == 0)) && !(force && force[0] == 's');
+  /* OHP_DYN=1: dynamically scheduled tiles in the pipelined solver.  Measured SLOWER than the static partition (1.05 M rows:
+   * 36.2 vs 32.5 us per iteration with a 70 % static share, 34.8 with 85 %): the scattered tail of tiles and the counter
+   * round trips cost more than the 14.0-17.3 us spread between CTAs that it removes.  Kept for A/B runs. */
+  static const char *dyn = getenv("OHP_DYN");
+  if (tma && epi.pipe && dyn && dyn[0] == '1' && !(force && force[0] >= '0' && force[0] <= '9')) return spmv_dyn_launch(A, x, y, st, mode, pd, epi);
   if (tma) {
     const int cfg = (force && force[0] >= '0' && force[0] <= '9') ? force[0] - '0' : 0;
     switch (cfg) {
@@ -1095,7 +1291,8 @@ static int cgcg_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o,
   static const char *nooverlap = getenv("OHP_NOOVERLAP");
   const bool overlap = p2p && spmv_use_tma(m) && m->ghost_cta && !nooverlap && !getenv("OHP_SPMV");
   const int wait_in_vec = overlap ? 0 : 1;
-  epi.ghost_cta = overlap ? m->ghost_cta : nullptr;
+  epi.ghost_cta = overlap ? (m->cta_tile0 ? m->ghost_cta_w : m->ghost_cta) : nullptr;
+  epi.cta_tile0 = overlap ? m->cta_tile0 : nullptr;
   static const char *nopdl = getenv("OHP_NOPDL");
   const bool pdl = !nopdl;
   const int check_every = o->check_every > 0 ? o->check_every : 50;
@@ -1177,7 +1374,7 @@ static int cgcg_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o,
 /* 2.8e-8 |b| after 5454 iterations although the recurred norm met rtol = 1e-9).  So every         */
 /* kPipeReplaceEvery iterations one pass RECOMPUTES them (the residual-replacement form of         */
 /* Cools & Vanroose): p = u + beta p and x += alpha p as usual, then s = A p, z = A M^-1 s,         */
-/* r = b - A x, w = A M^-1 r with four extra SpMVs -- 2 % more SpMVs at a period of 200, after       */
+/* r = b - A x, w = A M^-1 r with four extra SpMVs -- 1 % more SpMVs at a period of 400, after       */
 /* which iteration counts and true residuals match classic CG (tests/, bench check object).       */
 /*                                                                                               */
 /* The host knows the pass number L (the device only knows `done`), so each launch is told what    */
@@ -1189,7 +1386,7 @@ static int cgcg_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o,
 /* A push into a buffer is safe because the neighbour's SpMV that last read it completed before the */
 /* neighbour's previous push, which this rank's previous SpMV has waited for.                      */
 /* ------------------------------------------------------------------------------------ */
-constexpr int kPipeReplaceEvery = 200;
+constexpr int kPipeReplaceEvery = 400;
 enum { PK_INIT = 0, PK_TAKE_W = 1, PK_ITER = 2, PK_PX = 3, PK_STAGE_S = 4, PK_STAGE_X = 5, PK_NEW_R = 6, PK_STAGE_P = 7 };
 struct ohp_pipe_vecs {
   double *M0, *M1;   /* SpMV input m = M^-1 w (the NVLink-exported buffers on a partitioned run) */
@@ -1197,6 +1394,8 @@ struct ohp_pipe_vecs {
   double *Z0, *Z1;
   double *r, *s, *p, *x;
   const double *nb, *b, *dinv;
+  unsigned *tcnt;    /* tile counter of the dynamically scheduled SpMV that follows: re-armed here (NULL = none) */
+  unsigned tinit;
 };
 
 /* the value pass `kind` stages into the SpMV input buffer for dof l: computed from arrays that no block writes in that
@@ -1223,6 +1422,7 @@ k_pipecg_vec(const ohp_pipe_vecs v, int n, const ohp_cg_state *st, double *vpart
              unsigned *halo_ticket, int wait_here, const ohp_trace trace, int kind, int cur) {
   pdl_wait();
   pdl_launch();
+  if (v.tcnt && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *v.tcnt = v.tinit; /* the previous SpMV has completed */
   if (st->done) return;
   if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) trace_put(trace, TR_VEC_BEGIN, st->its);
   const double alpha = st->alpha, beta = st->beta;
@@ -1347,6 +1547,12 @@ static int pipecg_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *
   } else { v.W0 = v.M0; v.W1 = v.M1; }
   v.Z0 = A->z; v.Z1 = A->z1;
   v.r = A->r; v.s = A->s; v.p = A->p; v.x = x->d; v.nb = A->w; v.b = b->d; v.dinv = A->dinv;
+  {
+    int G_, st_, ch_;
+    dyn_sched_params(m, ctx->num_sms, &G_, &st_, &ch_);
+    v.tcnt = (getenv("OHP_DYN") && getenv("OHP_DYN")[0] == '1') ? ctx->d_ticket + 3 : nullptr;
+    v.tinit = (unsigned)(G_ * st_);
+  }
   double *hist = nullptr;
   int hist_cap = 0;
   if (o->history && o->history_cap > 0) {
@@ -1378,7 +1584,8 @@ static int pipecg_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *
   static const char *nooverlap = getenv("OHP_NOOVERLAP");
   const bool overlap = p2p && m->ghost_cta && !nooverlap;
   const int wait_in_vec = overlap ? 0 : 1;
-  epi.ghost_cta = overlap ? m->ghost_cta : nullptr;
+  epi.ghost_cta = overlap ? (m->cta_tile0 ? m->ghost_cta_w : m->ghost_cta) : nullptr;
+  epi.cta_tile0 = overlap ? m->cta_tile0 : nullptr;
   static const char *nopdl = getenv("OHP_NOPDL");
   const bool pdl = !nopdl;
   static const char *rr_env = getenv("OHP_PIPE_RR"); /* replacement period (A/B runs); 0 = never */
@@ -1658,6 +1865,7 @@ k_pipecg_fused(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colid
   ohp_cg_state *me = f.rep + blockIdx.x;
   if (warp == 0) {
     int done = me->done;
+    if (lane == 0 && f.trace.buf) trace_put(f.trace, TR_VEC_BEGIN, me->its + (me->x_pending ? 1 : 0));
     if (!done) {
       double t[3];
       pf_sum_parts(f.parts + (size_t)f.rpar * 3 * f.G, f.G, lane, t);
@@ -1668,7 +1876,8 @@ k_pipecg_fused(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colid
         *me = loc;
         done = loc.done;
         s_scal[0] = loc.alpha; s_scal[1] = loc.beta;
-        if (blockIdx.x == 0) { *f.st_host = loc; trace_put(f.trace, TR_SPMV_BEGIN, loc.its); }
+        if (blockIdx.x == 0) *f.st_host = loc;
+        trace_put(f.trace, TR_SPMV_BEGIN, loc.its);
       }
     }
     if (lane == 0) { s_flag[0] = done; s_flag[1] = 0; }
@@ -1726,8 +1935,22 @@ k_pipecg_fused(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colid
       }
     }
   }
-  if (blockIdx.x == 0 && tid == 0) trace_put(f.trace, TR_SPMV_CTA_DONE, me->its);
+  if (tid == 0) trace_put(f.trace, TR_SPMV_CTA_DONE, me->its);
   if (MODE != OHP_MODE_P2P) return;
+  /* ---- rank total for the other ranks: the last CTA to arrive adds the G partials and posts them.  Taken BEFORE the halo push:
+   * the push's system-scope fence and the NVLink round trip (5-8 us in the boundary CTAs) then overlap the all-reduce ---- */
+  if (warp == 0) {
+    int last = 0;
+    if (lane == 0) { __threadfence(); last = (atomicInc(f.cnt + 1, (unsigned)(f.G - 1)) == (unsigned)(f.G - 1)); }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+      __threadfence();
+      double t[3];
+      pf_sum_parts(f.parts + (size_t)(f.rpar ^ 1) * 3 * f.G, f.G, lane, t);
+      pf_post_total(pd, t, lane);
+      if (lane == 0) trace_put(f.trace, TR_AR_POSTED, me->its);
+    }
+  }
   /* ---- halo: push w' (m') of the rows the neighbours ghost, publish when every contributor has arrived ---- */
   if (contrib) {
     /* a neighbour may still be READING the tail this push overwrites unless its own previous push has been seen */
@@ -1753,19 +1976,6 @@ k_pipecg_fused(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colid
         sq = __shfl_sync(0xffffffffu, sq, 0);
         if (lane < pd.n_nbr) st_release_sys(pd.hflags[pd.nbr[lane]] + pd.rank, sq);
       }
-    }
-  }
-  /* ---- rank total for the other ranks: the last CTA to arrive adds the G partials and posts them ---- */
-  if (warp == 0) {
-    int last = 0;
-    if (lane == 0) { __threadfence(); last = (atomicInc(f.cnt + 1, (unsigned)(f.G - 1)) == (unsigned)(f.G - 1)); }
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (last) {
-      __threadfence();
-      double t[3];
-      pf_sum_parts(f.parts + (size_t)(f.rpar ^ 1) * 3 * f.G, f.G, lane, t);
-      pf_post_total(pd, t, lane);
-      if (lane == 0) trace_put(f.trace, TR_AR_POSTED, me->its);
     }
   }
 }
@@ -1927,6 +2137,12 @@ static int pipefused_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_option
   } else { v.W0 = v.M0; v.W1 = v.M1; }
   v.Z0 = v.Z1 = A->z; /* z is updated in place here (row-local) */
   v.r = A->r; v.s = A->s; v.p = A->p; v.x = x->d; v.nb = A->w; v.b = b->d; v.dinv = A->dinv;
+  {
+    int G_, st_, ch_;
+    dyn_sched_params(m, ctx->num_sms, &G_, &st_, &ch_);
+    v.tcnt = (getenv("OHP_DYN") && getenv("OHP_DYN")[0] == '1') ? ctx->d_ticket + 3 : nullptr;
+    v.tinit = (unsigned)(G_ * st_);
+  }
   double *hist = nullptr;
   int hist_cap = 0;
   if (o->history && o->history_cap > 0) {
@@ -1956,7 +2172,8 @@ static int pipefused_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_option
   static const char *nooverlap = getenv("OHP_NOOVERLAP");
   const bool overlap = p2p && m->ghost_cta && !nooverlap;
   const int wait_in_vec = overlap ? 0 : 1;
-  epi.ghost_cta = overlap ? m->ghost_cta : nullptr;
+  epi.ghost_cta = overlap ? (m->cta_tile0 ? m->ghost_cta_w : m->ghost_cta) : nullptr;
+  epi.cta_tile0 = overlap ? m->cta_tile0 : nullptr;
   static const char *nopdl = getenv("OHP_NOPDL");
   const bool pdl = !nopdl;
   static const char *rr_env = getenv("OHP_PIPE_RR");
@@ -2092,14 +2309,28 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
     const bool feasible_pipe = (spmv_use_tma(m) || m->n_tiles == 0) && (ctx->nranks == 1 ? n > 0 : can_p2p);
     if (o->ksp_type == OHP_KSP_PIPECG && n == 0 && ctx->nranks == 1) { res->its = 0; res->reason = 3; res->rnorm = res->rnorm0 = 0.0; res->spmv_ms = res->total_ms = 0.f; res->spmv_samples = 0; return 0; }
     if (o->ksp_type == OHP_KSP_PIPECG && !feasible_pipe) OHP_FAIL(OHP_ERR_SUP, "ohp_ksp_cg: -ksp_type pipecg needs the TMA SpMV and, on a partitioned run, the NVLink peer transport");
-    /* OHP_CG=pipecg2: the two-launch form of the pipelined recurrence (A/B runs); pipecg / -ksp_type pipecg: one launch per iteration */
-    if (force && !strcmp(force, "pipecg2") && feasible_pipe) return pipecg_solve(A, b, x, o, res, can_p2p);
-    if ((o->ksp_type == OHP_KSP_PIPECG || (force && force[0] == 'p' && force[1] == 'i')) && feasible_pipe) return pipefused_solve(A, b, x, o, res, can_p2p);
+    /* the pipelined recurrence has two forms: one launch per iteration (vector update fused into the SpMV: fewest bytes and
+     * kernel boundaries, but the dot products are needed at the start of the next launch, so across ranks the all-reduce is
+     * exposed) and two launches (the all-reduce hides behind the SpMV).  Measured on the 16 M-triangle box: one GPU at
+     * 1.05 M rows 29.0 vs 32.5 us per iteration; 8 GPUs 49.5 vs 38.4.  -ksp_type pipecg picks by the number of ranks;
+     * OHP_CG=pipecg1 / pipecg2 force a form (A/B runs). */
+    const bool want_pipe = o->ksp_type == OHP_KSP_PIPECG || (force && force[0] == 'p' && force[1] == 'i');
+    if (want_pipe && feasible_pipe) {
+      bool one_launch = ctx->nranks == 1;
+      if (force && !strcmp(force, "pipecg1")) one_launch = true;
+      if (force && !strcmp(force, "pipecg2")) one_launch = false;
+      return one_launch ? pipefused_solve(A, b, x, o, res, can_p2p) : pipecg_solve(A, b, x, o, res, can_p2p);
+    }
     if (persistent) return ohp_cg_persistent_solve(A, b, x, o, res, can_p2p);
     /* single-reduction recurrence in two launches: default for partitioned runs over NVLink peer memory (one
      * all-reduce and one kernel boundary fewer per iteration); OHP_CG=cgcg forces it on one GPU */
     /* every rank must take the same branch: decide on GLOBAL quantities only (a rank may own no rows at all) */
     const int64_t rows_per_rank = m->n_global / std::max(1, ctx->nranks);
+    /* strong-scaling regime (measured at 1.05 M rows per rank, 8 GPUs: classic 3 launches 58, single-reduction 48.8,
+     * pipelined two-launch 38.4 us per iteration): reductions and rank skew must be off the critical path */
+    bool pipe2 = can_p2p && m->all_tma && rows_per_rank < kPipelinedBelowRows;
+    if (force && force[0] == 'c') pipe2 = false;
+    if (pipe2) return pipecg_solve(A, b, x, o, res, can_p2p);
     bool cgcg = can_p2p && rows_per_rank < kSingleReductionBelowRows; /* measured crossover: 0.145 vs 0.141 ms at 4.2 M rows/rank, 0.056 vs 0.068 at 1.05 M */
     if (force && force[0] == 'c' && force[1] == 'l') cgcg = false;                          /* classic */
     if (force && force[0] == 'c' && force[1] == 'g') cgcg = (ctx->nranks == 1 || can_p2p);  /* cgcg */
@@ -2154,7 +2385,8 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
   const int wait_in_vec = overlap ? 0 : 1;
   ohp_cgcg_epi cepi;
   memset(&cepi, 0, sizeof(cepi));
-  cepi.ghost_cta = overlap ? m->ghost_cta : nullptr;
+  cepi.ghost_cta = overlap ? (m->cta_tile0 ? m->ghost_cta_w : m->ghost_cta) : nullptr;
+  cepi.cta_tile0 = overlap ? m->cta_tile0 : nullptr;
   cepi.trace = ohp_cg_trace_open(ctx);
   if (p2p) OHP_TRY(ohp_p2p_entry_barrier(m));
   const int nhalo = p2p ? std::max(1, std::min(16, (pd.soff[pd.n_nbr] + 255) / 256)) : 0;
