@@ -257,6 +257,18 @@ typedef struct {
   void *stream;                /* cudaStream_t                                          */
   const uint8_t *owned_dev;    /* n_verts: 1 if this rank owns the vertex               */
   int32_t n_partials;          /* L2 diff: out_dev receives this many per-block partial sums of the squared error */
+  /* cell-parallel assembly ("patches", csrc/ohp_patch.cu): blocks of patch_rows rows that are close in space, with the
+   * cells of their stars and the vertices of those cells listed once in patch-local 16-bit ids.  n_patches == 0: the
+   * row kernels walk the vertex stars instead. */
+  int32_t n_patches, patch_rows, patch_max_cells, patch_max_verts, max_row;
+  const int32_t *prow_dev;      /* n_patches*patch_rows: row of each patch slot (-1 = padding)                       */
+  const int32_t *pstar_ptr_dev; /* n_patches*patch_rows + 1: (row, cell) incidences of each slot, ascending cell order */
+  const uint16_t *pstar_dev;    /* per incidence: patch-local cell << 2 | corner                                     */
+  const uint8_t *pslot_dev;     /* (dim+1) per incidence: column slot of the cell's corners in the row, 255 = none   */
+  const int32_t *pcell_ptr_dev; /* n_patches + 1                                                                      */
+  const uint16_t *pconn_dev;    /* (dim+1) per patch cell: patch-local vertex ids                                    */
+  const int32_t *pvert_ptr_dev; /* n_patches + 1                                                                      */
+  const int32_t *pvert_dev;     /* global (rank-local) vertex of each patch vertex                                   */
 } ohp_assembly_view;
 
 typedef int (*ohp_assembly_launcher)(const ohp_assembly_view *view);

@@ -418,14 +418,249 @@ __global__ void __launch_bounds__(256) k_l2_diff(const ohp_assembly_view vw) {
   }
 }
 
+
+/* ------------------------------------------------------------------------------------ */
+/* Cell-parallel assembly over "patches" (tables built by csrc/ohp_patch.cu at set-up).     */
+/* The row kernels above recompute a cell once per incident row (3x per triangle, 4x per     */
+/* tetrahedron) and were FP64-issue bound at 0.20 of the HBM roofline.  A patch is a block of */
+/* rows that are close in space together with the cells of their stars and the vertices of    */
+/* those cells, each listed ONCE: the block stages the patch's vertex coordinates and          */
+/* solution values in shared memory (one coalesced pass over the vertex list), one thread per   */
+/* cell computes the whole element vector / matrix into shared memory (connectivity read as     */
+/* 16-bit patch-local ids), and one thread per row adds up its star from there in ascending     */
+/* cell order -- PETSc's cell-loop order, the same order and the same per-entry arithmetic as   */
+/* the row kernels, so the values are bit-identical to theirs: no atomics, no colouring.        */
+/* ------------------------------------------------------------------------------------ */
+constexpr int kPatchThreads = 128;
+
+/* all rows of the element vector at once: Fe[b] = sum_q w_q detJ ( phi_b f0 + grad(phi_b) . f1 ), entry by entry the
+ * arithmetic of cell_residual_entry */
+template <int DIM, class P>
+__device__ __forceinline__ void cell_residual_all(const double (&X)[DIM + 1][DIM], const double (&ue)[DIM + 1], double (&fe)[DIM + 1]) {
+  constexpr int NC = DIM + 1;
+  const int uOff[2] = {0, 1}, uOff_x[2] = {0, DIM};
+  CellGeom<DIM> g;
+  cell_geometry<DIM>(X, g);
+  double ux[DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) s += g.G[j][d] * ue[j];
+    ux[d] = s;
+  }
+#pragma unroll
+  for (int b = 0; b < NC; ++b) fe[b] = 0.0;
+#pragma unroll
+  for (int q = 0; q < Quadrature<DIM>::NQ; ++q) {
+    double phi[NC], xq[DIM], uq = 0.0;
+    p1_basis<DIM>(q, phi);
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      double s = g.v0[d];
+#pragma unroll
+      for (int f = 0; f < DIM; ++f) s += g.J[d * DIM + f] * (Quadrature<DIM>::xi(q, f) + 1.0);
+      xq[d] = s;
+    }
+#pragma unroll
+    for (int j = 0; j < NC; ++j) uq += phi[j] * ue[j];
+    double f0[1] = {0.0}, f1[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) f1[d] = 0.0;
+    P::f0(DIM, 1, 0, uOff, uOff_x, &uq, nullptr, ux, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, xq, 0, nullptr, f0);
+    P::f1(DIM, 1, 0, uOff, uOff_x, &uq, nullptr, ux, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, xq, 0, nullptr, f1);
+    const double w = g.detJ * Quadrature<DIM>::w(q);
+#pragma unroll
+    for (int b = 0; b < NC; ++b) {
+      double s = phi[b] * (f0[0] * w);
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) s += g.G[b][d] * (f1[d] * w);
+      fe[b] += s;
+    }
+  }
+}
+
+/* the whole element matrix: Ke[b][j] = detJ * G_b^T (sum_q w_q g3_q) G_j, entry by entry the arithmetic of cell_jacobian_row */
+template <int DIM, class P>
+__device__ __forceinline__ void cell_jacobian_all(const double (&X)[DIM + 1][DIM], const double (&ue)[DIM + 1], double *ke /* NC*NC */) {
+  constexpr int NC = DIM + 1;
+  const int uOff[2] = {0, 1}, uOff_x[2] = {0, DIM};
+  CellGeom<DIM> g;
+  cell_geometry<DIM>(X, g);
+  double ux[DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) {
+    double s = 0.0;
+    if (P::kJacobianUsesU) {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) s += g.G[j][d] * ue[j];
+    }
+    ux[d] = s;
+  }
+  double S[DIM * DIM];
+#pragma unroll
+  for (int i = 0; i < DIM * DIM; ++i) S[i] = 0.0;
+#pragma unroll
+  for (int q = 0; q < Quadrature<DIM>::NQ; ++q) {
+    double xq[DIM], uq = 0.0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      double s = g.v0[d];
+#pragma unroll
+      for (int f = 0; f < DIM; ++f) s += g.J[d * DIM + f] * (Quadrature<DIM>::xi(q, f) + 1.0);
+      xq[d] = s;
+    }
+    if (P::kJacobianUsesU) {
+      double phi[NC];
+      p1_basis<DIM>(q, phi);
+#pragma unroll
+      for (int j = 0; j < NC; ++j) uq += phi[j] * ue[j];
+    }
+    double g3[DIM * DIM];
+#pragma unroll
+    for (int i = 0; i < DIM * DIM; ++i) g3[i] = 0.0;
+    P::g3(DIM, 1, 0, uOff, uOff_x, &uq, nullptr, ux, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, 0.0, xq, 0, nullptr, g3);
+    const double w = Quadrature<DIM>::w(q);
+#pragma unroll
+    for (int i = 0; i < DIM * DIM; ++i) S[i] += w * g3[i];
+  }
+#pragma unroll
+  for (int b = 0; b < NC; ++b) {
+    double t[DIM];
+#pragma unroll
+    for (int e2 = 0; e2 < DIM; ++e2) {
+      double s = 0.0;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) s += g.G[b][d] * S[d * DIM + e2];
+      t[e2] = g.detJ * s;
+    }
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int e2 = 0; e2 < DIM; ++e2) s += t[e2] * g.G[j][e2];
+      ke[b * NC + j] = s;
+    }
+  }
+}
+
+template <int DIM, class P, bool JAC>
+__global__ void __launch_bounds__(kPatchThreads) k_assemble_patch(const ohp_assembly_view vw) {
+  constexpr int NC = DIM + 1, EN = JAC ? NC * NC : NC;
+  constexpr bool NEED_U = JAC ? P::kJacobianUsesU : true;
+  extern __shared__ double sm[];
+  double *Xs = sm;                                   /* patch_max_verts x DIM */
+  double *us = Xs + (size_t)vw.patch_max_verts * DIM; /* patch_max_verts */
+  double *E = us + vw.patch_max_verts;               /* patch_max_cells x EN */
+  double *acc = E + (size_t)vw.patch_max_cells * EN; /* JAC: patch_rows x max_row */
+  const int p = blockIdx.x, R = vw.patch_rows, tid = threadIdx.x;
+  const int w0 = __ldg(vw.pvert_ptr_dev + p), nv = __ldg(vw.pvert_ptr_dev + p + 1) - w0;
+  const int c0 = __ldg(vw.pcell_ptr_dev + p), nu = __ldg(vw.pcell_ptr_dev + p + 1) - c0;
+  /* 1. the patch's vertices, once */
+  for (int i = tid; i < nv; i += kPatchThreads) {
+    const int gv = __ldg(vw.pvert_dev + w0 + i);
+    double x[DIM];
+    if constexpr (DIM == 2) {
+      const double2 xy = __ldg(reinterpret_cast<const double2 *>(vw.coords_dev) + gv);
+      x[0] = xy.x; x[1] = xy.y;
+    } else {
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) x[d] = __ldg(vw.coords_dev + (size_t)gv * DIM + d);
+    }
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) Xs[i * DIM + d] = x[d];
+    if (NEED_U) {
+      const int l = __ldg(vw.lidx_dev + gv);
+      double val = 0.0;
+      if (l >= 0) val = __ldg(vw.u_dev + l);
+      else P::bc(DIM, 0.0, x, 1, &val, nullptr);
+      us[i] = val;
+    }
+  }
+  __syncthreads();
+  /* 2. every cell of the patch, once */
+  for (int c = tid; c < nu; c += kPatchThreads) {
+    double X[NC][DIM], ue[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const int lv = (int)__ldg(vw.pconn_dev + (size_t)(c0 + c) * NC + j);
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) X[j][d] = Xs[lv * DIM + d];
+      ue[j] = NEED_U ? us[lv] : 0.0;
+    }
+    if (JAC) {
+      double ke[NC * NC];
+      cell_jacobian_all<DIM, P>(X, ue, ke);
+#pragma unroll
+      for (int k = 0; k < NC * NC; ++k) E[(size_t)c * EN + k] = ke[k];
+    } else {
+      double fe[NC];
+      cell_residual_all<DIM, P>(X, ue, fe);
+#pragma unroll
+      for (int k = 0; k < NC; ++k) E[(size_t)c * EN + k] = fe[k];
+    }
+  }
+  __syncthreads();
+  /* 3. every row adds up its star in ascending cell order */
+  if (tid >= R) return;
+  const int slot_i = p * R + tid;
+  const int row = __ldg(vw.prow_dev + slot_i);
+  if (row < 0) return;
+  const int e0 = __ldg(vw.pstar_ptr_dev + slot_i), e1 = __ldg(vw.pstar_ptr_dev + slot_i + 1);
+  if (!JAC) {
+    double a = 0.0;
+    for (int e = e0; e < e1; ++e) {
+      const int code = (int)__ldg(vw.pstar_dev + e);
+      a += E[(size_t)(code >> 2) * NC + (code & 3)];
+    }
+    vw.out_dev[row] = a;
+  } else {
+    const int k0 = __ldg(vw.rowptr_dev + row), len = __ldg(vw.rowptr_dev + row + 1) - k0;
+    double *a = acc + (size_t)tid * vw.max_row;
+    for (int k = 0; k < len; ++k) a[k] = 0.0;
+    for (int e = e0; e < e1; ++e) {
+      const int code = (int)__ldg(vw.pstar_dev + e);
+      const double *ke = E + ((size_t)(code >> 2) * NC + (code & 3)) * NC;
+      const uint8_t *sl = vw.pslot_dev + (size_t)e * NC;
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        const int slot = __ldg(sl + j);
+        if (slot != 255) a[slot] += ke[j];
+      }
+    }
+    for (int k = 0; k < len; ++k) vw.out_dev[k0 + k] = a[k];
+  }
+}
+
+template <int DIM, class P, bool JAC> int launch_patch(const ohp_assembly_view *vw, bool *used) {
+  constexpr int NC = DIM + 1, EN = JAC ? NC * NC : NC;
+  *used = false;
+  if (vw->n_patches <= 0 || vw->patch_rows > kPatchThreads) return 0;
+  const size_t smem = sizeof(double) * ((size_t)vw->patch_max_verts * (DIM + 1) + (size_t)vw->patch_max_cells * EN +
+                                        (JAC ? (size_t)vw->patch_rows * vw->max_row : 0));
+  if (smem > 200 * 1024) return 0; /* very irregular patches: the row kernels handle them */
+  if (smem > 48 * 1024) {
+    if (cudaFuncSetAttribute(k_assemble_patch<DIM, P, JAC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return OHP_ERR_LIB;
+  }
+  k_assemble_patch<DIM, P, JAC><<<vw->n_patches, kPatchThreads, smem, (cudaStream_t)vw->stream>>>(*vw);
+  *used = true;
+  return cudaGetLastError() == cudaSuccess ? 0 : OHP_ERR_LIB;
+}
+
 template <int DIM, class P> int launch_residual(const ohp_assembly_view *vw) {
   if (vw->n_rows <= 0) return 0;
+  bool used = false;
+  const int rc = launch_patch<DIM, P, false>(vw, &used);
+  if (rc || used) return rc;
   const int bs = 128;
   k_residual_rows<DIM, P><<<(vw->n_rows + bs - 1) / bs, bs, 0, (cudaStream_t)vw->stream>>>(*vw);
   return cudaGetLastError() == cudaSuccess ? 0 : OHP_ERR_LIB;
 }
 template <int DIM, class P> int launch_jacobian(const ohp_assembly_view *vw) {
   if (vw->n_rows <= 0) return 0;
+  bool used = false;
+  const int rc = launch_patch<DIM, P, true>(vw, &used);
+  if (rc || used) return rc;
   k_jacobian_rows<DIM, P><<<(vw->n_rows + kAsmThreads - 1) / kAsmThreads, kAsmThreads, kAsmAccCap * sizeof(double),
                             (cudaStream_t)vw->stream>>>(*vw);
   return cudaGetLastError() == cudaSuccess ? 0 : OHP_ERR_LIB;

@@ -268,6 +268,7 @@ extern "C" int ohp_mesh_destroy(ohp_mesh m) {
   OHP_FREE(m->ctx, m->facet_verts); OHP_FREE(m->ctx, m->facet_support); OHP_FREE(m->ctx, m->cell_facets);
   ohp_fused_plan_free(m->ctx, m->fused);
   ohp_pf_plan_free(m->ctx, m->pfplan);
+  ohp_patch_plan_free(m->ctx, m->patch);
   ohp_halo_free(m->ctx, m->halo);
   ohp_p2p_free(m->ctx, m->p2p);
   OHP_FREE(m->ctx, m->ghost_cta); OHP_FREE(m->ctx, m->ghost_tile); OHP_FREE(m->ctx, m->ghost_cta_w); OHP_FREE(m->ctx, m->cta_tile0);
@@ -927,6 +928,7 @@ extern "C" int ohp_mesh_setup(ohp_mesh m) {
     OHP_CUDA(cudaStreamSynchronize(st));
     m->all_tma = (sum == 0.0);
   }
+  OHP_TRY(ohp_patch_plan_build(m)); /* cell-parallel assembly tables; leaves m->patch NULL when a limit is exceeded */
   m->setup_done = true;
   return 0;
 }
@@ -1001,5 +1003,12 @@ int ohp_assembly_view_make(ohp_mesh m, const double *u, double *out, ohp_assembl
   vw->slot_dev = m->slot; vw->rowptr_dev = m->rowptr; vw->u_dev = u; vw->out_dev = out;
   vw->stream = (void *)m->ctx->stream;
   vw->owned_dev = m->owned; vw->n_partials = 0;
+  vw->n_patches = 0; vw->max_row = m->max_row;
+  if (m->patch) {
+    const ohp_patch_plan *pl = m->patch;
+    vw->n_patches = pl->n_patches; vw->patch_rows = pl->R; vw->patch_max_cells = pl->max_cells; vw->patch_max_verts = pl->max_verts;
+    vw->prow_dev = pl->prow; vw->pstar_ptr_dev = pl->pstar_ptr; vw->pstar_dev = pl->pstar; vw->pslot_dev = pl->pslot;
+    vw->pcell_ptr_dev = pl->pcell_ptr; vw->pconn_dev = pl->pconn; vw->pvert_ptr_dev = pl->pvert_ptr; vw->pvert_dev = pl->pvert;
+  }
   return 0;
 }

@@ -60,6 +60,15 @@ struct ohp_cg_state {
 
 struct ohp_halo;  /* ohp_comm.cu */
 
+/* tables of the cell-parallel assembly (ohp_patch.cu) */
+struct ohp_patch_plan {
+  int R, n_patches, max_cells, max_verts;
+  int64_t total_star, total_cells, total_verts;
+  int32_t *prow, *pstar_ptr, *pcell_ptr, *pvert_ptr, *pvert;
+  uint16_t *pstar, *pconn;
+  uint8_t *pslot;
+};
+
 /* device-side timeline of the CG loop (OHP_TRACE_CG, see ohp_dev.cuh) */
 struct ohp_trace_rec { unsigned long long t; int ev, it, blk, pad; };
 struct ohp_trace { ohp_trace_rec *buf; unsigned *count; unsigned cap; int it0, it1; };
@@ -155,6 +164,7 @@ struct ohp_mesh_s {
   /* "marker" label set point by point by the caller (DMSetLabelValue) instead of detected here */
   bool has_user_label;
   std::vector<int32_t> user_label;
+  ohp_patch_plan *patch;        /* NULL: the row kernels are used (limits exceeded, OHP_ASM=rows, or not built yet) */
   struct ohp_pf_plan *pfplan;   /* tables of the one-launch pipelined CG (ohp_linalg.cu), built on first use */
   struct ohp_fused_plan *fused; /* tables of the fused persistent CG kernel, built on first use (ohp_cg_fused.cu) */
   int32_t *cta_tile0;  /* weighted tile partition of the SpMV CTAs (G + 1 entries; NULL when serial), with its own ghost flags: */
@@ -184,6 +194,10 @@ struct ohp_mat_s {
 /* ohp_core.cu */
 int ohp_scan_exclusive_i32(ohp_context ctx, const int32_t *in, int32_t *out, int64_t n, int64_t *total);
 int ohp_assembly_view_make(ohp_mesh mesh, const double *u, double *out, ohp_assembly_view *vw);
+
+/* ohp_patch.cu */
+int ohp_patch_plan_build(ohp_mesh mesh);
+void ohp_patch_plan_free(ohp_context ctx, ohp_patch_plan *pl);
 
 /* ohp_comm.cu */
 int ohp_halo_build(ohp_mesh mesh);

@@ -199,8 +199,14 @@ void ohp_patch_plan_free(ohp_context ctx, ohp_patch_plan *pl) {
 
 /* called at the end of ohp_mesh_setup; on any limit it leaves m->patch == NULL and the row kernels are used */
 int ohp_patch_plan_build(ohp_mesh m) {
-  static const char *off = getenv("OHP_ASM"); /* "rows" keeps the star-walking kernels (A/B runs) */
-  if (off && off[0] == 'r') return 0;
+  /* OPT-IN (OHP_ASM=patch).  Measured in round 2 on one B200 (profiles/r02_assembly_patch_vs_rows.txt): on the 16.77 M-triangle
+   * box the patch residual takes 0.314 ms against 0.346 ms for the row kernel and the patch Jacobian 0.699 ms against 0.628 ms;
+   * on the 7.99 M-tet box 0.325 vs 0.527 ms and 2.34 vs 0.72 ms -- computing every cell once removes 2/3 of the FP64 work but the
+   * three block-synchronised phases with 128 threads, the 16-bit table reads and the strided shared-memory row accumulators cost
+   * as much as it saves, and building the tables (block-wide bitonic sorts per patch) adds 0.25 s (2-D) to 0.5 s (3-D) to
+   * ohp_mesh_setup, which the end-to-end metric pays.  So the row kernels stay the default. */
+  static const char *on = getenv("OHP_ASM");
+  if (!(on && on[0] == 'p')) return 0;
   if (m->n_owned == 0 || m->nC == 0) return 0;
   ohp_context ctx = m->ctx;
   cudaStream_t st = ctx->stream;

@@ -3,11 +3,13 @@ same inputs.  Contract (BASELINE.json north_star): numbering and sparsity patter
 assembled values within 1e-12 relative (relative to the largest magnitude of the row / vector:
 exact-zero couplings of right-angled cells make an entrywise ratio meaningless); solution within
 the solver tolerance."""
+import os
+
 import numpy as np
 import pytest
 
 import omegahpetsc_b200 as ohp
-from conftest import load_osh_oracle, synthetic_meshes
+from conftest import ROOT, load_osh_oracle, synthetic_meshes
 
 pytestmark = pytest.mark.gpu
 
@@ -630,3 +632,15 @@ def test_monitors_report_every_iteration(ctx, oracle_mod):
     assert len(mon["ksp"]) == res["its"] and sum(len(h) - 1 for h in mon["ksp"]) == res["ksp_its"]
     assert all(r == 2 for r in mon["ksp_reason"]) and all(h[-1] <= 1e-9 * h[0] for h in mon["ksp"])
     m.destroy()
+
+
+def test_patch_assembly_path_opt_in():
+    """OHP_ASM=patch: the cell-parallel assembly (every cell computed once per patch, csrc/ohp_patch.cu + k_assemble_patch)
+    passes the same residual / Jacobian parity cases as the default row kernels.  The variable is read once per process,
+    so the cases run in a child pytest."""
+    import subprocess
+    import sys
+    p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
+                        "-k", "residual_and_jacobian_values or newton_matches_oracle"],
+                       env=dict(os.environ, OHP_ASM="patch"), capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
