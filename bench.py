@@ -384,13 +384,23 @@ def measure_workload(job, args, workload, steps, warmup, e2e_steps, sampler, wit
         breakdown[name] = breakdown.get(name, 0.0) + (now - t_prev) * 1e3
         return now
 
+    if part is not None:
+        # host inputs of the partitioned build, prepared once like the cell list itself (what a picpart file holds: global
+        # ids, owners): NOT part of any timed region
+        core_gid = np.ascontiguousarray(part["gverts"], dtype=np.int64)
+        core_owned = np.ascontiguousarray(vo[part["gverts"]] == rank, dtype=np.uint8)
+        ghost_local = np.ascontiguousarray(part["ghost_local"], dtype=np.int32)
+        ghost_owner = np.ascontiguousarray(part["ghost_owner"], dtype=np.int32)
+        ghost_gid = np.ascontiguousarray(core_gid[ghost_local])
+
     def build_mesh():
         t = time.perf_counter()
         m = ohp.Mesh(ctx, lcells, lcoords)
         t = lap("mesh_create_h2d", t)
         if part is not None:
             # A6 behind the C-ABI: ghost roots from global vertex ids on the device (ohp_ghost_roots_from_gids)
-            m.set_ghosts_from_gids(part["ghost_local"], part["ghost_owner"], part["gverts"], vo[part["gverts"]] == rank)
+            roots = ctx.ghost_roots_from_gids(ghost_gid, ghost_owner, core_gid, core_owned)
+            m.set_ghosts(ghost_local, ghost_owner, roots)
             t = lap("ghost_roots_from_gids", t)
         m.setup()
         t = lap("mesh_setup", t)

@@ -626,6 +626,7 @@ k_spmv_dyn(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colidx, c
 constexpr int kPersistentBelowRows = 400000;
 constexpr int kSingleReductionBelowRows = 1600000;
 constexpr int kPipelinedBelowRows = 1600000;
+constexpr int kPipelinedAboveRows = 300000;
 static bool spmv_use_tma(ohp_mesh m) { return m->max_tile_rows <= kSpmvRowCap - 1 && m->n_tiles > 0; }
 
 static int spmv_smem_bytes(ohp_mesh m) { return (int)sizeof(double) * (kSpmvTile + std::max(1, m->max_row)); }
@@ -2328,7 +2329,10 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
     const int64_t rows_per_rank = m->n_global / std::max(1, ctx->nranks);
     /* strong-scaling regime (measured at 1.05 M rows per rank, 8 GPUs: classic 3 launches 58, single-reduction 48.8,
      * pipelined two-launch 38.4 us per iteration): reductions and rank skew must be off the critical path */
-    bool pipe2 = can_p2p && m->all_tma && rows_per_rank < kPipelinedBelowRows;
+    /* ... and only where it was measured to win: below kPipelinedAboveRows per rank (the reference's own 24k-element XGC
+     * fixtures) the single-reduction recurrence stays -- it keeps CG's iterates to rounding, while the pipelined recurrence
+     * takes 4-7 % more iterations on that ill-conditioned mesh (535 against 505 at 2 GPUs) */
+    bool pipe2 = can_p2p && m->all_tma && rows_per_rank < kPipelinedBelowRows && rows_per_rank >= kPipelinedAboveRows;
     if (force && force[0] == 'c') pipe2 = false;
     if (pipe2) return pipecg_solve(A, b, x, o, res, can_p2p);
     bool cgcg = can_p2p && rows_per_rank < kSingleReductionBelowRows; /* measured crossover: 0.145 vs 0.141 ms at 4.2 M rows/rank, 0.056 vs 0.068 at 1.05 M */
