@@ -96,6 +96,7 @@ extern "C" int ohp_comm_rank_size(ohp_context ctx, int *rank, int *nranks) {
 }
 
 void ohp_comm_destroy(ohp_context ctx) {
+  ohp_p2p_cache_drop(ctx);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->comm);
   ctx->comm = nullptr;
 }
@@ -439,8 +440,7 @@ int ohp_halo_build(ohp_mesh m) {
  * so every rank first closes its mappings, then all ranks meet (a 1-element all-reduce as the barrier), then
  * each frees its own heap.  ohp_mesh_destroy therefore has to be called by all ranks, like DMDestroy on a
  * parallel DM. */
-void ohp_p2p_free(ohp_context ctx, ohp_p2p *p) {
-  if (!p) return;
+static void p2p_release(ohp_context ctx, ohp_p2p *p) {
   for (int q = 0; q < kMaxRanks; ++q)
     if (p->peer[q] && p->peer[q] != p->heap) cudaIpcCloseMemHandle(p->peer[q]);
   if (p->attached && ctx->comm && ctx->nranks > 1) {
@@ -450,6 +450,24 @@ void ohp_p2p_free(ohp_context ctx, ohp_p2p *p) {
   }
   cudaFree(p->heap);
   delete p;
+}
+/* An attached heap is not released with its mesh but kept in the context for the next mesh (ex12 builds one DM per run, a
+ * time-stepping or adaptive caller rebuilds it every step): cudaMalloc + cudaIpcOpenMemHandle for 7 peers + cudaFree cost
+ * ~25 ms per mesh at 8 GPUs (measured with OHP_BENCH_E2E_BREAKDOWN), 8 % of a 0.29 s Newton step.  All ranks keep / reuse
+ * / drop the cache in lockstep: the decisions depend only on quantities that are equal on every rank. */
+void ohp_p2p_free(ohp_context ctx, ohp_p2p *p) {
+  if (!p) return;
+  static const char *nocache = getenv("OHP_P2P_NOCACHE");
+  if (p->attached && ctx->comm && ctx->nranks > 1 && !nocache) {
+    if (ctx->p2p_cache) p2p_release(ctx, ctx->p2p_cache); /* keep the most recent one */
+    ctx->p2p_cache = p;
+    return;
+  }
+  p2p_release(ctx, p);
+}
+void ohp_p2p_cache_drop(ohp_context ctx) {
+  if (ctx->p2p_cache) p2p_release(ctx, ctx->p2p_cache);
+  ctx->p2p_cache = nullptr;
 }
 
 extern "C" int ohp_mesh_p2p_export(ohp_mesh m, void *handle64) {
@@ -461,8 +479,25 @@ extern "C" int ohp_mesh_p2p_export(ohp_mesh m, void *handle64) {
   OHP_CUDA(cudaSetDevice(ctx->device));
   std::vector<int64_t> lens;
   OHP_TRY(ohp_allgather_i64(ctx, (int64_t)m->n_owned + m->n_ghost, lens));
+  const int64_t need_cap = (*std::max_element(lens.begin(), lens.end()) + 63) / 64 * 64 + 64;
+  if (ctx->p2p_cache && ctx->p2p_cache->pcap >= need_cap) {
+    /* reuse the cached heap and the peers' mappings (every rank sees the same need_cap and the same cached capacity, so
+     * all of them reuse together).  No peer writes here any more: its last solve on the old mesh ended with `done`, after
+     * which its kernels return without pushing.  The control words are cleared in stream order, before the next solve's
+     * entry barrier lets anybody push. */
+    ohp_p2p *p = ctx->p2p_cache;
+    ctx->p2p_cache = nullptr;
+    p->reused = true;
+    p->attached = false;
+    OHP_CUDA(cudaMemsetAsync(p->heap, 0, p->off_p0, ctx->stream));
+    OHP_CUDA(cudaMemsetAsync((char *)p->heap + p->bytes - 256, 0, 256, ctx->stream));
+    memcpy(handle64, p->handle, 64);
+    m->p2p = p;
+    return 0;
+  }
+  if (ctx->p2p_cache) ohp_p2p_cache_drop(ctx); /* too small for this mesh (on every rank alike) */
   ohp_p2p *p = new ohp_p2p();
-  p->pcap = (*std::max_element(lens.begin(), lens.end()) + 63) / 64 * 64 + 64;
+  p->pcap = need_cap;
   p->off_slots = 0;
   p->off_hflags = 2 * kMaxRanks * sizeof(ohp_ar_slot);
   p->off_p0 = 4096;
@@ -474,6 +509,7 @@ extern "C" int ohp_mesh_p2p_export(ohp_mesh m, void *handle64) {
   OHP_CUDA(cudaIpcGetMemHandle(&hnd, p->heap));
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
   memcpy(handle64, &hnd, 64);
+  memcpy(p->handle, &hnd, 64);
   m->p2p = p;
   return 0;
 }
@@ -486,6 +522,7 @@ extern "C" int ohp_mesh_p2p_attach(ohp_mesh m, const void *handles) {
   OHP_CUDA(cudaSetDevice(ctx->device));
   for (int q = 0; q < ctx->nranks; ++q) {
     if (q == ctx->rank) { p->peer[q] = p->heap; continue; }
+    if (p->reused && p->peer[q]) continue; /* mapping kept from the previous mesh */
     cudaIpcMemHandle_t hnd;
     memcpy(&hnd, (const char *)handles + 64 * q, 64);
     OHP_CUDA(cudaIpcOpenMemHandle(&p->peer[q], hnd, cudaIpcMemLazyEnablePeerAccess));

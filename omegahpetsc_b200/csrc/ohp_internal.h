@@ -94,7 +94,9 @@ struct ohp_p2p {
   size_t bytes = 0, off_slots = 0, off_hflags = 0, off_p0 = 0, off_p1 = 0;
   int64_t pcap = 0;                  /* capacity (doubles) of each p buffer: max over ranks */
   void *peer[kMaxRanks] = {nullptr};
+  unsigned char handle[64] = {0};    /* this rank's CUDA IPC handle of `heap` */
   bool attached = false;
+  bool reused = false;               /* taken from the context's cache: the peers' mappings are already open */
   ohp_p2p_dev dev;
 };
 
@@ -112,6 +114,7 @@ struct ohp_context_s {
   ohp_cg_state *h_cg;   /* pinned */
   int *d_flag;          /* device error flag for setup kernels */
   ohp_trace trace;      /* buf == NULL unless OHP_TRACE_CG is set */
+  struct ohp_p2p *p2p_cache; /* exchange heap (with the peers' IPC mappings) of the last mesh destroyed, kept for the next one */
   /* communicator (NULL = serial) */
   void *nccl_lib;
   void *comm;
@@ -211,6 +214,8 @@ int ohp_sparse_exchange(ohp_context ctx, int elem_bytes, const void *d_send, con
                         void **d_recv, std::vector<int64_t> &rcount);
 void ohp_comm_destroy(ohp_context ctx);
 void ohp_p2p_free(ohp_context ctx, ohp_p2p *p);
+/* really release the cached exchange heap (collective; context teardown) */
+void ohp_p2p_cache_drop(ohp_context ctx);
 /* solve entry in the peer-to-peer modes: a stream-ordered barrier over the communicator, so that the first fused
  * all-reduce / halo wait of a solve never measures start-up skew (lazy module load, allocation, a profiler) */
 int ohp_p2p_entry_barrier(ohp_mesh mesh);
