@@ -632,7 +632,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="box2d_2896", choices=sorted(WORKLOADS))
     ap.add_argument("--secondary", default="box3d_110", help="second workload measured into the `secondary` object ('none' to skip)")
-    ap.add_argument("--secondary-steps", type=int, default=30)
+    ap.add_argument("--secondary-steps", type=int, default=60)  # ~2 s of timed steps: the clock sampler needs a few samples
     ap.add_argument("--n", type=int, default=0, help="override the box resolution (development only)")
     ap.add_argument("--check-every", type=int, default=0)
     ap.add_argument("--profile", type=int, default=64, help="SpMV launches bracketed by CUDA events per solve")

@@ -375,6 +375,32 @@ int ohp_halo_build(ohp_mesh m) {
   OHP_CUDA(cudaMemcpyAsync(owner_ldof_all.data(), d_tmp, sizeof(int32_t) * m->nV, cudaMemcpyDeviceToHost, st));
   OHP_CUDA(cudaStreamSynchronize(st));
   OHP_FREE(ctx, d_tmp);
+  {
+    /* consistency of the point SF: a ghost that is FREE here (its label came from the owner) must be a free, OWNED vertex on
+     * its owner.  A root that points at a vertex the owner does not own has no row there (-1) and would silently be treated
+     * as constrained.  Every rank learns the global count before any of them returns, so that nobody is left waiting in the
+     * next collective. */
+    std::vector<uint8_t> bnd(std::max(1, m->nV));
+    OHP_CUDA(cudaMemcpyAsync(bnd.data(), m->bnd, m->nV, cudaMemcpyDeviceToHost, st));
+    OHP_CUDA(cudaStreamSynchronize(st));
+    double bad = 0.0;
+    int first_bad = -1;
+    for (int i = 0; i < nleaf; ++i) {
+      const int32_t gv = m->ghost_vertex[i];
+      if (owner_ldof_all[gv] < 0 && bnd[gv] == 0) { bad += 1.0; if (first_bad < 0) first_bad = i; }
+    }
+    OHP_CUDA(cudaMemcpyAsync(ctx->d_scalars + 13, &bad, sizeof(double), cudaMemcpyHostToDevice, st));
+    OHP_TRY(ohp_allreduce_sum(ctx, ctx->d_scalars + 13, 1));
+    double total = 0.0;
+    OHP_CUDA(cudaMemcpyAsync(&total, ctx->d_scalars + 13, sizeof(double), cudaMemcpyDeviceToHost, st));
+    OHP_CUDA(cudaStreamSynchronize(st));
+    if (total > 0.0) {
+      if (first_bad >= 0)
+        OHP_FAIL(OHP_ERR_ARG_WRONG, "point SF: ghost vertex %d is free but its root (rank %d, vertex %d) is not an owned free vertex there (%g such ghosts over all ranks)",
+                 m->ghost_vertex[first_bad], m->ghost_owner_rank[first_bad], m->ghost_owner_vertex[first_bad], total);
+      OHP_FAIL(OHP_ERR_ARG_WRONG, "point SF: %g ghosts on other ranks point at roots that are not owned free vertices", total);
+    }
+  }
   /* unconstrained ghosts, ordered by (owner rank, owner dof): contiguous receive ranges */
   struct G { int rank; int32_t ldof; int32_t vertex; };
   std::vector<G> gh;

@@ -146,3 +146,28 @@ def test_default_options(L):
     s = ohp.SnesOptions()
     assert L.ohp_snes_default_options(ctypes.byref(s)) == 0
     assert (s.rtol, s.abstol, s.stol, s.max_it) == (1e-8, 1e-50, 1e-8, 50)
+
+
+def test_ctypes_mirrors_match_the_header(tmp_path):
+    """The Python harness mirrors ohp.h's structs by hand (ctypes): sizes and field offsets must equal what a C compiler
+    lays out from the header itself (fields were appended in round 2: ksp_type, algo, the patch tables of the view)."""
+    import ctypes
+    import subprocess
+
+    import omegahpetsc_b200 as ohp
+    mirrors = {"ohp_ksp_options": ohp.KspOptions, "ohp_ksp_result": ohp.KspResult, "ohp_snes_options": ohp.SnesOptions,
+               "ohp_snes_result": ohp.SnesResult}
+    lines = []
+    for cname, cls in mirrors.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "ohp.h"\nint main(void) {\n%s\nreturn 0; }\n' % "\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in mirrors.items():
+        assert int(out[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(out["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
