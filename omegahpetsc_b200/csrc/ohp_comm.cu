@@ -66,6 +66,17 @@ int nccl_load() {
 
 static inline unsigned nblk(int64_t n, int bs) { return (unsigned)std::max<int64_t>(1, (n + bs - 1) / bs); }
 
+/* an NCCL group that is closed on EVERY exit path: an error raised between GroupStart and GroupEnd must not leave the
+ * group open (every later NCCL call of this process would be queued into it) */
+namespace {
+struct NcclGroup {
+  bool open = false;
+  ncclResult_t start() { const ncclResult_t r = g_nccl.GroupStart(); open = (r == ncclSuccess); return r; }
+  ncclResult_t end() { open = false; return g_nccl.GroupEnd(); }
+  ~NcclGroup() { if (open) g_nccl.GroupEnd(); }
+};
+}  // namespace
+
 extern "C" int ohp_comm_unique_id(void *out) {
   if (!out) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_comm_unique_id: null buffer");
   OHP_TRY(nccl_load());
@@ -183,13 +194,14 @@ static int exchange_lists(ohp_context ctx, const std::vector<std::vector<int32_t
   std::vector<int32_t> flat((size_t)ns);
   for (int q = 0; q < P; ++q) std::copy(send[q].begin(), send[q].end(), flat.begin() + soff[q]);
   OHP_CUDA(cudaMemcpyAsync(d_s, flat.data(), sizeof(int32_t) * ns, cudaMemcpyHostToDevice, st));
-  OHP_NCCL(g_nccl.GroupStart());
+  NcclGroup grp;
+  OHP_NCCL(grp.start());
   for (int q = 0; q < P; ++q) {
     if (q == ctx->rank) continue;
     if (soff[q + 1] > soff[q]) OHP_NCCL(g_nccl.Send(d_s + soff[q], (size_t)(soff[q + 1] - soff[q]), ncclInt32, q, (ncclComm_t)ctx->comm, st));
     if (roff[q + 1] > roff[q]) OHP_NCCL(g_nccl.Recv(d_r + roff[q], (size_t)(roff[q + 1] - roff[q]), ncclInt32, q, (ncclComm_t)ctx->comm, st));
   }
-  OHP_NCCL(g_nccl.GroupEnd());
+  OHP_NCCL(grp.end());
   std::vector<int32_t> rflat((size_t)nr);
   OHP_CUDA(cudaMemcpyAsync(rflat.data(), d_r, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, st));
   OHP_CUDA(cudaStreamSynchronize(st));
@@ -334,13 +346,14 @@ int ohp_vertex_halo_i32(ohp_mesh m, int32_t *data) {
   ohp_halo *h = m->halo;
   cudaStream_t st = ctx->stream;
   if (h->v_ns) { k_gather_i32<<<nblk(h->v_ns, 256), 256, 0, st>>>(data, h->d_v_send_idx, h->v_ns, h->d_v_sbuf); OHP_CHECK_LAUNCH(ctx); }
-  OHP_NCCL(g_nccl.GroupStart());
+  NcclGroup grp;
+  OHP_NCCL(grp.start());
   for (size_t k = 0; k < h->nbr.size(); ++k) {
     const int64_t ns = h->v_soff[k + 1] - h->v_soff[k], nr = h->v_roff[k + 1] - h->v_roff[k];
     if (ns) OHP_NCCL(g_nccl.Send(h->d_v_sbuf + h->v_soff[k], (size_t)ns, ncclInt32, h->nbr[k], (ncclComm_t)ctx->comm, st));
     if (nr) OHP_NCCL(g_nccl.Recv(h->d_v_rbuf + h->v_roff[k], (size_t)nr, ncclInt32, h->nbr[k], (ncclComm_t)ctx->comm, st));
   }
-  OHP_NCCL(g_nccl.GroupEnd());
+  OHP_NCCL(grp.end());
   if (h->v_nr) { k_scatter_i32<<<nblk(h->v_nr, 256), 256, 0, st>>>(data, h->d_v_recv_idx, h->v_nr, h->d_v_rbuf); OHP_CHECK_LAUNCH(ctx); }
   return 0;
 }
@@ -642,12 +655,13 @@ int ohp_halo_exchange(ohp_mesh m, double *x) {
   cudaStream_t st = ctx->stream;
   if (h->d_ns) { k_gather_f64<<<nblk(h->d_ns, 256), 256, 0, st>>>(x, h->d_send_ldof, h->d_ns, h->d_sbuf); OHP_CHECK_LAUNCH(ctx); }
   if (h->d_nbr.empty()) return 0;
-  OHP_NCCL(g_nccl.GroupStart());
+  NcclGroup grp;
+  OHP_NCCL(grp.start());
   for (size_t k = 0; k < h->d_nbr.size(); ++k) {
     const int64_t ns = h->d_soff[k + 1] - h->d_soff[k], nr = h->d_roff[k + 1] - h->d_roff[k];
     if (ns) OHP_NCCL(g_nccl.Send(h->d_sbuf + h->d_soff[k], (size_t)ns, ncclFloat64, h->d_nbr[k], (ncclComm_t)ctx->comm, st));
     if (nr) OHP_NCCL(g_nccl.Recv(x + m->n_owned + h->d_roff[k], (size_t)nr, ncclFloat64, h->d_nbr[k], (ncclComm_t)ctx->comm, st));
   }
-  OHP_NCCL(g_nccl.GroupEnd());
+  OHP_NCCL(grp.end());
   return 0;
 }

@@ -768,6 +768,11 @@ static int spmv_enqueue(ohp_mat A, const double *x, double *y, ohp_cg_state *st,
       /* 4, 5: two CTAs per SM with two stages -- measured slower (0.151 / 0.177 ms vs 0.146 on the 16 M box), kept for A/B */
       case 4: if (m->col16 && ctx->nranks == 1) return spmv_tma_launch_ts<2, 352, int16_t, false, 2>(A, m->col16, x, y, st, sums, mode, x_alt, pd, epi); break;
       case 5: if (m->col16 && ctx->nranks == 1) return spmv_tma_launch_ts<2, 288, int16_t, false, 2>(A, m->col16, x, y, st, sums, mode, x_alt, pd, epi); break;
+      /* 6-8: one thread per row whatever the row length (no lane sharing), fewer consumer warps (long-row matrices, A/B) */
+      case 6: if (m->col16) return spmv_tma_launch_ts<3, 384, int16_t, false>(A, m->col16, x, y, st, sums, mode, x_alt, pd, epi); break;
+      case 7: if (m->col16) return spmv_tma_launch_ts<3, 320, int16_t, false>(A, m->col16, x, y, st, sums, mode, x_alt, pd, epi); break;
+      case 8: if (m->col16) return spmv_tma_launch_ts<3, 448, int16_t, false>(A, m->col16, x, y, st, sums, mode, x_alt, pd, epi); break;
+      case 9: if (m->col16) return spmv_tma_launch_ts<3, 512, int16_t, true>(A, m->col16, x, y, st, sums, mode, x_alt, pd, epi); break;
       case 1: return spmv_tma_launch<3, 384>(A, x, y, st, sums, mode, x_alt, pd, epi);
       case 2: return spmv_tma_launch<3, 768>(A, x, y, st, sums, mode, x_alt, pd, epi);
       case 3: return spmv_tma_launch<2, 640>(A, x, y, st, sums, mode, x_alt, pd, epi);
