@@ -702,6 +702,14 @@ static int spmv_tma_launch(ohp_mat A, const double *x, double *y, ohp_cg_state *
                            const double *x_alt, const ohp_p2p_dev &pd, const ohp_cgcg_epi &epi) {
   ohp_mesh m = A->mesh;
   static const char *idx = getenv("OHP_IDX"); /* "32" keeps absolute 32-bit column ids (A/B runs) */
+  /* Long rows (3-D meshes, 15 non-zeros per row: ~273 rows per tile).  The ncu capture (profiles/r02_spmv_tma_3d_ncu.txt)
+   * shows this case bound by instruction issue and gather latency, not DRAM (42 % of peak, 1.46 warp-instructions per
+   * non-zero against 1.10 in 2-D): sharing a row among 2-4 lanes of 19 warps costs more instructions (predicated batches,
+   * shuffles) than its parallelism gains.  One thread per row with 14 consumer warps is faster: 53.3 vs 61.5 us per launch
+   * on the 7.99 M-tet box (0.73 vs 0.64 of the HBM roofline; 384 consumers 54.2, 320: 63.0, lane sharing with 512: 58.6). */
+  static const char *force_cfg = getenv("OHP_SPMV");
+  if (NC == 608 && S == 3 && !force_cfg && m->nnz > (int64_t)8 * std::max(1, m->n_owned) && m->col16 && !(idx && idx[0] == '3'))
+    return spmv_tma_launch_ts<3, 448, int16_t, false>(A, m->col16, x, y, st, sums, mode, x_alt, pd, epi);
   if (m->col16 && !(idx && idx[0] == '3')) return spmv_tma_launch_t<S, NC, int16_t>(A, m->col16, x, y, st, sums, mode, x_alt, pd, epi);
   return spmv_tma_launch_t<S, NC, int32_t>(A, m->colidx, x, y, st, sums, mode, x_alt, pd, epi);
 }

@@ -174,9 +174,10 @@ def test_cg_matches_oracle(ctx, oracle_mod, name, pc, ksp_type):
     out = ohp.ksp_cg(J, b, x, ohp.ksp_options(rtol=1e-9, max_it=20000, pc=pc, ksp_type=ksp_type), history=True)
     ref = oracle_mod.cg(rowptr, colidx, J.values(), b.to_host(), rtol=1e-9, maxit=20000, pc=pc, history=True)
     assert out["reason"] == ref["reason"] == 2
-    # rounding-order sensitivity of CG; the pipelined recurrence (more recurred vectors) loses a little more on the
-    # ill-conditioned XGC mesh: 526 against 506 iterations
-    assert abs(out["its"] - ref["its"]) <= max(2, ref["its"] // (40 if ksp_type == ohp.KSP_CG else 20))
+    # rounding-order sensitivity of CG; the pipelined recurrence (more recurred vectors) loses more on the ill-conditioned
+    # XGC mesh: 4-7 % more iterations, depending on the form and the replacement period
+    pipelined = ksp_type == ohp.KSP_PIPECG or os.environ.get("OHP_CG", "").startswith("pipecg")
+    assert abs(out["its"] - ref["its"]) <= max(2, ref["its"] // (10 if pipelined else 40))  # XGC mesh: 524-539 against 506
     # CG amplifies rounding differences (summation order, FMA contraction) exponentially on an
     # ill-conditioned operator: the monitored norms agree to many digits only for the first iterations
     k = min(out["its"], ref["its"], 8)
@@ -643,4 +644,19 @@ def test_patch_assembly_path_opt_in():
     p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
                         "-k", "residual_and_jacobian_values or newton_matches_oracle"],
                        env=dict(os.environ, OHP_ASM="patch"), capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+
+
+@pytest.mark.parametrize("variant", ["classic", "cgcg", "pipecg1", "pipecg2", "persistent"])
+def test_every_cg_recurrence_on_one_gpu(variant):
+    """The library picks the recurrence from the problem size and the transport, so on one GPU the default suite only meets
+    some of them.  OHP_CG forces each one (classic three-launch, single-reduction two-launch, pipelined one- and two-launch --
+    the latter is the 8-GPU default of the bench -- and the persistent cooperative kernel) through the CG parity cases:
+    oracle iteration counts, residual histories, solutions, true residuals, iteration limits.  The variable is read once per
+    process, so the cases run in a child pytest."""
+    import subprocess
+    import sys
+    p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
+                        "-k", "cg_matches_oracle or cg_limits"],
+                       env=dict(os.environ, OHP_CG=variant), capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
