@@ -141,6 +141,55 @@ def newton(problem, cells, coords, gidx, N, rowptr, colidx, u0=None, snes_rtol=1
     return dict(u=u, snes_its=int(out[0]), ksp_its=int(out[1]), reason=int(out[2]), norms=norms[: out[0] + 1].copy())
 
 
+def bd_residual(cells, coords, gidx, N, u, F):
+    """F += natural-boundary term of ex12's -bc_type neumann (f0_bd_u, f1_bd_zero); returns F."""
+    cells = np.ascontiguousarray(cells, dtype=np.int32)
+    coords = np.ascontiguousarray(coords, dtype=np.float64)
+    nC, nc = cells.shape
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    F = np.ascontiguousarray(F, dtype=np.float64)
+    rc = lib().orc_bd_residual(nc - 1, ctypes.c_int64(nC), gidx.size, _p(cells, c_i32p), _p(coords, c_f64p),
+                               _p(gidx, c_i32p), N, _p(u, c_f64p), _p(F, c_f64p))
+    assert rc == 0
+    return F
+
+
+def hash_noise(n, start=0):
+    L = lib()
+    L.orc_hash_noise.restype = ctypes.c_double
+    return np.array([L.orc_hash_noise(ctypes.c_int64(start + i)) for i in range(n)])
+
+
+def estimate_emax(rowptr, colidx, vals, dinv, steps=10):
+    L = lib()
+    L.orc_estimate_emax.restype = ctypes.c_double
+    dinv = np.ascontiguousarray(dinv, dtype=np.float64)
+    return L.orc_estimate_emax(rowptr.size - 1, _p(rowptr, c_i32p), _p(colidx, c_i32p), _p(vals, c_f64p),
+                               _p(dinv, c_f64p), steps)
+
+
+def pcg(rowptr, colidx, vals, b, rtol=1e-5, abstol=1e-50, dtol=1e5, maxit=10000, pc=0, cheb_its=4, emin=0.0,
+        emax=0.0, nullspace=False, history=False):
+    """orc_pcg: pc 0 none, 1 Jacobi, 2 Chebyshev(cheb_its)/Jacobi; nullspace = project the constants out."""
+    N = rowptr.size - 1
+    x = np.zeros(N)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    its = ctypes.c_int()
+    reason = ctypes.c_int()
+    rnorm = ctypes.c_double()
+    eig = np.zeros(2)
+    hist = np.zeros(maxit + 1) if history else None
+    lib().orc_pcg(N, _p(rowptr, c_i32p), _p(colidx, c_i32p), _p(vals, c_f64p), _p(b, c_f64p), _p(x, c_f64p),
+                  ctypes.c_double(rtol), ctypes.c_double(abstol), ctypes.c_double(dtol), maxit, pc, cheb_its,
+                  ctypes.c_double(emin), ctypes.c_double(emax), int(bool(nullspace)),
+                  ctypes.byref(its), ctypes.byref(reason), ctypes.byref(rnorm),
+                  _p(hist, c_f64p) if history else None, _p(eig, c_f64p))
+    out = dict(x=x, its=its.value, reason=reason.value, rnorm=rnorm.value, emin=eig[0], emax=eig[1])
+    if history:
+        out["hist"] = hist[: its.value + 1]
+    return out
+
+
 def num_threads(omp=True):
     return lib(omp).orc_num_threads()
 

@@ -651,3 +651,290 @@ int orc_set_num_threads(int n) {
   return 1;
 #endif
 }
+
+/* ========================================================================= */
+/* natural (Neumann) boundary term, null space, a          */
+/* polynomial preconditioner.  Same status as the rest of this file: test       */
+/* infrastructure, parity unpinned.                                             */
+/* ========================================================================= */
+
+/* boundary pointwise callbacks: f0_bd_u (ex12.cpp:179-186), f1_bd_zero (ex12.cpp:188-195); the argument list of the
+ * volume callbacks plus the unit outward normal n[] after x[] */
+typedef void (*orc_bdfn)(int dim, int Nf, int NfAux, const int uOff[], const int uOff_x[], const double u[],
+                         const double u_t[], const double u_x[], const int aOff[], const int aOff_x[], const double a[],
+                         const double a_t[], const double a_x[], double t, const double x[], const double n[],
+                         int numConstants, const double constants[], double f[]);
+#define BD_ARGS                                                                                  \
+  int dim, int Nf, int NfAux, const int uOff[], const int uOff_x[], const double u[],            \
+      const double u_t[], const double u_x[], const int aOff[], const int aOff_x[],              \
+      const double a[], const double a_t[], const double a_x[], double t, const double x[],      \
+      const double n[], int numConstants, const double constants[]
+static void cb_f0_bd_u(BD_ARGS, double f0[]) {
+  f0[0] = 0.0;
+  for (int d = 0; d < dim; ++d) f0[0] += -n[d] * 2.0 * x[d];
+}
+static void cb_f1_bd_zero(BD_ARGS, double f1[]) {
+  for (int c = 0; c < dim; ++c) f1[c] = 0.0;
+}
+
+/* Natural boundary residual [PETSc-internal DMPlexComputeBdResidual_Internal -> PetscFEIntegrateBdResidual_Basic,
+ * reached from DMPlexSetSNESLocalFEM ex12.cpp:1540 when SetupProblem registered PetscDSSetBdResidual(prob, 0, f0_bd_u,
+ * f1_bd_zero) (ex12.cpp:1226,1231) and DMAddBoundary(DM_BC_NATURAL, "wall", "boundary", ...) (ex12.cpp:1237)].
+ * Label "boundary" = the facets with one supporting cell (DMPlexMarkBoundaryFaces, ex12.cpp:1088-1094).  Per boundary
+ * facet F of cell c, per face quadrature point q (face rule of PetscFECreateDefault: 2 Gauss points on an edge, the
+ * 4-point conical rule on a triangle; weights sum to 2):
+ *     Fe[b] += w_q detJ_F ( phi_b(x_q) f0_bd(u, grad u, x_q, n) + grad(phi_b) . f1_bd(...) ),   detJ_F = |F| / 2,
+ * phi_b = the cell's basis restricted to the face, n = unit normal pointing out of c.  ADDS into F (call after
+ * orc_residual); constrained rows (gidx < 0) are dropped like everywhere else. */
+int orc_bd_residual(int dim, int64_t nC, int nV, const int *cells, const double *coords, const int *gidx, int N,
+                    const double *u, double *F) {
+  (void)N;
+  const int nc = dim + 1, nf = dim;
+  orc_problem p;
+  if (orc_problem_get(0, dim, &p)) return 1;
+  const orc_bdfn f0_bd = cb_f0_bd_u, f1_bd = cb_f1_bd_zero;
+  int64_t *ptr; int *adj;
+  build_v2c(nc, nC, nV, cells, &ptr, &adj);
+  double *uloc = (double *)malloc((size_t)nV * sizeof(double));
+  local_values(&p, dim, nV, coords, gidx, u, uloc);
+  /* face rule on the biunit (dim-1)-simplex */
+  int nq = 0; double fxi[ORC_MAXQ * 2], fw[ORC_MAXQ];
+  if (dim == 2) {
+    double gx[2], gw[2];
+    gauss_jacobi2(0, gx, gw);
+    nq = 2;
+    for (int q = 0; q < 2; ++q) { fxi[q] = gx[q]; fw[q] = gw[q]; }
+  } else if (orc_quadrature(2, &nq, fxi, fw)) return 1;
+  const int uOff[2] = {0, 1}, uOff_x[2] = {0, dim};
+  for (int64_t c = 0; c < nC; ++c) { /* serial: the order of the additions into F is then fixed */
+    const int *cv = cells + c * nc;
+    for (int skip = 0; skip < nc; ++skip) {
+      int fv[ORC_MAXNC], fb[ORC_MAXNC], k = 0;
+      for (int j = 0; j < nc; ++j) if (j != skip) { fv[k] = cv[j]; fb[k] = j; ++k; }
+      int support = 0;
+      for (int64_t s = ptr[fv[0]]; s < ptr[fv[0] + 1]; ++s) {
+        const int *ov = cells + (int64_t)adj[s] * nc;
+        int all = 1;
+        for (int a = 1; a < nf && all; ++a) {
+          int found = 0;
+          for (int j = 0; j < nc; ++j) found |= (ov[j] == fv[a]);
+          all = found;
+        }
+        support += all;
+      }
+      if (support != 1) continue;
+      /* cell gradient (constant for P1) */
+      const double *X[ORC_MAXNC];
+      double ue[ORC_MAXNC];
+      for (int b = 0; b < nc; ++b) { X[b] = coords + (size_t)cv[b] * dim; ue[b] = uloc[cv[b]]; }
+      cell_geom g;
+      cell_geometry(dim, X, &g);
+      double ux[ORC_MAXDIM] = {0, 0, 0};
+      for (int b = 0; b < nc; ++b) for (int d = 0; d < dim; ++d) ux[d] += g.G[b][d] * ue[b];
+      /* face geometry */
+      const double *P0 = coords + (size_t)fv[0] * dim, *P1 = coords + (size_t)fv[1] * dim;
+      const double *Po = coords + (size_t)cv[skip] * dim;
+      double e1[3] = {0, 0, 0}, e2[3] = {0, 0, 0}, n[3] = {0, 0, 0}, meas;
+      for (int d = 0; d < dim; ++d) e1[d] = P1[d] - P0[d];
+      if (dim == 2) {
+        meas = sqrt(e1[0] * e1[0] + e1[1] * e1[1]);
+        n[0] = e1[1] / meas; n[1] = -e1[0] / meas;
+      } else {
+        const double *P2 = coords + (size_t)fv[2] * dim;
+        for (int d = 0; d < 3; ++d) e2[d] = P2[d] - P0[d];
+        n[0] = e1[1] * e2[2] - e1[2] * e2[1]; n[1] = e1[2] * e2[0] - e1[0] * e2[2]; n[2] = e1[0] * e2[1] - e1[1] * e2[0];
+        const double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        meas = 0.5 * nn;
+        for (int d = 0; d < 3; ++d) n[d] /= nn;
+      }
+      double side = 0.0;
+      for (int d = 0; d < dim; ++d) side += n[d] * (Po[d] - P0[d]);
+      if (side > 0.0) for (int d = 0; d < dim; ++d) n[d] = -n[d];
+      const double detJf = 0.5 * meas;
+      double Fe[ORC_MAXNC] = {0, 0, 0, 0};
+      for (int q = 0; q < nq; ++q) {
+        double lam[3], xq[ORC_MAXDIM], uq = 0.0;
+        if (dim == 2) { lam[0] = 0.5 * (1.0 - fxi[q]); lam[1] = 0.5 * (1.0 + fxi[q]); }
+        else { lam[1] = 0.5 * (1.0 + fxi[q * 2]); lam[2] = 0.5 * (1.0 + fxi[q * 2 + 1]); lam[0] = 1.0 - lam[1] - lam[2]; }
+        for (int d = 0; d < dim; ++d) {
+          xq[d] = 0.0;
+          for (int a = 0; a < nf; ++a) xq[d] += lam[a] * coords[(size_t)fv[a] * dim + d];
+        }
+        for (int a = 0; a < nf; ++a) uq += lam[a] * uloc[fv[a]];
+        double f0[1] = {0.0}, f1[ORC_MAXDIM] = {0, 0, 0};
+        f0_bd(dim, 1, 0, uOff, uOff_x, &uq, NULL, ux, NULL, NULL, NULL, NULL, NULL, 0.0, xq, n, 0, NULL, f0);
+        f1_bd(dim, 1, 0, uOff, uOff_x, &uq, NULL, ux, NULL, NULL, NULL, NULL, NULL, 0.0, xq, n, 0, NULL, f1);
+        const double w = detJf * fw[q];
+        for (int a = 0; a < nf; ++a) {
+          double s = lam[a] * f0[0];
+          for (int d = 0; d < dim; ++d) s += g.G[fb[a]][d] * f1[d];
+          Fe[a] += w * s;
+        }
+      }
+      for (int a = 0; a < nf; ++a) {
+        const int r = gidx[fv[a]];
+        if (r >= 0) F[r] += Fe[a];
+      }
+    }
+  }
+  free(uloc); free(ptr); free(adj);
+  return 0;
+}
+
+/* largest eigenvalue of the symmetric tridiagonal (d[0..n), e[0..n-1)) by bisection on the Sturm count */
+static double tridiag_lambda_max(int n, const double *d, const double *e) {
+  double lo = d[0], hi = d[0];
+  for (int i = 0; i < n; ++i) {
+    const double r = (i > 0 ? fabs(e[i - 1]) : 0.0) + (i < n - 1 ? fabs(e[i]) : 0.0);
+    if (d[i] - r < lo) lo = d[i] - r;
+    if (d[i] + r > hi) hi = d[i] + r;
+  }
+  for (int it = 0; it < 200 && hi - lo > 1e-14 * fmax(fabs(hi), fabs(lo)); ++it) {
+    const double mid = 0.5 * (lo + hi);
+    int below = 0; /* number of eigenvalues < mid */
+    double q = d[0] - mid;
+    if (q < 0.0) ++below;
+    for (int i = 1; i < n; ++i) {
+      if (q == 0.0) q = 1e-300;
+      q = d[i] - mid - e[i - 1] * e[i - 1] / q;
+      if (q < 0.0) ++below;
+    }
+    if (below >= n) hi = mid; else lo = mid;
+  }
+  return 0.5 * (lo + hi);
+}
+
+/* deterministic "noise" in [-1,1) from the global row number (PETSc seeds KSPChebyshev's eigenvalue estimate with a random
+ * vector, -ksp_chebyshev_esteig_noisy; a hash keeps runs and partitions reproducible) */
+double orc_hash_noise(int64_t i) {
+  uint64_t z = (uint64_t)i + 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  z ^= z >> 31;
+  return (double)(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+}
+
+/* lambda_max(D^-1 A) from `steps` iterations of Jacobi-preconditioned CG on the noise vector (the Lanczos tridiagonal of
+ * CG: T_jj = 1/alpha_j + beta_{j-1}/alpha_{j-1}, T_{j,j+1} = sqrt(beta_j)/alpha_j) [PETSc-internal
+ * KSPChebyshevEstEigSet / KSPComputeExtremeSingularValues; PETSc runs GMRES there, whose Ritz values equal Lanczos' for
+ * a symmetric operator] */
+double orc_estimate_emax(int N, const int *rowptr, const int *colidx, const double *vals, const double *dinv, int steps) {
+  double *r = malloc(sizeof(double) * (size_t)N), *z = malloc(sizeof(double) * (size_t)N);
+  double *p = malloc(sizeof(double) * (size_t)N), *w = malloc(sizeof(double) * (size_t)N);
+  double td[64], te[64];
+  if (steps > 64) steps = 64;
+  for (int i = 0; i < N; ++i) { r[i] = orc_hash_noise(i); z[i] = dinv[i] * r[i]; p[i] = z[i]; }
+  double beta = vdot(N, z, r), alpha_old = 1.0, bb_old = 0.0;
+  int n = 0;
+  for (int j = 0; j < steps && beta > 0.0; ++j) {
+    orc_spmv(N, rowptr, colidx, vals, p, w);
+    const double pw = vdot(N, p, w);
+    if (!(pw > 0.0)) break;
+    const double alpha = beta / pw;
+    td[n] = 1.0 / alpha + (j > 0 ? bb_old / alpha_old : 0.0);
+    for (int i = 0; i < N; ++i) { r[i] -= alpha * w[i]; z[i] = dinv[i] * r[i]; }
+    const double beta_new = vdot(N, z, r);
+    const double bb = beta_new / beta;
+    te[n] = sqrt(bb) / alpha;
+    ++n;
+    for (int i = 0; i < N; ++i) p[i] = z[i] + bb * p[i];
+    beta = beta_new; alpha_old = alpha; bb_old = bb;
+  }
+  const double lam = n ? tridiag_lambda_max(n, td, te) : 1.0;
+  free(r); free(z); free(p); free(w);
+  return lam;
+}
+
+/* z = p_k(D^-1 A) D^-1 r: `its` iterations of the Chebyshev semi-iteration with Jacobi inside, zero initial guess
+ * [PETSc-internal KSPSolve_Chebyshev as -pc_type ksp -ksp_ksp_type chebyshev -ksp_pc_type jacobi -ksp_ksp_max_it its
+ * runs it: three rotating iterates, scale = 2/(emax+emin), alpha = 1 - scale*emin, mu = 1/alpha, c_{k+1} = 2 mu c_k -
+ * c_{k-1}, omega = (2/alpha) c_k / c_{k+1},  y_{k+1} = omega (y_k - y_{k-1} + scale B^-1 (r - A y_k)) + y_{k-1}] */
+static void cheb_apply(int N, const int *rowptr, const int *colidx, const double *vals, const double *dinv, int its,
+                       double emin, double emax, const double *r, double *z, double *y0, double *y1, double *t) {
+  const double scale = 2.0 / (emax + emin), alpha = 1.0 - scale * emin, mu = 1.0 / alpha, omegaprod = 2.0 / alpha;
+  double c_km1 = 1.0, c_k = mu;
+  double *ykm1 = y0, *yk = y1, *ykp1 = z;
+  for (int i = 0; i < N; ++i) { ykm1[i] = 0.0; yk[i] = scale * dinv[i] * r[i]; }
+  for (int k = 1; k < its; ++k) {
+    orc_spmv(N, rowptr, colidx, vals, yk, t);
+    const double c_kp1 = 2.0 * mu * c_k - c_km1, omega = omegaprod * c_k / c_kp1;
+    for (int i = 0; i < N; ++i)
+      ykp1[i] = (1.0 - omega) * ykm1[i] + omega * yk[i] + scale * omega * (dinv[i] * (r[i] - t[i]));
+    double *tmp = ykm1; ykm1 = yk; yk = ykp1; ykp1 = tmp;
+    c_km1 = c_k; c_k = c_kp1;
+  }
+  if (yk != z) memcpy(z, yk, sizeof(double) * (size_t)N);
+}
+
+/* Preconditioned CG with the options this row adds to orc_cg: pc 2 = the Chebyshev/Jacobi polynomial above
+ * (emax <= 0: 1.1 x the estimate of 10 Lanczos steps, PETSc's safety factor; emin <= 0: emax / (4 k^2 + 36), an
+ * interval that widens with the degree because the polynomial preconditions CG here instead of smoothing for multigrid --
+ * PETSc's smoother default emin = 0.1 x estimate is reached by passing both ends), and
+ * `nullspace` = 1: the constants are projected out of every preconditioned residual [PETSc-internal KSP_PCApply ->
+ * KSP_RemoveNullSpace, with the MatNullSpaceCreate(comm, PETSC_TRUE, 0, NULL) that ex12.cpp:1534-1538 attaches when
+ * -bc_type is not dirichlet].  Iteration and convergence test as orc_cg.  eig[0..1] returns the interval used. */
+int orc_pcg(int N, const int *rowptr, const int *colidx, const double *vals, const double *b, double *x, double rtol,
+            double abstol, double dtol, int maxit, int pc, int cheb_its, double emin, double emax, int nullspace,
+            int *its_out, int *reason_out, double *rnorm_out, double *hist, double *eig) {
+  const size_t nb = sizeof(double) * (size_t)(N > 0 ? N : 1);
+  double *r = malloc(nb), *z = malloc(nb), *p = malloc(nb), *w = malloc(nb), *dinv = malloc(nb);
+  double *y0 = malloc(nb), *y1 = malloc(nb), *t = malloc(nb);
+  for (int i = 0; i < N; ++i) {
+    const int64_t s = find_slot(rowptr, colidx, i, i);
+    const double d = (s >= 0) ? vals[s] : 0.0;
+    dinv[i] = (pc != 0 && d != 0.0) ? 1.0 / d : 1.0;
+  }
+  if (pc == 2) {
+    if (!(emax > 0.0)) emax = 1.1 * orc_estimate_emax(N, rowptr, colidx, vals, dinv, 10);
+    if (!(emin > 0.0)) emin = emax / (4.0 * cheb_its * cheb_its + 36.0);
+  }
+  if (eig) { eig[0] = emin; eig[1] = emax; }
+#define ORC_APPLY_PC()                                                                              \
+  do {                                                                                              \
+    if (pc == 2) cheb_apply(N, rowptr, colidx, vals, dinv, cheb_its, emin, emax, r, z, y0, y1, t);  \
+    else for (int k = 0; k < N; ++k) z[k] = dinv[k] * r[k];                                         \
+    if (nullspace && N > 0) {                                                                       \
+      double s = 0.0;                                                                               \
+      for (int k = 0; k < N; ++k) s += z[k];                                                        \
+      s /= N;                                                                                       \
+      for (int k = 0; k < N; ++k) z[k] -= s;                                                        \
+    }                                                                                               \
+  } while (0)
+  int reason = 0, i = 0;
+  for (int k = 0; k < N; ++k) { x[k] = 0.0; r[k] = b[k]; }
+  ORC_APPLY_PC();
+  double dp = sqrt(vdot(N, z, z));
+  double beta = vdot(N, z, r), betaold = 1.0;
+  const double rnorm0 = dp, ttol = fmax(rtol * rnorm0, abstol);
+  if (hist) hist[0] = dp;
+  if (dp != dp) reason = -9;
+  else if (dp <= ttol) reason = (dp < abstol) ? 3 : 2;
+  while (!reason && i < maxit) {
+    if (beta == 0.0) { reason = 3; break; }
+    if (i == 0) memcpy(p, z, nb);
+    else {
+      const double bb = beta / betaold;
+      for (int k = 0; k < N; ++k) p[k] = z[k] + bb * p[k];
+    }
+    orc_spmv(N, rowptr, colidx, vals, p, w);
+    const double dpi = vdot(N, p, w);
+    betaold = beta;
+    if (!(dpi > 0.0)) { reason = (dpi != dpi) ? -9 : -8; ++i; break; }
+    const double a = beta / dpi;
+    for (int k = 0; k < N; ++k) { x[k] += a * p[k]; r[k] -= a * w[k]; }
+    ORC_APPLY_PC();
+    dp = sqrt(vdot(N, z, z));
+    ++i;
+    if (hist) hist[i] = dp;
+    if (dp != dp) reason = -9;
+    else if (dp <= ttol) reason = (dp < abstol) ? 3 : 2;
+    else if (dp >= dtol * rnorm0) reason = -4;
+    if (reason) break;
+    beta = vdot(N, z, r);
+  }
+#undef ORC_APPLY_PC
+  if (!reason) reason = -3;
+  *its_out = i; *reason_out = reason; *rnorm_out = dp;
+  free(r); free(z); free(p); free(w); free(dinv); free(y0); free(y1); free(t);
+  return 0;
+}
