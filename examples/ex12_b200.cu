@@ -6,7 +6,8 @@
  * INTEGRATION.md lists what a maintainer edits in ex12.cpp itself.
  *
  *   ./ex12_b200 -mesh <dir.osh | box | picpart> [-picpart_path <prefix>] [-cells nx,ny] [-run_type full|test|perf]
- *               [-variable_coefficient none|analytic|circle|cross] [-ksp_rtol 1e-9] [-ksp_max_it N] [-pc_type none|jacobi]
+ *               [-variable_coefficient none|analytic|circle|cross] [-bc_type dirichlet|neumann] [-ksp_rtol 1e-9] [-ksp_max_it N]
+ *               [-pc_type none|jacobi|ksp [-ksp_ksp_max_it k] [-ksp_ksp_chebyshev_eigenvalues emin,emax]]
  *               [-boundary device|plex] [-snes_monitor_short] [-ksp_monitor_short] [-snes_converged_reason]
  *               [-ksp_converged_reason] [-dm_view] [-vec_view vtk:out.vtu]
  * Partitioned runs (one process per GPU, no MPI needed):
@@ -45,6 +46,15 @@ PETSC_HOSTDEVICE static void flux(OHP_PF_ARGS, PetscScalar f1[]) {
 PETSC_HOSTDEVICE static void dflux(OHP_PJ_ARGS, PetscScalar g3[]) {
   for (PetscInt d = 0; d < dim; ++d) g3[d * dim + d] = 1.0;
 }
+/* natural boundary data of -bc_type neumann: -du/dn of the manufactured solution, and no boundary flux term
+ * (f0_bd_u / f1_bd_zero, ex12.cpp:179-195); OHP_BD_ARGS = OHP_PF_ARGS with the unit outward normal n[] after x[] */
+PETSC_HOSTDEVICE static void bd_source(OHP_BD_ARGS, PetscScalar f0[]) {
+  f0[0] = 0.0;
+  for (PetscInt d = 0; d < dim; ++d) f0[0] += -n[d] * 2.0 * x[d];
+}
+PETSC_HOSTDEVICE static void bd_flux(OHP_BD_ARGS, PetscScalar f1[]) {
+  for (PetscInt d = 0; d < dim; ++d) f1[d] = 0.0;
+}
 
 /* nu = x + y: -div(nu grad u) + 6 (x + y) = 0 (ex12.cpp:283,292,313) */
 PETSC_HOSTDEVICE static void source_nu(OHP_PF_ARGS, PetscScalar f0[]) { f0[0] = 6.0 * (x[0] + x[1]); }
@@ -78,7 +88,7 @@ PETSC_HOSTDEVICE static void source_cross(OHP_PF_ARGS, PetscScalar f0[]) { f0[0]
 }  // namespace poisson
 
 /* one line per callback set: instantiates the assembly kernels with the callbacks inlined */
-OHP_DEFINE_PROBLEM(constant, poisson::source, poisson::flux, poisson::dflux, poisson::exact2d, poisson::exact2d)
+OHP_DEFINE_PROBLEM_BD(constant, poisson::source, poisson::flux, poisson::dflux, poisson::exact2d, poisson::exact2d, poisson::bd_source, poisson::bd_flux)
 OHP_DEFINE_PROBLEM(variable, poisson::source_nu, poisson::flux_nu, poisson::dflux_nu, poisson::exact2d, poisson::exact2d)
 OHP_DEFINE_PROBLEM(circle, poisson::source_circle, poisson::flux, poisson::dflux, poisson::circle2d, poisson::circle2d)
 OHP_DEFINE_PROBLEM(cross, poisson::source_cross, poisson::flux, poisson::dflux, poisson::cross2d, poisson::cross2d)
@@ -91,6 +101,7 @@ OHP_DEFINE_FUNCTION(guess, poisson::guess)
 struct Config {
   enum Run { FULL, TEST, PERF } run = FULL;
   enum Coeff { NONE, ANALYTIC, CIRCLE, CROSS } coeff = NONE;
+  enum BC { NEUMANN, DIRICHLET } bc = DIRICHLET;   /* -bc_type (ex12.cpp:39,432) */
   bool plex_boundary = false;   /* -boundary plex: walk the edges as ex12.cpp:986-1033 does, instead of the device detection */
   PetscInt dim = 2;
   PetscInt cells[3] = {2, 2, 2};
@@ -113,6 +124,12 @@ static PetscErrorCode read_options(Config *cfg) {
     else if (!strcmp(word, "cross")) { cfg->coeff = Config::CROSS; cfg->exact[0] = poisson::cross2d; }
     else if (strcmp(word, "none")) SETERRQ1(PETSC_COMM_SELF, PETSC_ERR_ARG_WRONG, "-variable_coefficient %s is not built", word);
   }
+  ierr = PetscOptionsGetString(NULL, NULL, "-bc_type", word, sizeof(word), &given);CHKERRQ(ierr);
+  if (given) {
+    if (!strcmp(word, "neumann")) cfg->bc = Config::NEUMANN;
+    else if (strcmp(word, "dirichlet")) SETERRQ1(PETSC_COMM_SELF, PETSC_ERR_ARG_WRONG, "-bc_type %s is not built", word);
+  }
+  if (cfg->bc == Config::NEUMANN && cfg->coeff != Config::NONE) SETERRQ(PETSC_COMM_SELF, PETSC_ERR_SUP, "-bc_type neumann is wired for -variable_coefficient none here");
   ierr = PetscOptionsGetString(NULL, NULL, "-boundary", word, sizeof(word), &given);CHKERRQ(ierr);
   if (given) cfg->plex_boundary = !strcmp(word, "plex");
   ierr = PetscOptionsGetIntArray(NULL, NULL, "-cells", cfg->cells, &n, NULL);CHKERRQ(ierr);
@@ -304,7 +321,15 @@ static PetscErrorCode setup_problem(DM dm, Config *cfg) {
       ierr = PetscDSSetResidual(ds, 0, poisson::source, poisson::flux);CHKERRQ(ierr);
       ierr = PetscDSSetJacobian(ds, 0, 0, NULL, NULL, NULL, poisson::dflux);CHKERRQ(ierr);
   }
-  ierr = DMAddBoundary(dm, DM_BC_ESSENTIAL, "wall", "marker", 0, 0, NULL, (void (*)(void))cfg->exact[0], NULL, 1, &wall, cfg);CHKERRQ(ierr);
+  if (cfg->bc == Config::NEUMANN) {                                             /* ex12.cpp:1088-1094,1226,1237 */
+    DMLabel label;
+    ierr = DMCreateLabel(dm, "boundary");CHKERRQ(ierr);
+    ierr = DMGetLabel(dm, "boundary", &label);CHKERRQ(ierr);
+    ierr = DMPlexMarkBoundaryFaces(dm, 1, label);CHKERRQ(ierr);
+    ierr = PetscDSSetBdResidual(ds, 0, poisson::bd_source, poisson::bd_flux);CHKERRQ(ierr);
+  }
+  ierr = DMAddBoundary(dm, cfg->bc == Config::DIRICHLET ? DM_BC_ESSENTIAL : DM_BC_NATURAL, "wall", cfg->bc == Config::DIRICHLET ? "marker" : "boundary",
+                       0, 0, NULL, (void (*)(void))cfg->exact[0], NULL, 1, &wall, cfg);CHKERRQ(ierr);
   ierr = PetscDSSetExactSolution(ds, 0, cfg->exact[0], cfg);CHKERRQ(ierr);
   ierr = PetscFEDestroy(&fe);CHKERRQ(ierr);
   return 0;
@@ -393,6 +418,11 @@ int main(int argc, char **argv) {
   ierr = DMCreateGlobalVector(dm, &u);CHKERRQ(ierr);
   ierr = VecSetName(u, "potential");CHKERRQ(ierr);
   ierr = DMCreateMatrix(dm, &J);CHKERRQ(ierr);
+  MatNullSpace nullSpace = NULL;                                /* "May be necessary for Neumann conditions", ex12.cpp:1478,1534-1538 */
+  if (cfg.bc != Config::DIRICHLET) {
+    ierr = MatNullSpaceCreate(PETSC_COMM_WORLD, PETSC_TRUE, 0, NULL, &nullSpace);CHKERRQ(ierr);
+    ierr = MatSetNullSpace(J, nullSpace);CHKERRQ(ierr);
+  }
   ierr = DMPlexSetSNESLocalFEM(dm, &cfg, &cfg, &cfg);CHKERRQ(ierr);
   ierr = SNESSetJacobian(snes, J, J, NULL, NULL);CHKERRQ(ierr);
   ierr = SNESSetFromOptions(snes);CHKERRQ(ierr);
@@ -404,6 +434,7 @@ int main(int argc, char **argv) {
     case Config::TEST: ierr = run_test(snes, dm, u, J, &cfg);CHKERRQ(ierr); break;
   }
 
+  ierr = MatNullSpaceDestroy(&nullSpace);CHKERRQ(ierr);
   ierr = MatDestroy(&J);CHKERRQ(ierr);
   ierr = VecDestroy(&u);CHKERRQ(ierr);
   ierr = SNESDestroy(&snes);CHKERRQ(ierr);

@@ -175,6 +175,14 @@ int ohp_mesh_set_point_sf(ohp_mesh mesh, int32_t n_leaves, const int32_t *leaf_p
  * Collective when a communicator is attached. */
 int ohp_mesh_setup(ohp_mesh mesh);
 
+/* DMAddBoundary's type (ex12.cpp:1237): OHP_BC_ESSENTIAL (-bc_type dirichlet, default) constrains the dofs of the
+ * "marker" vertices; OHP_BC_NATURAL (-bc_type neumann) constrains nothing -- every owned vertex gets a row -- and
+ * ohp_residual adds the boundary integral of the problem's boundary callbacks (PetscDSSetBdResidual, ex12.cpp:1226,1231)
+ * over the facets with one supporting cell (label "boundary", DMPlexMarkBoundaryFaces ex12.cpp:1088-1094); OHP_BC_NONE
+ * (-bc_type none) constrains nothing and integrates nothing.  Call before ohp_mesh_setup. */
+enum { OHP_BC_ESSENTIAL = 0, OHP_BC_NATURAL = 1, OHP_BC_NONE = 2 };
+int ohp_mesh_set_bc_type(ohp_mesh mesh, int bc_type);
+
 /* Plex queries for callers that walk the interpolated mesh themselves, as CreateQuadMesh does between
  * DMPlexInterpolate and the solve (ex12.cpp:958-1033).  Facets are the points DMPlexInterpolate creates between
  * cells and vertices: edges in 2-D (Plex points [nC+nV, nC+nV+nF)), triangles in 3-D.  Built on the device on first
@@ -269,12 +277,17 @@ typedef struct {
   const uint16_t *pconn_dev;    /* (dim+1) per patch cell: patch-local vertex ids                                    */
   const int32_t *pvert_ptr_dev; /* n_patches + 1                                                                      */
   const int32_t *pvert_dev;     /* global (rank-local) vertex of each patch vertex                                   */
+  const uint8_t *bnd_dev;       /* n_verts: label "marker" (1 on vertices of facets with one supporting cell)        */
 } ohp_assembly_view;
 
 typedef int (*ohp_assembly_launcher)(const ohp_assembly_view *view);
 /* `project_exact` and `l2_diff` may be NULL (the problem then has no exact solution to project / compare with) */
 int ohp_problem_register(ohp_assembly_launcher residual, ohp_assembly_launcher jacobian,
                          ohp_assembly_launcher project_exact, ohp_assembly_launcher l2_diff, int *problem_id);
+/* PetscDSSetBdResidual(prob, 0, f0_bd, f1_bd) (ex12.cpp:1226,1231): the launcher ADDS the boundary integral into
+ * out_dev[n_rows] (ohp::launch_bd_residual_any<P>); used by ohp_residual on OHP_BC_NATURAL meshes.  The built-in problems
+ * carry ex12's f0_bd_u / f1_bd_zero (ex12.cpp:179-195). */
+int ohp_problem_set_bd_residual(int problem_id, ohp_assembly_launcher bd_residual);
 /* DMProjectFunction of an arbitrary point function compiled for the device (ohp::launch_project_fn<F>) */
 int ohp_project_function(ohp_mesh mesh, ohp_assembly_launcher project, ohp_vec u);
 
@@ -305,6 +318,12 @@ int ohp_mat_destroy(ohp_mat A);
 int ohp_mat_zero(ohp_mat A);
 int ohp_mat_get_values(ohp_mat A, double *vals /* nnz, pattern order */);
 int ohp_mat_mult(ohp_mat A, ohp_vec x, ohp_vec y); /* y = A x (halo exchange inside) */
+/* MatNullSpaceCreate(comm, PETSC_TRUE, 0, NULL) + MatSetNullSpace(A, nullSpace) (ex12.cpp:1534-1538, done when -bc_type is
+ * not dirichlet): the operator annihilates the constants.  ohp_ksp_cg then projects them out of every preconditioned
+ * residual [PETSc-internal KSP_PCApply -> KSP_RemoveNullSpace].  ohp_vec_remove_constant = MatNullSpaceRemove(nullSpace, u)
+ * (ex12.cpp:1667): u -= mean(u) over all ranks. */
+int ohp_mat_set_nullspace(ohp_mat A, int has_constant);
+int ohp_vec_remove_constant(ohp_vec v);
 
 /* ------------------------------------------------------------------------------------ */
 /* FEM evaluators installed by DMPlexSetSNESLocalFEM (ex12.cpp:1540) and called through   */
@@ -321,7 +340,11 @@ int ohp_l2_error(ohp_mesh mesh, int problem, ohp_vec u, double *err);
 /* ------------------------------------------------------------------------------------ */
 /* KSP CG (PETSc-internal KSPSolve_CG selected by -ksp_type cg at ex12.cpp:1543).        */
 /* ------------------------------------------------------------------------------------ */
-enum { OHP_PC_NONE = 0, OHP_PC_JACOBI = 1 };
+/* OHP_PC_CHEBYSHEV ("preconditioning beyond Jacobi"): the Chebyshev polynomial in D^-1 A that PETSc
+ * builds with -pc_type ksp -ksp_ksp_type chebyshev -ksp_pc_type jacobi -ksp_ksp_max_it <cheb_its> [PETSc-internal
+ * KSPSolve_Chebyshev inside PCApply_KSP], applied without any reduction; the outer CG then runs in the general
+ * host-driven loop (csrc/ohp_pcg.cu) instead of the fused recurrences. */
+enum { OHP_PC_NONE = 0, OHP_PC_JACOBI = 1, OHP_PC_CHEBYSHEV = 2 };
 /* -ksp_type: cg (the library picks the recurrence -- classic, single-reduction or pipelined -- from the global problem
  * size and the transport; all give CG's iterates in exact arithmetic) or pipecg (PETSc's KSPPIPECG, Ghysels-Vanroose:
  * forces the pipelined recurrence, whose reductions overlap the SpMV) */
@@ -335,10 +358,16 @@ typedef struct {
   double *history;           /* host array receiving the monitored norm per iteration (-ksp_monitor) */
   int32_t profile;           /* >0: bracket up to this many SpMV launches with CUDA events (-log_view analogue) */
   int32_t ksp_type;          /* OHP_KSP_CG (default) | OHP_KSP_PIPECG */
+  int32_t cheb_its;          /* OHP_PC_CHEBYSHEV: Chebyshev iterations per application, -ksp_ksp_max_it (0 = 8) */
+  int32_t reserved0;
+  double cheb_emin, cheb_emax; /* -ksp_ksp_chebyshev_eigenvalues emin,emax.  emax <= 0: 1.1 x lambda_max(D^-1 A) estimated with
+                                * 10 Lanczos steps on a reproducible noise vector (KSPChebyshevEstEigSet's role); emin <= 0:
+                                * emax / (4 cheb_its^2 + 36) (see csrc/ohp_pcg.hpp; PETSc's smoother default is 0.1 x estimate) */
 } ohp_ksp_options;
 /* the kernel the profiled launches belong to: k_spmv_tma (classic three-launch CG, single-reduction two-launch CG, two-launch
  * pipelined CG), the persistent cooperative kernel, or k_pipecg_fused (SpMV + the whole vector update in one launch) */
-enum { OHP_ALGO_CLASSIC = 0, OHP_ALGO_SINGLE_REDUCTION = 1, OHP_ALGO_PERSISTENT = 2, OHP_ALGO_PIPELINED_2L = 3, OHP_ALGO_PIPELINED_FUSED = 4, OHP_ALGO_FUSED_PERSISTENT = 5 };
+enum { OHP_ALGO_CLASSIC = 0, OHP_ALGO_SINGLE_REDUCTION = 1, OHP_ALGO_PERSISTENT = 2, OHP_ALGO_PIPELINED_2L = 3, OHP_ALGO_PIPELINED_FUSED = 4, OHP_ALGO_FUSED_PERSISTENT = 5,
+       OHP_ALGO_GENERAL_PCG = 6 /* host-driven loop of csrc/ohp_pcg.cu: Chebyshev preconditioner and / or null space */ };
 typedef struct {
   int32_t its;
   int32_t reason; /* KSPConvergedReason: 2 RTOL, 3 ATOL, -3 ITS, -4 DTOL, -8 INDEFINITE_MAT, -9 NANORINF */
@@ -348,6 +377,9 @@ typedef struct {
   int32_t spmv_samples; /* how many launches that mean is over */
   float total_ms;       /* device time of the whole solve (CUDA events) */
   int32_t algo;         /* which recurrence ran (OHP_ALGO_*): names the kernel that `spmv_ms` times */
+  double cheb_emin, cheb_emax; /* OHP_PC_CHEBYSHEV: the interval the polynomial was built for (0 otherwise) */
+  int32_t spmvs;        /* OHP_ALGO_GENERAL_PCG: operator applications, eigenvalue estimate included (0 otherwise) */
+  int32_t reserved0;
 } ohp_ksp_result;
 int ohp_ksp_default_options(ohp_ksp_options *o);
 int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *opts, ohp_ksp_result *res);

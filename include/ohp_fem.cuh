@@ -689,6 +689,177 @@ template <class F> int launch_project_fn(const ohp_assembly_view *vw) {
   return cudaGetLastError() == cudaSuccess ? 0 : OHP_ERR_LIB;
 }
 
+/* ------------------------------------------------------------------------------------ */
+/* Natural boundary residual (-bc_type neumann, ex12.cpp:1226-1238).    */
+/* [PETSc-internal DMPlexComputeBdResidual_Internal -> PetscFEIntegrateBdResidual_Basic]:    */
+/* over every facet F with one supporting cell (label "boundary", ex12.cpp:1088-1094), with   */
+/* the face rule of PetscFECreateDefault (2 Gauss points on an edge, the 4-point conical rule  */
+/* on a triangle; weights sum to 2, detJ_F = |F| / 2):                                        */
+/*     Fe[b] += w_q detJ_F ( phi_b(x_q) f0_bd(u, grad u, x_q, n) + grad(phi_b) . f1_bd(...) )  */
+/* n = unit normal pointing out of the supporting cell.  "Owner computes" like the volume      */
+/* kernels: the thread of row v walks star(v); a facet of a star cell that contains v is on    */
+/* the boundary iff no other cell of star(v) contains it (any cell sharing the facet contains  */
+/* v, so the star is the whole support -- also on a partitioned mesh, where every rank holds   */
+/* all cells touching the vertices it owns).  Contributions are added in star order: no        */
+/* atomics, bitwise reproducible.  Only rows of "marker" vertices do any work.                 */
+/* The per-row function is __host__ __device__ and free of CUDA intrinsics so that the CPU     */
+/* unit test (tests/host/bd_host.cu) can run exactly this code on host arrays.                 */
+/* ------------------------------------------------------------------------------------ */
+#define OHP_BD_ARGS                                                                              \
+  int dim, int Nf, int NfAux, const int uOff[], const int uOff_x[], const double u[],            \
+      const double u_t[], const double u_x[], const int aOff[], const int aOff_x[],              \
+      const double a[], const double a_t[], const double a_x[], double t, const double x[],      \
+      const double n[], int numConstants, const double constants[]
+
+#if defined(__CUDA_ARCH__)
+#define OHP_LD(p) __ldg(p)
+#else
+#define OHP_LD(p) (*(p))
+#endif
+
+/* barycentric coordinates of the face quadrature points with respect to the face's vertices, and the weights */
+template <int DIM> struct FaceQuadrature;
+template <> struct FaceQuadrature<2> {
+  static constexpr int NQ = 2;
+  OHP_HD static void lam(int q, double (&l)[2]) {
+    const double s = (q == 0) ? -5.77350269189625764509e-01 : 5.77350269189625764509e-01; /* Gauss-Legendre on [-1,1] */
+    l[0] = 0.5 * (1.0 - s); l[1] = 0.5 * (1.0 + s);
+  }
+  OHP_HD static double w(int) { return 1.0; }
+};
+template <> struct FaceQuadrature<3> {
+  static constexpr int NQ = Quadrature<2>::NQ;
+  OHP_HD static void lam(int q, double (&l)[3]) {
+    l[1] = 0.5 * (1.0 + Quadrature<2>::xi(q, 0)); l[2] = 0.5 * (1.0 + Quadrature<2>::xi(q, 1)); l[0] = 1.0 - l[1] - l[2];
+  }
+  OHP_HD static double w(int q) { return Quadrature<2>::w(q); }
+};
+
+template <int DIM, class P>
+OHP_HD double bd_residual_row(const ohp_assembly_view &vw, int k0, int k1) {
+  constexpr int NC = DIM + 1;
+  const int uOff[2] = {0, 1}, uOff_x[2] = {0, DIM};
+  double acc = 0.0;
+  for (int k = k0; k < k1; ++k) {
+    const int e = OHP_LD(vw.v2c_dev + k), c = e >> 2, b = e & 3;
+    int cv[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) cv[j] = OHP_LD(vw.cells_dev + (size_t)c * NC + j);
+    for (int skip = 0; skip < NC; ++skip) {
+      if (skip == b) continue; /* the facet opposite corner `skip` contains this row's vertex iff skip != b */
+      bool shared = false;
+      for (int k2 = k0; k2 < k1 && !shared; ++k2) {
+        if (k2 == k) continue;
+        const int c2 = OHP_LD(vw.v2c_dev + k2) >> 2;
+        int ov[NC];
+#pragma unroll
+        for (int j = 0; j < NC; ++j) ov[j] = OHP_LD(vw.cells_dev + (size_t)c2 * NC + j);
+        bool all = true;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+          bool found = (j == skip);
+#pragma unroll
+          for (int i = 0; i < NC; ++i) found |= (ov[i] == cv[j]);
+          all &= found;
+        }
+        shared = all;
+      }
+      if (shared) continue;
+      /* closure of the supporting cell */
+      double X[NC][DIM], ue[NC];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) X[j][d] = OHP_LD(vw.coords_dev + (size_t)cv[j] * DIM + d);
+        const int l = OHP_LD(vw.lidx_dev + cv[j]);
+        if (l >= 0) ue[j] = OHP_LD(vw.u_dev + l);
+        else { double val = 0.0; P::bc(DIM, 0.0, X[j], 1, &val, nullptr); ue[j] = val; }
+      }
+      CellGeom<DIM> g;
+      cell_geometry<DIM>(X, g);
+      double ux[DIM];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) s += g.G[j][d] * ue[j];
+        ux[d] = s;
+      }
+      /* the face: corners of the cell in cell order, `skip` left out */
+      int fj[DIM], nf = 0, av = 0;
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+        if (j != skip) { if (j == b) av = nf; fj[nf++] = j; }
+      double e1[DIM], n[DIM], meas;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) e1[d] = X[fj[1]][d] - X[fj[0]][d];
+      if constexpr (DIM == 2) {
+        meas = sqrt(e1[0] * e1[0] + e1[1] * e1[1]);
+        n[0] = e1[1] / meas; n[1] = -e1[0] / meas;
+      } else {
+        double e2[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) e2[d] = X[fj[2]][d] - X[fj[0]][d];
+        n[0] = e1[1] * e2[2] - e1[2] * e2[1]; n[1] = e1[2] * e2[0] - e1[0] * e2[2]; n[2] = e1[0] * e2[1] - e1[1] * e2[0];
+        const double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        meas = 0.5 * nn;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) n[d] /= nn;
+      }
+      double side = 0.0;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) side += n[d] * (X[skip][d] - X[fj[0]][d]);
+      if (side > 0.0) {
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) n[d] = -n[d];
+      }
+      const double detJf = 0.5 * meas;
+      for (int q = 0; q < FaceQuadrature<DIM>::NQ; ++q) {
+        double lam[DIM], xq[DIM], uq = 0.0;
+        FaceQuadrature<DIM>::lam(q, lam);
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+          double s = 0.0;
+#pragma unroll
+          for (int a = 0; a < DIM; ++a) s += lam[a] * X[fj[a]][d];
+          xq[d] = s;
+        }
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) uq += lam[a] * ue[fj[a]];
+        double f0[1] = {0.0}, f1[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) f1[d] = 0.0;
+        P::f0_bd(DIM, 1, 0, uOff, uOff_x, &uq, nullptr, ux, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, xq, n, 0, nullptr, f0);
+        P::f1_bd(DIM, 1, 0, uOff, uOff_x, &uq, nullptr, ux, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, xq, n, 0, nullptr, f1);
+        double s = lam[av] * f0[0];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) s += g.G[b][d] * f1[d];
+        acc += (detJf * FaceQuadrature<DIM>::w(q)) * s;
+      }
+    }
+  }
+  return acc;
+}
+
+template <int DIM, class P>
+__global__ void __launch_bounds__(128) k_bd_residual_rows(const ohp_assembly_view vw) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= vw.n_rows) return;
+  const int v = __ldg(vw.row_vertex_dev + r);
+  if (!__ldg(vw.bnd_dev + v)) return;
+  vw.out_dev[r] += bd_residual_row<DIM, P>(vw, __ldg(vw.v2c_ptr_dev + v), __ldg(vw.v2c_ptr_dev + v + 1));
+}
+
+template <int DIM, class P> int launch_bd_residual(const ohp_assembly_view *vw) {
+  if (vw->n_rows <= 0) return 0;
+  const int bs = 128;
+  k_bd_residual_rows<DIM, P><<<(vw->n_rows + bs - 1) / bs, bs, 0, (cudaStream_t)vw->stream>>>(*vw);
+  return cudaGetLastError() == cudaSuccess ? 0 : OHP_ERR_LIB;
+}
+template <class P> int launch_bd_residual_any(const ohp_assembly_view *vw) {
+  return vw->dim == 2 ? launch_bd_residual<2, P>(vw) : vw->dim == 3 ? launch_bd_residual<3, P>(vw) : OHP_ERR_SUP;
+}
+
 /* dimension dispatch used by both the built-in problems and user registrations */
 template <class P> int launch_residual_any(const ohp_assembly_view *vw) {
   return vw->dim == 2 ? launch_residual<2, P>(vw) : vw->dim == 3 ? launch_residual<3, P>(vw) : OHP_ERR_SUP;

@@ -98,6 +98,10 @@ typedef void (*PetscPointJac)(PetscInt, PetscInt, PetscInt, const PetscInt[], co
                               const PetscScalar[], const PetscScalar[], const PetscScalar[], PetscReal, PetscReal,
                               const PetscReal[], PetscInt, const PetscScalar[], PetscScalar[]);
 typedef PetscErrorCode (*PetscSimplePointFunc)(PetscInt, PetscReal, const PetscReal[], PetscInt, PetscScalar *, void *);
+/* PetscBdPointFunc: the volume form plus the unit outward normal n[] after x[] (f0_bd_u, ex12.cpp:179-182) */
+typedef void (*PetscBdPointFunc)(PetscInt, PetscInt, PetscInt, const PetscInt[], const PetscInt[], const PetscScalar[], const PetscScalar[],
+                                 const PetscScalar[], const PetscInt[], const PetscInt[], const PetscScalar[], const PetscScalar[],
+                                 const PetscScalar[], PetscReal, const PetscReal[], const PetscReal[], PetscInt, const PetscScalar[], PetscScalar[]);
 
 namespace ohp {
 
@@ -114,7 +118,7 @@ struct ProblemKey {
     return bc < o.bc;
   }
 };
-struct ProblemRecord { int id; void *exact; };
+struct ProblemRecord { int id; void *exact; void *f0_bd = nullptr, *f1_bd = nullptr; };
 inline std::map<ProblemKey, ProblemRecord> &problem_registry() { static std::map<ProblemKey, ProblemRecord> r; return r; }
 
 /* point functions compiled for the device so that DMProjectFunction can evaluate them at the vertices */
@@ -126,6 +130,14 @@ template <class P> int register_problem(void *f0, void *f1, void *g3, void *bc, 
   int id = -1;
   if (ohp_problem_register(launch_residual_any<P>, launch_jacobian_any<P>, launch_project_exact_any<P>, launch_l2_diff_any<P>, &id)) return -1;
   problem_registry()[ProblemKey{f0, f1, g3, bc}] = ProblemRecord{id, exact};
+  return id;
+}
+/* the same with boundary callbacks (PetscDSSetBdResidual): also instantiates the natural-boundary kernel */
+template <class P> int register_problem_bd(void *f0, void *f1, void *g3, void *bc, void *exact, void *f0_bd, void *f1_bd) {
+  const int id = register_problem<P>(f0, f1, g3, bc, exact);
+  if (id < 0 || ohp_problem_set_bd_residual(id, launch_bd_residual_any<P>)) return -1;
+  ProblemRecord &r = problem_registry()[ProblemKey{f0, f1, g3, bc}];
+  r.f0_bd = f0_bd; r.f1_bd = f1_bd;
   return id;
 }
 #endif
@@ -156,6 +168,38 @@ template <class P> int register_problem(void *f0, void *f1, void *g3, void *bc, 
       (void *)(PetscPointFunc)F0, (void *)(PetscPointFunc)F1, (void *)(PetscPointJac)G3,                        \
       (void *)(PetscSimplePointFunc)BC, (void *)(PetscSimplePointFunc)EXACT);
 
+/* The same for a callback set that also registers boundary callbacks with PetscDSSetBdResidual (-bc_type neumann,
+ * ex12.cpp:1226,1231): F0_BD / F1_BD have the PetscBdPointFunc signature (OHP_BD_ARGS, then the output array). */
+#define OHP_DEFINE_PROBLEM_BD(name, F0, F1, G3, BC, EXACT, F0_BD, F1_BD)                                        \
+  struct ohp_problem_##name {                                                                                   \
+    static constexpr bool kJacobianUsesU = true;                                                                \
+    OHP_HD static void f0(OHP_PF_ARGS, double f[]) {                                                            \
+      F0(dim, Nf, NfAux, uOff, uOff_x, u, u_t, u_x, aOff, aOff_x, a, a_t, a_x, t, x, numConstants, constants, f); \
+    }                                                                                                           \
+    OHP_HD static void f1(OHP_PF_ARGS, double f[]) {                                                            \
+      F1(dim, Nf, NfAux, uOff, uOff_x, u, u_t, u_x, aOff, aOff_x, a, a_t, a_x, t, x, numConstants, constants, f); \
+    }                                                                                                           \
+    OHP_HD static void g3(OHP_PJ_ARGS, double g[]) {                                                            \
+      G3(dim, Nf, NfAux, uOff, uOff_x, u, u_t, u_x, aOff, aOff_x, a, a_t, a_x, t, u_tShift, x, numConstants, constants, g); \
+    }                                                                                                           \
+    OHP_HD static void f0_bd(OHP_BD_ARGS, double f[]) {                                                         \
+      F0_BD(dim, Nf, NfAux, uOff, uOff_x, u, u_t, u_x, aOff, aOff_x, a, a_t, a_x, t, x, n, numConstants, constants, f); \
+    }                                                                                                           \
+    OHP_HD static void f1_bd(OHP_BD_ARGS, double f[]) {                                                         \
+      F1_BD(dim, Nf, NfAux, uOff, uOff_x, u, u_t, u_x, aOff, aOff_x, a, a_t, a_x, t, x, n, numConstants, constants, f); \
+    }                                                                                                           \
+    OHP_HD static int bc(int dim, double time, const double x[], int Nc, double *u, void *ctx) {                \
+      return BC(dim, time, x, Nc, u, ctx);                                                                      \
+    }                                                                                                           \
+    OHP_HD static int exact(int dim, double time, const double x[], int Nc, double *u, void *ctx) {             \
+      return EXACT(dim, time, x, Nc, u, ctx);                                                                   \
+    }                                                                                                           \
+  };                                                                                                            \
+  static const int ohp_problem_id_##name = ohp::register_problem_bd<ohp_problem_##name>(                        \
+      (void *)(PetscPointFunc)F0, (void *)(PetscPointFunc)F1, (void *)(PetscPointJac)G3,                        \
+      (void *)(PetscSimplePointFunc)BC, (void *)(PetscSimplePointFunc)EXACT, (void *)(PetscBdPointFunc)F0_BD,    \
+      (void *)(PetscBdPointFunc)F1_BD);
+
 /* Makes a PetscSimplePointFunc (initial guess, any function handed to DMProjectFunction) available on the device */
 #define OHP_DEFINE_FUNCTION(name, FN)                                                                           \
   struct ohp_function_##name {                                                                                  \
@@ -175,6 +219,7 @@ struct _p_PetscDS {
   PetscPointFunc f0 = nullptr, f1 = nullptr;
   PetscPointJac g3 = nullptr;
   PetscSimplePointFunc bc = nullptr, exact = nullptr;
+  PetscBdPointFunc f0_bd = nullptr, f1_bd = nullptr;
   void *exact_ctx = nullptr;
   int problem = -1;
 };
@@ -195,12 +240,14 @@ struct _p_DM {
   void *app_ctx = nullptr;
   _p_PetscSF sf;
   _p_PetscDS ds;
-  _p_DMLabel marker;
+  _p_DMLabel marker, boundary;
   bool has_marker = false, has_field = false, has_bc = false;
+  int bc_type = OHP_BC_ESSENTIAL; /* DMAddBoundary's type: DM_BC_NATURAL (-bc_type neumann) constrains nothing */
   PetscInt dim = 0;
 };
 struct _p_Vec { ohp_vec v = nullptr; _p_DM *dm = nullptr; std::string name; };
 struct _p_Mat { ohp_mat m = nullptr; _p_DM *dm = nullptr; };
+struct _p_MatNullSpace { PetscBool has_cnst; };
 struct _p_SNES {
   _p_DM *dm = nullptr;
   _p_Mat *A = nullptr, *J = nullptr;
@@ -343,14 +390,20 @@ inline PetscErrorCode PetscSFSetGraph(PetscSF sf, PetscInt /*nroots*/, PetscInt 
 inline PetscErrorCode PetscMalloc1(size_t n, void *out, size_t elem) { *(void **)out = malloc(n * elem); return *(void **)out ? 0 : OHP_ERR_MEM; }
 #define PetscMalloc1(n, pp) PetscMalloc1((size_t)(n), (void *)(pp), sizeof(**(pp)))
 inline PetscErrorCode DMPlexInterpolate(DM dm, DM *idm) { dm->refs++; *idm = dm; return 0; } /* edges are implicit here */
-inline PetscErrorCode DMCreateLabel(DM dm, const char *name) { dm->marker.name = name; return 0; }
-inline PetscErrorCode DMGetLabel(DM dm, const char *, DMLabel *label) { *label = &dm->marker; return 0; }
+/* two labels exist on this path: "marker" (vertices, ex12.cpp:521,1025) and "boundary" (facets, -bc_type neumann,
+ * ex12.cpp:1091); both describe the facets with one supporting cell, which the library finds itself */
+inline PetscErrorCode DMCreateLabel(DM dm, const char *name) {
+  if (!strcmp(name, "boundary")) dm->boundary.name = name; else dm->marker.name = name;
+  return 0;
+}
+inline PetscErrorCode DMGetLabel(DM dm, const char *name, DMLabel *label) { *label = !strcmp(name, "boundary") ? &dm->boundary : &dm->marker; return 0; }
 inline PetscErrorCode DMHasLabel(DM dm, const char *, PetscBool *has) { *has = dm->has_marker ? PETSC_TRUE : PETSC_FALSE; return 0; }
 
 inline PetscErrorCode ohp_dm_setup(DM dm) {
   if (dm->set_up) return 0;
   PetscErrorCode ierr = 0;
   if (dm->label_by_caller) ierr = ohp_mesh_set_label(dm->mesh, (PetscInt)dm->label_verts.size(), dm->label_verts.data());
+  if (!ierr && dm->bc_type != OHP_BC_ESSENTIAL) ierr = ohp_mesh_set_bc_type(dm->mesh, dm->bc_type);
   if (!ierr) ierr = ohp_mesh_setup(dm->mesh);
   /* partitioned run: NVLink peer mapping for the fused halo / all-reduce kernels (OHP_COMM=nccl keeps plain NCCL) */
   if (!ierr) {
@@ -475,6 +528,12 @@ inline PetscErrorCode PetscDSSetJacobian(PetscDS ds, PetscInt f, PetscInt g, Pet
   ds->g3 = g3; ds->problem = -1;
   return 0;
 }
+/* PetscDSSetBdResidual(prob, 0, f0_bd_u, f1_bd_zero) -- ex12.cpp:1226,1231 */
+inline PetscErrorCode PetscDSSetBdResidual(PetscDS ds, PetscInt f, PetscBdPointFunc f0, PetscBdPointFunc f1) {
+  if (f != 0) return PETSC_ERR_SUP;
+  ds->f0_bd = f0; ds->f1_bd = f1; ds->problem = -1;
+  return 0;
+}
 inline PetscErrorCode PetscDSSetExactSolution(PetscDS ds, PetscInt f, PetscSimplePointFunc sol, void *ctx) {
   if (f != 0) return PETSC_ERR_SUP;
   ds->exact = sol; ds->exact_ctx = ctx;
@@ -483,10 +542,16 @@ inline PetscErrorCode PetscDSSetExactSolution(PetscDS ds, PetscInt f, PetscSimpl
 inline PetscErrorCode DMAddBoundary(DM dm, DMBoundaryConditionType type, const char *, const char *labelname, PetscInt field,
                                     PetscInt numcomps, const PetscInt *, void (*bcFunc)(void), void (*)(void), PetscInt numids,
                                     const PetscInt *ids, void *) {
-  if (type != DM_BC_ESSENTIAL || field != 0 || numcomps != 0 || numids != 1 || ids[0] != 1 || strcmp(labelname, "marker")) {
-    fprintf(stderr, "[0]PETSC ERROR: only the essential condition on label \"marker\" = 1 is built (ex12.cpp:1237-1239)\n");
+  /* ex12.cpp:1237-1239: DM_BC_ESSENTIAL on label "marker" (-bc_type dirichlet) or DM_BC_NATURAL on label "boundary"
+   * (-bc_type neumann: nothing is constrained, the PetscDSSetBdResidual callbacks are integrated over the boundary facets) */
+  const bool essential = type == DM_BC_ESSENTIAL && !strcmp(labelname, "marker");
+  const bool natural = type == DM_BC_NATURAL && !strcmp(labelname, "boundary");
+  if (!(essential || natural) || field != 0 || numcomps != 0 || numids != 1 || ids[0] != 1) {
+    fprintf(stderr, "[0]PETSC ERROR: only DM_BC_ESSENTIAL on label \"marker\" = 1 and DM_BC_NATURAL on label \"boundary\" = 1 are built (ex12.cpp:1237-1239)\n");
     return PETSC_ERR_SUP;
   }
+  if (dm->set_up) { fprintf(stderr, "[0]PETSC ERROR: DMAddBoundary after the DM was set up (vectors or matrices exist)\n"); return OHP_ERR_ORDER; }
+  dm->bc_type = natural ? OHP_BC_NATURAL : OHP_BC_ESSENTIAL;
   dm->ds.bc = (PetscSimplePointFunc)bcFunc;
   dm->ds.problem = -1;
   dm->has_bc = true;
@@ -500,6 +565,11 @@ inline PetscErrorCode ohp_ds_problem(PetscDS ds, int *problem) {
     if (it == reg.end()) {
       fprintf(stderr, "[0]PETSC ERROR: this (f0, f1, g3, bc) callback set has no device instantiation: declare it with "
                       "OHP_DEFINE_PROBLEM(...) in the translation unit that defines the callbacks\n");
+      return PETSC_ERR_SUP;
+    }
+    if (ds->f0_bd && ((void *)ds->f0_bd != it->second.f0_bd || (void *)ds->f1_bd != it->second.f1_bd)) {
+      fprintf(stderr, "[0]PETSC ERROR: the boundary callbacks given to PetscDSSetBdResidual have no device instantiation: declare the "
+                      "callback set with OHP_DEFINE_PROBLEM_BD(name, f0, f1, g3, bc, exact, f0_bd, f1_bd)\n");
       return PETSC_ERR_SUP;
     }
     ds->problem = it->second.id;
@@ -563,7 +633,16 @@ inline PetscErrorCode MatGetSize(Mat A, PetscInt *M, PetscInt *N) {
   if (N) *N = (PetscInt)info.n_global;
   return ierr;
 }
-inline PetscErrorCode MatSetNullSpace(Mat, MatNullSpace) { return 0; }
+/* MatNullSpaceCreate(comm, PETSC_TRUE, 0, NULL, &nullSpace) + MatSetNullSpace(A, nullSpace) (ex12.cpp:1534-1538);
+ * MatNullSpaceRemove(nullSpace, u) (ex12.cpp:1667); MatNullSpaceDestroy (ex12.cpp:1695).  Only the constant null space. */
+inline PetscErrorCode MatNullSpaceCreate(MPI_Comm, PetscBool has_cnst, PetscInt n, const Vec *, MatNullSpace *sp) {
+  if (n != 0) { fprintf(stderr, "[0]PETSC ERROR: MatNullSpaceCreate: only the constant null space is built (ex12.cpp:1536)\n"); return PETSC_ERR_SUP; }
+  *sp = new _p_MatNullSpace{has_cnst};
+  return 0;
+}
+inline PetscErrorCode MatNullSpaceDestroy(MatNullSpace *sp) { if (sp && *sp) { delete *sp; *sp = nullptr; } return 0; }
+inline PetscErrorCode MatSetNullSpace(Mat A, MatNullSpace sp) { return ohp_mat_set_nullspace(A->m, sp && sp->has_cnst ? 1 : 0); }
+inline PetscErrorCode MatNullSpaceRemove(MatNullSpace sp, Vec u) { return (sp && sp->has_cnst) ? ohp_vec_remove_constant(u->v) : 0; }
 
 /* ---- projection / error ---- */
 inline PetscErrorCode DMProjectFunction(DM dm, PetscReal, PetscSimplePointFunc *funcs, void **, InsertMode, Vec u) {
@@ -670,7 +749,32 @@ inline PetscErrorCode SNESSetFromOptions(SNES snes) {
   if (set) {
     if (!strcmp(buf, "none")) snes->opts.ksp.pc = OHP_PC_NONE;
     else if (!strcmp(buf, "jacobi")) snes->opts.ksp.pc = OHP_PC_JACOBI;
-    else { fprintf(stderr, "[0]PETSC ERROR: -pc_type %s: only none and jacobi are built\n", buf); return PETSC_ERR_SUP; }
+    else if (!strcmp(buf, "ksp") || !strcmp(buf, "chebyshev")) {
+      /* -pc_type ksp -ksp_ksp_type chebyshev -ksp_pc_type jacobi -ksp_ksp_max_it k [-ksp_ksp_chebyshev_eigenvalues emin,emax]:
+       * PETSc's way of using a Chebyshev/Jacobi polynomial as the preconditioner of the outer CG (PCKSP) */
+      char inner[64] = "chebyshev", ipc[64] = "jacobi";
+      PetscBool iset;
+      PetscOptionsGetString(NULL, NULL, "-ksp_ksp_type", inner, sizeof(inner), &iset);
+      PetscOptionsGetString(NULL, NULL, "-ksp_pc_type", ipc, sizeof(ipc), &iset);
+      if (strcmp(inner, "chebyshev") || strcmp(ipc, "jacobi")) {
+        fprintf(stderr, "[0]PETSC ERROR: -pc_type ksp: only -ksp_ksp_type chebyshev with -ksp_pc_type jacobi is built\n");
+        return PETSC_ERR_SUP;
+      }
+      snes->opts.ksp.pc = OHP_PC_CHEBYSHEV;
+      PetscInt k = 0;
+      PetscOptionsGetInt(NULL, NULL, "-ksp_ksp_max_it", &k, NULL);
+      snes->opts.ksp.cheb_its = k;
+      char eb[128];
+      PetscOptionsGetString(NULL, NULL, "-ksp_ksp_chebyshev_eigenvalues", eb, sizeof(eb), &iset);
+      if (iset) {
+        double lo = 0.0, hi = 0.0;
+        if (sscanf(eb, "%lf,%lf", &lo, &hi) != 2 || !(hi > lo) || !(lo > 0.0)) {
+          fprintf(stderr, "[0]PETSC ERROR: -ksp_ksp_chebyshev_eigenvalues %s: expected emin,emax with 0 < emin < emax\n", eb);
+          return PETSC_ERR_ARG_WRONG;
+        }
+        snes->opts.ksp.cheb_emin = lo; snes->opts.ksp.cheb_emax = hi;
+      }
+    } else { fprintf(stderr, "[0]PETSC ERROR: -pc_type %s: none, jacobi and ksp (Chebyshev/Jacobi polynomial) are built\n", buf); return PETSC_ERR_SUP; }
   }
   PetscBool b;
   PetscOptionsHasName(NULL, NULL, "-snes_monitor_short", &b); snes->monitor = b;

@@ -16,7 +16,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("OHP_LIB") or os.path.join(_HERE, "lib", "libohp.so")  # OHP_LIB: A/B builds of the same ABI
 
 PROBLEM_COEFF_NONE, PROBLEM_ANALYTIC, PROBLEM_NONLINEAR, PROBLEM_CIRCLE, PROBLEM_CROSS = 0, 1, 2, 3, 4
-PC_NONE, PC_JACOBI = 0, 1
+PC_NONE, PC_JACOBI, PC_CHEBYSHEV = 0, 1, 2
+BC_ESSENTIAL, BC_NATURAL, BC_NONE = 0, 1, 2
+ALGO_GENERAL_PCG = 6
 KSP_CG, KSP_PIPECG = 0, 1
 
 _i32p = ctypes.POINTER(ctypes.c_int32)
@@ -48,13 +50,15 @@ class KspOptions(ctypes.Structure):
     _fields_ = [("rtol", ctypes.c_double), ("abstol", ctypes.c_double), ("dtol", ctypes.c_double),
                 ("max_it", ctypes.c_int32), ("pc", ctypes.c_int32), ("check_every", ctypes.c_int32),
                 ("history_cap", ctypes.c_int32), ("history", _f64p), ("profile", ctypes.c_int32),
-                ("ksp_type", ctypes.c_int32)]
+                ("ksp_type", ctypes.c_int32), ("cheb_its", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+                ("cheb_emin", ctypes.c_double), ("cheb_emax", ctypes.c_double)]
 
 
 class KspResult(ctypes.Structure):
     _fields_ = [("its", ctypes.c_int32), ("reason", ctypes.c_int32), ("rnorm", ctypes.c_double),
                 ("rnorm0", ctypes.c_double), ("spmv_ms", ctypes.c_float), ("spmv_samples", ctypes.c_int32),
-                ("total_ms", ctypes.c_float), ("algo", ctypes.c_int32)]
+                ("total_ms", ctypes.c_float), ("algo", ctypes.c_int32), ("cheb_emin", ctypes.c_double),
+                ("cheb_emax", ctypes.c_double), ("spmvs", ctypes.c_int32), ("reserved0", ctypes.c_int32)]
 
 
 SNES_MONITOR_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int32, ctypes.c_double)
@@ -359,6 +363,11 @@ class Vec:
     def device_ptr(self):
         return lib().ohp_vec_device_ptr(self.h)
 
+    def remove_constant(self):
+        """MatNullSpaceRemove for the constant null space (ex12.cpp:1667): subtract the global mean."""
+        _chk(lib().ohp_vec_remove_constant(self.h))
+        return self
+
 
 class Mat:
     def __init__(self, mesh):
@@ -383,13 +392,20 @@ class Mat:
         _chk(lib().ohp_mat_mult(self.h, x.h, y.h))
         return y
 
+    def set_nullspace(self, has_constant=True):
+        """MatNullSpaceCreate(comm, PETSC_TRUE, 0, NULL) + MatSetNullSpace (ex12.cpp:1534-1538)."""
+        _chk(lib().ohp_mat_set_nullspace(self.h, int(bool(has_constant))))
+        return self
 
-def ksp_options(rtol=1e-5, abstol=1e-50, dtol=1e5, max_it=10000, pc=PC_NONE, check_every=0, profile=0, ksp_type=KSP_CG):
+
+def ksp_options(rtol=1e-5, abstol=1e-50, dtol=1e5, max_it=10000, pc=PC_NONE, check_every=0, profile=0, ksp_type=KSP_CG,
+                cheb_its=0, cheb_emin=0.0, cheb_emax=0.0):
     o = KspOptions()
     _chk(lib().ohp_ksp_default_options(ctypes.byref(o)))
     o.rtol, o.abstol, o.dtol, o.max_it, o.pc, o.check_every = rtol, abstol, dtol, int(max_it), int(pc), int(check_every)
     o.profile = int(profile)
     o.ksp_type = int(ksp_type)
+    o.cheb_its, o.cheb_emin, o.cheb_emax = int(cheb_its), float(cheb_emin), float(cheb_emax)
     return o
 
 
@@ -408,7 +424,8 @@ def ksp_cg(A, b, x, opts=None, history=False):
         o.history_cap = 0
         o.history = None
     out = dict(its=res.its, reason=res.reason, rnorm=res.rnorm, rnorm0=res.rnorm0, spmv_ms=res.spmv_ms,
-               spmv_samples=res.spmv_samples, total_ms=res.total_ms)
+               spmv_samples=res.spmv_samples, total_ms=res.total_ms, algo=res.algo, cheb_emin=res.cheb_emin,
+               cheb_emax=res.cheb_emax, spmvs=res.spmvs)
     if history:
         out["hist"] = hist[:res.its + 1].copy()
     return out
@@ -468,6 +485,11 @@ class Mesh:
         rr = np.ascontiguousarray(root_rank, dtype=np.int32)
         rp = np.ascontiguousarray(root_point, dtype=np.int32)
         _chk(lib().ohp_mesh_set_point_sf(self.h, lp.size, _ptr(lp, _i32p), _ptr(rr, _i32p), _ptr(rp, _i32p)))
+
+    def set_bc_type(self, bc_type):
+        """DMAddBoundary's type (ex12.cpp:1237): BC_ESSENTIAL (default), BC_NATURAL (-bc_type neumann), BC_NONE."""
+        _chk(lib().ohp_mesh_set_bc_type(self.h, int(bc_type)))
+        return self
 
     def setup(self):
         _chk(lib().ohp_mesh_setup(self.h))

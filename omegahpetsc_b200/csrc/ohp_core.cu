@@ -377,10 +377,12 @@ __global__ void k_mark_boundary(const int32_t *cells, int nC, const int32_t *ptr
   }
 }
 
-__global__ void k_free_mask(const uint8_t *bnd, const uint8_t *owned, int nV, int32_t *mask, int32_t *bmask) {
+/* `constrain` = 0: DM_BC_NATURAL / no boundary condition (ex12.cpp:1237, -bc_type neumann|none): the "marker" vertices
+ * keep their dofs */
+__global__ void k_free_mask(const uint8_t *bnd, const uint8_t *owned, int nV, int32_t *mask, int32_t *bmask, int constrain) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nV) return;
-  mask[v] = (owned[v] && !bnd[v]) ? 1 : 0;
+  mask[v] = (owned[v] && !(constrain && bnd[v])) ? 1 : 0;
   bmask[v] = bnd[v] ? 1 : 0;
 }
 
@@ -744,6 +746,15 @@ extern "C" int ohp_mesh_set_label(ohp_mesh m, int32_t n, const int32_t *vertices
   return 0;
 }
 
+extern "C" int ohp_mesh_set_bc_type(ohp_mesh m, int bc_type) {
+  if (!m) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_mesh_set_bc_type: null mesh");
+  if (m->setup_done) OHP_FAIL(OHP_ERR_ORDER, "ohp_mesh_set_bc_type: called after ohp_mesh_setup");
+  if (bc_type != OHP_BC_ESSENTIAL && bc_type != OHP_BC_NATURAL && bc_type != OHP_BC_NONE)
+    OHP_FAIL(OHP_ERR_ARG_OUTOFRANGE, "ohp_mesh_set_bc_type: unknown type %d", bc_type);
+  m->bc_type = bc_type;
+  return 0;
+}
+
 extern "C" int ohp_mesh_setup(ohp_mesh m) {
   if (!m) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_mesh_setup: null mesh");
   if (m->setup_done) return 0;
@@ -802,7 +813,7 @@ extern "C" int ohp_mesh_setup(ohp_mesh m) {
   }
 
   /* section: owned unconstrained vertices, ascending local point order */
-  k_free_mask<<<nblk(nV, BS), BS, 0, st>>>(m->bnd, m->owned, nV, tmp_a, tmp_b); OHP_CHECK_LAUNCH(ctx);
+  k_free_mask<<<nblk(nV, BS), BS, 0, st>>>(m->bnd, m->owned, nV, tmp_a, tmp_b, m->bc_type == OHP_BC_ESSENTIAL ? 1 : 0); OHP_CHECK_LAUNCH(ctx);
   int64_t n_owned = 0, n_bnd = 0;
   OHP_TRY(ohp_scan_exclusive_i32(ctx, tmp_b, deg, nV, &n_bnd));
   OHP_TRY(ohp_scan_exclusive_i32(ctx, tmp_a, deg, nV, &n_owned));
@@ -1002,7 +1013,7 @@ int ohp_assembly_view_make(ohp_mesh m, const double *u, double *out, ohp_assembl
   vw->row_vertex_dev = m->row_vertex; vw->v2c_ptr_dev = m->v2c_ptr; vw->v2c_dev = m->v2c;
   vw->slot_dev = m->slot; vw->rowptr_dev = m->rowptr; vw->u_dev = u; vw->out_dev = out;
   vw->stream = (void *)m->ctx->stream;
-  vw->owned_dev = m->owned; vw->n_partials = 0;
+  vw->owned_dev = m->owned; vw->n_partials = 0; vw->bnd_dev = m->bnd;
   vw->n_patches = 0; vw->max_row = m->max_row;
   if (m->patch) {
     const ohp_patch_plan *pl = m->patch;

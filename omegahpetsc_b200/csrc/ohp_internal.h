@@ -167,6 +167,7 @@ struct ohp_mesh_s {
   /* "marker" label set point by point by the caller (DMSetLabelValue) instead of detected here */
   bool has_user_label;
   std::vector<int32_t> user_label;
+  int bc_type;                  /* OHP_BC_ESSENTIAL (0, default) | OHP_BC_NATURAL | OHP_BC_NONE: the last two constrain no dof */
   ohp_patch_plan *patch;        /* NULL: the row kernels are used (limits exceeded, OHP_ASM=rows, or not built yet) */
   struct ohp_pf_plan *pfplan;   /* tables of the one-launch pipelined CG (ohp_linalg.cu), built on first use */
   struct ohp_fused_plan *fused; /* tables of the fused persistent CG kernel, built on first use (ohp_cg_fused.cu) */
@@ -192,6 +193,7 @@ struct ohp_mat_s {
   double *pm0, *pm1, *pw0, *pw1; /* pipelined recurrence: SpMV inputs m = M^-1 w (serial runs) and w, double-buffered */
   double *hist;
   int32_t hist_cap;
+  int32_t nullspace;            /* 1: the constants are in the kernel (ohp_mat_set_nullspace) */
 };
 
 /* ohp_core.cu */
@@ -237,8 +239,12 @@ void ohp_fused_plan_free(ohp_context ctx, struct ohp_fused_plan *p);
 /* ohp_cg_persistent.cu */
 int ohp_cg_persistent_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o, ohp_ksp_result *res, bool p2p);
 
+/* ohp_pcg.cu */
+int ohp_pcg_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o, ohp_ksp_result *res);
+
 /* ohp_problems.cu */
 int ohp_problem_lookup(int id, ohp_assembly_launcher *res, ohp_assembly_launcher *jac,
                        ohp_assembly_launcher *proj, ohp_assembly_launcher *l2);
+int ohp_problem_lookup_bd(int id, ohp_assembly_launcher *bd);
 
 #endif

@@ -1197,6 +1197,7 @@ int ohp_extract_dinv(ohp_mat A) {
 extern "C" int ohp_ksp_default_options(ohp_ksp_options *o) {
   o->rtol = 1e-5; o->abstol = 1e-50; o->dtol = 1e5; o->max_it = 10000; o->pc = OHP_PC_NONE;
   o->check_every = 0; o->history_cap = 0; o->history = nullptr; o->profile = 0; o->ksp_type = OHP_KSP_CG;
+  o->cheb_its = 0; o->reserved0 = 0; o->cheb_emin = 0.0; o->cheb_emax = 0.0;
   return 0;
 }
 
@@ -2302,9 +2303,12 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
   const int n = m->n_owned;
   if (b->n != n || x->n != n) OHP_FAIL(OHP_ERR_ARG_SIZ, "ohp_ksp_cg: vector sizes do not match the matrix");
   if (b == x) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_ksp_cg: b and x must differ");
-  if (o->pc != OHP_PC_NONE && o->pc != OHP_PC_JACOBI) OHP_FAIL(OHP_ERR_SUP, "ohp_ksp_cg: pc %d", o->pc);
+  if (o->pc != OHP_PC_NONE && o->pc != OHP_PC_JACOBI && o->pc != OHP_PC_CHEBYSHEV) OHP_FAIL(OHP_ERR_SUP, "ohp_ksp_cg: pc %d", o->pc);
   OHP_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
+  res->cheb_emin = res->cheb_emax = 0.0; res->spmvs = 0; res->reserved0 = 0;
+  /* the polynomial preconditioner and the null-space projection run in the general loop of ohp_pcg.cu */
+  if (o->pc == OHP_PC_CHEBYSHEV || A->nullspace) return ohp_pcg_solve(A, b, x, o, res);
   {
     /* algorithm selection (the role of -ksp_type among PETSc's CG variants): the three-launch classic
      * recurrence moves the fewest bytes and wins when the per-GPU problem is large; the persistent

@@ -5,7 +5,7 @@
  *
  * The loop is written against an `Ops` policy (vectors are small integer handles) so that the SAME control flow that
  * drives the device kernels in ohp_pcg.cu can be instantiated over plain host arrays by the CPU unit test
- * (tests/host/pcg_host.cpp) and compared with the oracle without a GPU.  Nothing here touches memory itself.
+ * (tests/host/pcg_host.cpp) and compared with the CPU restatement of the tests without a GPU.  Nothing here touches memory itself.
  *
  * Restated [PETSc-internal]:
  *   KSPSolve_CG + KSPConvergedDefault (as ohp_ksp_cg: zero initial guess, preconditioned norm, reasons 2/3/-3/-4/-8/-9),
@@ -102,7 +102,7 @@ template <class Ops> int estimate_emax(Ops &ops, int steps, double *lam, int *sp
 
 /* the interval the polynomial is built for.  emax <= 0: 1.1 x the estimate (PETSc's default safety factor).
  * emin <= 0: emax / (4 k^2 + 36) -- as a preconditioner for CG (not a multigrid smoother) the polynomial pays most
- * when its interval grows with the degree (measured on the oracle, 256^2 box: total operator applications stay within
+ * when its interval grows with the degree (measured on the 256^2 box with the CPU harness: total operator applications stay within
  * 5-15 % of plain CG's while the outer iterations, i.e. the global reductions, drop 4-14x); PETSc's smoother default
  * (emin = 0.1 x estimate) is obtained by passing both ends explicitly. */
 inline void chebyshev_interval(int k, double est, double *emin, double *emax) {

@@ -21,8 +21,20 @@
 
 namespace {
 
+/* natural boundary data of -bc_type neumann: f0_bd_u (ex12.cpp:179-186), f1_bd_zero (ex12.cpp:188-195), registered for every
+ * coefficient variant by SetupProblem (ex12.cpp:1226,1231) */
+struct NaturalBd {
+  OHP_HD static void f0_bd(OHP_BD_ARGS, double f0[]) {
+    f0[0] = 0.0;
+    for (int d = 0; d < dim; ++d) f0[0] += -n[d] * 2.0 * x[d];
+  }
+  OHP_HD static void f1_bd(OHP_BD_ARGS, double f1[]) {
+    for (int comp = 0; comp < dim; ++comp) f1[comp] = 0.0;
+  }
+};
+
 /* exact / Dirichlet data: quadratic_u_2d (ex12.cpp:113-117), quadratic_u_3d (ex12.cpp:408-412) */
-struct QuadraticBC {
+struct QuadraticBC : NaturalBd {
   OHP_HD static int bc(int dim, double time, const double x[], int Nc, double *u, void *ctx) {
     if (dim == 3) *u = 2.0 * (x[0] * x[0] + x[1] * x[1] + x[2] * x[2]) / 3.0;
     else *u = x[0] * x[0] + x[1] * x[1];
@@ -78,7 +90,7 @@ struct ProblemNonlinear : QuadraticBC {
 
 /* COEFF_CIRCLE / COEFF_CROSS: f0_circle_u (ex12.cpp:155-166), f0_cross_u (:168-177) with f1_u and g3_uu;
  * Dirichlet and "exact" data circle_u_2d (:127-136), cross_u_2d (:138-145), selected at :1197-1213 */
-struct ProblemCircle {
+struct ProblemCircle : NaturalBd {
   static constexpr bool kJacobianUsesU = false;
   OHP_HD static void f0(OHP_PF_ARGS, double f0[]) {
     const double alpha = 500., radius2 = 0.15 * 0.15;
@@ -97,7 +109,7 @@ struct ProblemCircle {
   }
   OHP_HD static int exact(int dim, double time, const double x[], int Nc, double *u, void *ctx) { return bc(dim, time, x, Nc, u, ctx); }
 };
-struct ProblemCross {
+struct ProblemCross : NaturalBd {
   static constexpr bool kJacobianUsesU = false;
   OHP_HD static double cross(const double x[]) {
     const double alpha = 50 * 4;
@@ -116,10 +128,11 @@ struct ProblemCross {
 };
 
 struct ProblemEntry {
-  ohp_assembly_launcher residual, jacobian, project, l2diff;
+  ohp_assembly_launcher residual, jacobian, project, l2diff, bd_residual;
 };
 template <class P> ProblemEntry builtin() {
-  return {ohp::launch_residual_any<P>, ohp::launch_jacobian_any<P>, ohp::launch_project_exact_any<P>, ohp::launch_l2_diff_any<P>};
+  return {ohp::launch_residual_any<P>, ohp::launch_jacobian_any<P>, ohp::launch_project_exact_any<P>, ohp::launch_l2_diff_any<P>,
+          ohp::launch_bd_residual_any<P>};
 }
 
 std::mutex g_reg_mutex;
@@ -147,8 +160,24 @@ extern "C" int ohp_problem_register(ohp_assembly_launcher residual, ohp_assembly
                                     ohp_assembly_launcher project_exact, ohp_assembly_launcher l2_diff, int *problem_id) {
   if (!residual || !jacobian || !problem_id) OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_problem_register: null launcher");
   std::lock_guard<std::mutex> lock(g_reg_mutex);
-  registry().push_back({residual, jacobian, project_exact, l2_diff});
+  registry().push_back({residual, jacobian, project_exact, l2_diff, nullptr});
   *problem_id = (int)registry().size() - 1;
+  return 0;
+}
+
+extern "C" int ohp_problem_set_bd_residual(int problem_id, ohp_assembly_launcher bd_residual) {
+  std::lock_guard<std::mutex> lock(g_reg_mutex);
+  auto &r = registry();
+  if (problem_id < 0 || problem_id >= (int)r.size()) OHP_FAIL(OHP_ERR_ARG_OUTOFRANGE, "ohp_problem_set_bd_residual: unknown problem id %d", problem_id);
+  r[problem_id].bd_residual = bd_residual;
+  return 0;
+}
+
+int ohp_problem_lookup_bd(int id, ohp_assembly_launcher *bd) {
+  std::lock_guard<std::mutex> lock(g_reg_mutex);
+  auto &r = registry();
+  if (id < 0 || id >= (int)r.size()) OHP_FAIL(OHP_ERR_ARG_OUTOFRANGE, "unknown problem id %d", id);
+  *bd = r[id].bd_residual;
   return 0;
 }
 
@@ -169,6 +198,14 @@ extern "C" int ohp_residual(ohp_mesh m, int problem, ohp_vec u, ohp_vec F) {
   int rc = fn(&vw);
   m->ctx->launches++;
   if (rc) OHP_FAIL(rc, "ohp_residual: kernel launch failed (%s)", cudaGetErrorString(cudaGetLastError()));
+  if (m->bc_type == OHP_BC_NATURAL) { /* DM_BC_NATURAL: the boundary integral of the PetscDSSetBdResidual callbacks (ex12.cpp:1226-1238) */
+    ohp_assembly_launcher bd = nullptr;
+    OHP_TRY(ohp_problem_lookup_bd(problem, &bd));
+    if (!bd) OHP_FAIL(OHP_ERR_SUP, "ohp_residual: the mesh has a natural boundary condition but problem %d registered no boundary residual", problem);
+    rc = bd(&vw);
+    m->ctx->launches++;
+    if (rc) OHP_FAIL(rc, "ohp_residual: boundary kernel launch failed (%s)", cudaGetErrorString(cudaGetLastError()));
+  }
   return 0;
 }
 

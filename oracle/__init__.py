@@ -141,14 +141,15 @@ def newton(problem, cells, coords, gidx, N, rowptr, colidx, u0=None, snes_rtol=1
     return dict(u=u, snes_its=int(out[0]), ksp_its=int(out[1]), reason=int(out[2]), norms=norms[: out[0] + 1].copy())
 
 
-def bd_residual(cells, coords, gidx, N, u, F):
-    """F += natural-boundary term of ex12's -bc_type neumann (f0_bd_u, f1_bd_zero); returns F."""
+def bd_residual(cells, coords, gidx, N, u, F, bd_set=0):
+    """F += natural-boundary term of ex12's -bc_type neumann (f0_bd_u, f1_bd_zero); returns F.
+    bd_set=1: a synthetic callback pair that reads u, grad u, x and n and has a non-zero f1."""
     cells = np.ascontiguousarray(cells, dtype=np.int32)
     coords = np.ascontiguousarray(coords, dtype=np.float64)
     nC, nc = cells.shape
     u = np.ascontiguousarray(u, dtype=np.float64)
     F = np.ascontiguousarray(F, dtype=np.float64)
-    rc = lib().orc_bd_residual(nc - 1, ctypes.c_int64(nC), gidx.size, _p(cells, c_i32p), _p(coords, c_f64p),
+    rc = lib().orc_bd_residual(int(bd_set), nc - 1, ctypes.c_int64(nC), gidx.size, _p(cells, c_i32p), _p(coords, c_f64p),
                                _p(gidx, c_i32p), N, _p(u, c_f64p), _p(F, c_f64p))
     assert rc == 0
     return F

@@ -676,6 +676,15 @@ static void cb_f0_bd_u(BD_ARGS, double f0[]) {
 static void cb_f1_bd_zero(BD_ARGS, double f1[]) {
   for (int c = 0; c < dim; ++c) f1[c] = 0.0;
 }
+/* a second, synthetic boundary callback set (not in ex12): reads EVERY argument the integrator supplies -- u, grad u, x, n --
+ * and has a non-zero f1 term, so that the checks of the boundary integrator do not rest on the one callback ex12 ships */
+static void cb_f0_bd_probe(BD_ARGS, double f0[]) {
+  f0[0] = 0.5 * u[0];
+  for (int d = 0; d < dim; ++d) f0[0] += n[d] * u_x[d] + (d + 1) * x[d] * n[d];
+}
+static void cb_f1_bd_probe(BD_ARGS, double f1[]) {
+  for (int d = 0; d < dim; ++d) f1[d] = u[0] * n[d] + 0.25 * x[d];
+}
 
 /* Natural boundary residual [PETSc-internal DMPlexComputeBdResidual_Internal -> PetscFEIntegrateBdResidual_Basic,
  * reached from DMPlexSetSNESLocalFEM ex12.cpp:1540 when SetupProblem registered PetscDSSetBdResidual(prob, 0, f0_bd_u,
@@ -685,14 +694,15 @@ static void cb_f1_bd_zero(BD_ARGS, double f1[]) {
  * 4-point conical rule on a triangle; weights sum to 2):
  *     Fe[b] += w_q detJ_F ( phi_b(x_q) f0_bd(u, grad u, x_q, n) + grad(phi_b) . f1_bd(...) ),   detJ_F = |F| / 2,
  * phi_b = the cell's basis restricted to the face, n = unit normal pointing out of c.  ADDS into F (call after
- * orc_residual); constrained rows (gidx < 0) are dropped like everywhere else. */
-int orc_bd_residual(int dim, int64_t nC, int nV, const int *cells, const double *coords, const int *gidx, int N,
+ * orc_residual); constrained rows (gidx < 0) are dropped like everywhere else.  bd_set 0 = ex12's callbacks, 1 = the
+ * synthetic probe set above. */
+int orc_bd_residual(int bd_set, int dim, int64_t nC, int nV, const int *cells, const double *coords, const int *gidx, int N,
                     const double *u, double *F) {
   (void)N;
   const int nc = dim + 1, nf = dim;
   orc_problem p;
   if (orc_problem_get(0, dim, &p)) return 1;
-  const orc_bdfn f0_bd = cb_f0_bd_u, f1_bd = cb_f1_bd_zero;
+  const orc_bdfn f0_bd = bd_set ? cb_f0_bd_probe : cb_f0_bd_u, f1_bd = bd_set ? cb_f1_bd_probe : cb_f1_bd_zero;
   int64_t *ptr; int *adj;
   build_v2c(nc, nC, nV, cells, &ptr, &adj);
   double *uloc = (double *)malloc((size_t)nV * sizeof(double));

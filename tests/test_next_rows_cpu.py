@@ -267,3 +267,81 @@ def test_product_control_flow_edge_cases(oracle_mod, pcg_host):
     # iteration limit
     h = pcg_host(rp, ci, vals, F, rtol=1e-14, maxit=3, pc=2, cheb_its=2)
     assert (h["its"], h["reason"]) == (3, -3)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the product's natural-boundary row function (include/ohp_fem.cuh: bd_residual_row, __host__ __device__) on host arrays
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def bd_host():
+    import shutil
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    out = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libbd_host.so")
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O2", "--expt-relaxed-constexpr",
+                    "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "host", "bd_host.cu"), "-o", so], check=True)
+    L = ctypes.CDLL(so)
+
+    def rows(bd_set, cells, coords, lidx, u, bnd):
+        """the data layout ohp_mesh_setup builds: stars as (cell*4 + corner) ascending, rows = vertices with lidx >= 0"""
+        cells = np.ascontiguousarray(cells, np.int32)
+        coords = np.ascontiguousarray(coords, np.float64)
+        nC, nc = cells.shape
+        nV = coords.shape[0]
+        code = (np.arange(nC, dtype=np.int64)[:, None] * 4 + np.arange(nc)[None, :]).reshape(-1)
+        vert = cells.reshape(-1)
+        order = np.lexsort((code, vert))
+        v2c = code[order].astype(np.int32)
+        v2c_ptr = np.zeros(nV + 1, np.int32)
+        np.add.at(v2c_ptr, vert + 1, 1)
+        v2c_ptr = np.cumsum(v2c_ptr).astype(np.int32)
+        lidx = np.ascontiguousarray(lidx, np.int32)
+        n_rows = int((lidx >= 0).sum())
+        row_vertex = np.zeros(max(n_rows, 1), np.int32)
+        row_vertex[lidx[lidx >= 0]] = np.nonzero(lidx >= 0)[0]
+        u = np.ascontiguousarray(u, np.float64)
+        bnd = np.ascontiguousarray(bnd, np.uint8)
+        outv = np.zeros(max(n_rows, 1))
+        c_u8p = ctypes.POINTER(ctypes.c_uint8)
+        rc = L.bd_host_rows(int(bd_set), nc - 1, nC, nV, _p(cells, c_i32p), _p(coords, c_f64p), _p(lidx, c_i32p), _p(u, c_f64p),
+                            _p(v2c_ptr, c_i32p), _p(v2c, c_i32p), n_rows, _p(row_vertex, c_i32p), _p(bnd, c_u8p), _p(outv, c_f64p))
+        assert rc == 0
+        return outv[:n_rows]
+
+    return rows
+
+
+@pytest.mark.parametrize("name", ["one_tri", "fan4", "box2d_8x8", "box2d_33x17", "sheared_21x13", "box3d_5x4x3", "warped3d_6x5x7"])
+@pytest.mark.parametrize("bd_set", [0, 1])
+def test_product_boundary_rows_match_oracle(oracle_mod, bd_host, name, bd_set):
+    cells, coords = synthetic_meshes()[name]
+    nV = coords.shape[0]
+    bnd = oracle_mod.mark_boundary(cells, nV)
+    gidx = np.arange(nV, dtype=np.int32)  # natural condition: nothing is constrained
+    u = np.sin(3 * coords[:, 0]) * np.cos(2 * coords[:, 1]) + 0.3
+    want = oracle_mod.bd_residual(cells, coords, gidx, nV, u, np.zeros(nV), bd_set=bd_set)
+    got = bd_host(bd_set, cells, coords, gidx, u, bnd)
+    assert np.abs(got - want).max() <= 1e-13 * max(1.0, np.abs(want).max())
+    assert np.abs(want).max() > 0
+
+
+def test_product_boundary_rows_with_constrained_and_permuted_dofs(oracle_mod, bd_host):
+    """rows in another order than the vertices, and some vertices constrained (their value comes from the Dirichlet function
+    inside the row function): the mixed situation of a user who integrates a boundary term on an essential-BC mesh"""
+    cells, coords = synthetic_meshes()["sheared_21x13"]
+    nV = coords.shape[0]
+    bnd = oracle_mod.mark_boundary(cells, nV)
+    rng = np.random.default_rng(5)
+    constrained = (rng.random(nV) < 0.2) & (bnd == 1)
+    free = np.nonzero(~constrained)[0]
+    perm = rng.permutation(free.size)
+    gidx = np.full(nV, -1, np.int32)
+    gidx[free] = perm
+    u = rng.normal(size=free.size)
+    want = oracle_mod.bd_residual(cells, coords, gidx, free.size, u, np.zeros(free.size), bd_set=1)
+    got = bd_host(1, cells, coords, gidx, u, bnd)
+    assert np.abs(got - want).max() <= 1e-13 * max(1.0, np.abs(want).max())
