@@ -230,7 +230,7 @@ extern "C" int ohp_mesh_create(ohp_context ctx, int dim, int32_t nC, int32_t nV,
   OHP_CUDA(cudaSetDevice(ctx->device));
   ohp_mesh m = new ohp_mesh_s();
   m->ctx = ctx; m->dim = dim; m->nc = nc; m->nC = nC; m->nV = nV;
-  m->cells = nullptr; m->coords = nullptr; m->owned = nullptr; m->setup_done = false;
+  m->cells = nullptr; m->coords = nullptr; m->owned = nullptr; m->setup_done = false; m->bc_type = OHP_BC_ESSENTIAL;
   m->v2c_ptr = m->v2c = nullptr; m->bnd = nullptr; m->lidx = m->row_vertex = nullptr; m->ldof_gid = nullptr;
   m->rowptr = m->colidx = nullptr; m->col16 = nullptr; m->slot = nullptr; m->tile_row = nullptr; m->halo = nullptr; m->p2p = nullptr; m->ghost_cta = nullptr;
   m->n_owned = m->n_ghost = m->n_bnd = 0; m->n_global = m->row_start = m->nnz = 0; m->max_row = 0; m->n_tiles = 0; m->max_tile_rows = 0;

@@ -927,7 +927,7 @@ extern "C" int ohp_mat_create(ohp_mesh m, ohp_mat *out) {
   if (!m || !m->setup_done) OHP_FAIL(OHP_ERR_ORDER, "ohp_mat_create: mesh not set up");
   OHP_CUDA(cudaSetDevice(m->ctx->device));
   ohp_mat A = new ohp_mat_s();
-  A->mesh = m; A->r = A->z = A->p = A->p1 = A->w = A->dinv = A->hist = A->s = A->r1 = A->z1 = A->s1 = nullptr; A->hist_cap = 0;
+  A->mesh = m; A->r = A->z = A->p = A->p1 = A->w = A->dinv = A->hist = A->s = A->r1 = A->z1 = A->s1 = nullptr; A->hist_cap = 0; A->nullspace = 0;
   OHP_CUDA(OHP_MALLOC(m->ctx, &A->vals, sizeof(double) * ohp_padded_nnz(m->nnz)));
   OHP_CUDA(cudaMemsetAsync(A->vals, 0, sizeof(double) * ohp_padded_nnz(m->nnz), m->ctx->stream));
   *out = A;
