@@ -116,3 +116,13 @@ def test_cxx_picpart_two_gpus_23elm(oracle_mod):
         assert m and int(m.group(1)) == N and int(m.group(2)) == 1, out
         assert abs(int(m.group(3)) - ref["ksp_its"]) <= 1
         assert out.count("KSP Residual norm") == int(m.group(3)) + 1 and "Linear solve converged due to CONVERGED_RTOL" in out
+
+
+def test_two_gpus_next_rows():
+    """SURVEY 8(f) rank 4 across ranks: Chebyshev/Jacobi-preconditioned CG, natural boundary condition, null-space CG, Newton."""
+    if ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = ["timeout", "300", sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29617", os.path.join(ROOT, "tests", "mgpu_next_worker.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "MGPU_NEXT_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
