@@ -229,6 +229,8 @@ ohp_trace ohp_cg_trace_open(ohp_context ctx);
 void ohp_cg_trace_dump(ohp_context ctx, const char *algo);
 int ohp_spmv_launch(ohp_mat A, const double *x, double *y);
 int ohp_extract_dinv(ohp_mat A);
+int ohp_spmv_cheb_launch(ohp_mat A, const double *yk, const double *ykm1, const double *r, const double *dinv, double *ynew,
+                         double a, double b, double c, int *fused);
 
 void ohp_pf_plan_free(ohp_context ctx, struct ohp_pf_plan *pl);
 

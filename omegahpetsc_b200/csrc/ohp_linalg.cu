@@ -797,6 +797,126 @@ static int spmv_enqueue(ohp_mat A, const double *x, double *y, ohp_cg_state *st,
   return 0;
 }
 
+/* ------------------------------------------------------------------------------------ */
+/* SpMV with the Chebyshev update in its consumer loop (general preconditioned CG,          */
+/* ohp_pcg.cu): y_{k+1}[row] = a y_{k-1}[row] + b y_k[row] + c D^-1[row] (r[row] - (A y_k)[row])     */
+/* while (A y_k)[row] is still in a register.  Against SpMV + k_pcg_cheb_step this saves the    */
+/* store and the re-load of A y_k (16 of 56 bytes per row next to the matrix stream) and one     */
+/* kernel boundary per application; the row's four vector operands are loaded before the row is  */
+/* summed, so their latency hides behind the gather (the emit.load / emit.store protocol of the   */
+/* fused pipelined-CG kernel).  Same producer warp, stages, tiles and summation order as           */
+/* k_spmv_tma; the per-row arithmetic is the expression of k_pcg_cheb_step.                        */
+/* ------------------------------------------------------------------------------------ */
+struct ChebRowUpdate {
+  const double *ykm1, *yk, *r, *dinv;
+  double *ynew;
+  double a, b, c;
+  struct Opnd { double km1, k, r, d; };
+  __device__ __forceinline__ Opnd load(int i) const {
+    Opnd o;
+    o.km1 = ykm1 ? ykm1[i] : 0.0; o.k = yk[i]; o.r = r[i]; o.d = dinv[i];
+    return o;
+  }
+  __device__ __forceinline__ void store(int i, double n, const Opnd &o) const {
+    ynew[i] = (ykm1 ? a * o.km1 : 0.0) + b * o.k + c * (o.d * (o.r - n));
+  }
+  __device__ __forceinline__ void operator()(int i, double n) const { store(i, n, load(i)); }
+};
+
+template <int S, int NC, class IDX, bool SPLIT>
+__global__ void __launch_bounds__(NC + 32, 1)
+k_spmv_cheb(const int32_t *__restrict__ rowptr, const IDX *__restrict__ colidx, const double *__restrict__ vals,
+            const int32_t *__restrict__ tile_row, int n_tiles, const double *x, ChebRowUpdate up, int pin_tiles) {
+  constexpr int T = kSpmvTile;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *vals_s = reinterpret_cast<double *>(smem_raw);
+  IDX *cols_s = reinterpret_cast<IDX *>(vals_s + S * T);
+  int32_t *rp_s = reinterpret_cast<int32_t *>(cols_s + S * T);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(rp_s + S * kTmaRpStride);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int t0 = (int)(((int64_t)n_tiles * blockIdx.x) / gridDim.x);
+  const int t1 = (int)(((int64_t)n_tiles * (blockIdx.x + 1)) / gridDim.x);
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 33); mbar_init(empty0 + 8 * s, NC / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == NC / 32) {
+    /* ---------------- producer warp ---------------- */
+    const uint64_t pol_last = l2_policy_evict_last(), pol_first = l2_policy_evict_first();
+    for (int t = t0; t < t1; ++t) {
+      const int i = t - t0, s = i % S;
+      if (i >= S) mbar_wait(empty0 + 8 * s, ((i / S) & 1) ^ 1); /* the first S stages are free at kernel start */
+      const int rs = __ldg(tile_row + t), re = __ldg(tile_row + t + 1);
+      if (lane == 0) {
+        mbar_expect_tx(full0 + 8 * s, T * (8 + (int)sizeof(IDX)));
+        if (pin_tiles != 0) {
+          const uint64_t pol = (i < pin_tiles) ? pol_last : pol_first;
+          tma_load_1d_hint(smem_u32(vals_s + s * T), vals + (size_t)t * T, T * 8, full0 + 8 * s, pol);
+          tma_load_1d_hint(smem_u32(cols_s + s * T), colidx + (size_t)t * T, T * (int)sizeof(IDX), full0 + 8 * s, pol);
+        } else {
+          tma_load_1d(smem_u32(vals_s + s * T), vals + (size_t)t * T, T * 8, full0 + 8 * s);
+          tma_load_1d(smem_u32(cols_s + s * T), colidx + (size_t)t * T, T * (int)sizeof(IDX), full0 + 8 * s);
+        }
+      }
+      int32_t *rp = rp_s + s * kTmaRpStride;
+      for (int j = lane; j <= re - rs; j += 32) cp_async4(smem_u32(rp + j), rowptr + rs + j);
+      if (lane < 2) cp_async4(smem_u32(rp + kSpmvRowCap + 2 + lane), tile_row + t + lane);
+      cp_async_mbar_arrive_noinc(full0 + 8 * s);
+    }
+    return;
+  }
+  /* ---------------- consumer warps ---------------- */
+  spmv_consume_emit<S, NC, IDX, SPLIT, false>(rowptr, colidx, vals, x, vals_s, cols_s, rp_s, full0, empty0, t0, t1, up);
+}
+
+template <int S, int NC, class IDX, bool SPLIT>
+static int spmv_cheb_launch_t(ohp_mat A, const IDX *cols, const double *x, const ChebRowUpdate &up) {
+  ohp_mesh m = A->mesh;
+  ohp_context ctx = m->ctx;
+  constexpr int smem = tma_smem_bytes(S, (int)sizeof(IDX));
+  static unsigned long long configured_devices = 0ull;
+  if (!((configured_devices >> (ctx->device & 63)) & 1ull)) {
+    OHP_CUDA(cudaFuncSetAttribute(k_spmv_cheb<S, NC, IDX, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured_devices |= 1ull << (ctx->device & 63);
+  }
+  const int grid = std::max(1, std::min(m->n_tiles, ctx->num_sms));
+  k_spmv_cheb<S, NC, IDX, SPLIT><<<grid, NC + 32, smem, ctx->stream>>>(m->rowptr, cols, A->vals, m->tile_row, m->n_tiles, x, up,
+                                                                     spmv_pin_tiles(m, grid, (int)sizeof(IDX)));
+  OHP_CHECK_LAUNCH(ctx);
+  return 0;
+}
+
+/* ynew = a ykm1 + b yk + c D^-1 (r - A yk) in ONE launch when the matrix fits the TMA-pipelined SpMV (*fused = 1); otherwise
+ * *fused = 0 and nothing was launched: the caller runs ohp_spmv_launch + the element-wise update.  ykm1 may be NULL (taken
+ * as zero).  yk's ghost tail must be current.  OHP_CHEB_FUSED=0 switches the fused kernel off, =1 also uses it for long-row
+ * matrices (A/B runs). */
+int ohp_spmv_cheb_launch(ohp_mat A, const double *yk, const double *ykm1, const double *r, const double *dinv, double *ynew,
+                         double a, double b, double c, int *fused) {
+  ohp_mesh m = A->mesh;
+  static const char *off = getenv("OHP_CHEB_FUSED");
+  static const char *force = getenv("OHP_SPMV");
+  static const char *idx = getenv("OHP_IDX");
+  *fused = 0;
+  if ((off && off[0] == '0') || force || !spmv_use_tma(m)) return 0;
+  /* Measured on B200 (profiles/r02_chebyshev_time_to_solution*.json, k = 16): 16 M-triangle box 1766 -> 1591 ms per solve
+   * with the fused kernel (plain CG: 1717); the 8 M-tet box (15 non-zeros per row, 1.3 M rows, latency-bound) 29.1 -> 33.2 ms:
+   * there one thread per row already waits on the gather and four more operand loads per row lengthen the chain.  So
+   * long-row matrices keep SpMV + element-wise update unless OHP_CHEB_FUSED=1 asks for the fused kernel (A/B runs). */
+  const bool long_rows = m->nnz > (int64_t)8 * std::max(1, m->n_owned);
+  if (long_rows && !(off && off[0] == '1')) return 0;
+  *fused = 1;
+  if (m->n_owned == 0) return 0;
+  ChebRowUpdate up;
+  up.ykm1 = ykm1; up.yk = yk; up.r = r; up.dinv = dinv; up.ynew = ynew; up.a = a; up.b = b; up.c = c;
+  const bool i16 = m->col16 && !(idx && idx[0] == '3');
+  /* long rows: one thread per row, 14 consumer warps (see spmv_tma_launch) */
+  if (i16) return long_rows ? spmv_cheb_launch_t<3, 448, int16_t, false>(A, m->col16, yk, up) : spmv_cheb_launch_t<3, 608, int16_t, false>(A, m->col16, yk, up);
+  return long_rows ? spmv_cheb_launch_t<3, 448, int32_t, false>(A, m->colidx, yk, up) : spmv_cheb_launch_t<3, 608, int32_t, false>(A, m->colidx, yk, up);
+}
+
 int ohp_spmv_launch(ohp_mat A, const double *x, double *y) {
   if (A->mesh->n_owned == 0) return 0;
   static const ohp_p2p_dev none = {};

@@ -8,9 +8,9 @@
  * The control flow is ohp_pcg.hpp (host, unit-tested on CPU through tests/host/pcg_host.cpp); this file
  * supplies the device operations it runs on: the library's own SpMV (k_spmv_tma / k_spmv_stream behind
  * ohp_spmv_launch, halo exchange included), its dot product, and the element-wise kernels below.  A polynomial
- * application launches k - 1 SpMVs and k fused updates without any reduction or host synchronisation; the two dot
- * products of an outer iteration synchronise with the host (they decide the next coefficients), which the degree
- * amortises.
+ * application is k - 1 launches of k_spmv_cheb (ohp_linalg.cu: the SpMV with the Chebyshev update of the row in its
+ * consumer loop) without any reduction or host synchronisation; the two dot products of an outer iteration synchronise
+ * with the host (they decide the next coefficients), which the degree amortises.
  */
 #include <algorithm>
 
@@ -79,8 +79,14 @@ struct DeviceOps {
     return ohp_spmv_launch(A, vec[x].d, vec[y].d);
   }
   int cheb_first(int y, int r, double scale) { k_pcg_cheb_first<<<grid, 256, 0, st>>>(vec[y].d, vec[r].d, dinv, n, scale); return launched(); }
-  int cheb_step(int ynew, int ykm1, int yk, int r, int t, double a, double b, double c) {
-    k_pcg_cheb_step<<<grid, 256, 0, st>>>(vec[ynew].d, ykm1 >= 0 ? vec[ykm1].d : nullptr, vec[yk].d, vec[r].d, vec[t].d, dinv, n, a, b, c);
+  int cheb_iter(int ynew, int ykm1, int yk, int r, int t, double a, double b, double c) {
+    if (ctx->nranks > 1) OHP_TRY(ohp_halo_exchange(m, vec[yk].d));
+    const double *km1 = ykm1 >= 0 ? vec[ykm1].d : nullptr;
+    int fused = 0;
+    OHP_TRY(ohp_spmv_cheb_launch(A, vec[yk].d, km1, vec[r].d, dinv, vec[ynew].d, a, b, c, &fused)); /* update inside the SpMV */
+    if (fused) return 0;
+    OHP_TRY(ohp_spmv_launch(A, vec[yk].d, vec[t].d));
+    k_pcg_cheb_step<<<grid, 256, 0, st>>>(vec[ynew].d, km1, vec[yk].d, vec[r].d, vec[t].d, dinv, n, a, b, c);
     return launched();
   }
 };

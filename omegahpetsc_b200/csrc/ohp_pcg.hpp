@@ -119,11 +119,12 @@ template <class Ops> int chebyshev_apply(Ops &ops, int its, double emin, double 
   OHP_PCG_TRY(ops.cheb_first(yk, V_R, scale));
   bool km1_is_zero = true;
   for (int k = 1; k < its; ++k) {
-    OHP_PCG_TRY(ops.spmv(yk, V_T));
     ++*spmvs;
     const double c_kp1 = 2.0 * mu * c_k - c_km1, omega = omegaprod * c_k / c_kp1;
-    /* y_{k+1} = (1 - omega) y_{k-1} + omega y_k + scale omega D^-1 (r - A y_k) */
-    OHP_PCG_TRY(ops.cheb_step(ykp1, km1_is_zero ? -1 : ykm1, yk, V_R, V_T, 1.0 - omega, omega, scale * omega));
+    /* y_{k+1} = (1 - omega) y_{k-1} + omega y_k + scale omega D^-1 (r - A y_k): one operator application and the update
+     * (on the device one kernel: the update runs in the SpMV's consumer loop; V_T is scratch for implementations that
+     * apply the operator first) */
+    OHP_PCG_TRY(ops.cheb_iter(ykp1, km1_is_zero ? -1 : ykm1, yk, V_R, V_T, 1.0 - omega, omega, scale * omega));
     km1_is_zero = false;
     const int tmp = ykm1; ykm1 = yk; yk = ykp1; ykp1 = tmp;
     c_km1 = c_k; c_k = c_kp1;

@@ -33,7 +33,8 @@ struct HostOps {
     return 0;
   }
   int cheb_first(int y, int r, double scale) { for (int i = 0; i < N; ++i) v[y][i] = scale * dinv[i] * v[r][i]; return 0; }
-  int cheb_step(int ynew, int ykm1, int yk, int r, int t, double a, double b, double c) {
+  int cheb_iter(int ynew, int ykm1, int yk, int r, int t, double a, double b, double c) {
+    spmv(yk, t);
     for (int i = 0; i < N; ++i)
       v[ynew][i] = (ykm1 >= 0 ? a * v[ykm1][i] : 0.0) + b * v[yk][i] + c * (dinv[i] * (v[r][i] - v[t][i]));
     return 0;
