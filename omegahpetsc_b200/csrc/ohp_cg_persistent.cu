@@ -332,7 +332,8 @@ int ohp_cg_persistent_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_optio
     OHP_CUDA(OHP_MALLOC(ctx, &A->w, sizeof(double) * len));
   }
   if (!A->s) OHP_CUDA(OHP_MALLOC(ctx, &A->s, sizeof(double) * len));
-  if (jac && !A->z) { OHP_CUDA(OHP_MALLOC(ctx, &A->z, sizeof(double) * len)); OHP_CUDA(OHP_MALLOC(ctx, &A->dinv, sizeof(double) * len)); }
+  if (jac && !A->z) OHP_CUDA(OHP_MALLOC(ctx, &A->z, sizeof(double) * len));
+  if (jac && !A->dinv) OHP_CUDA(OHP_MALLOC(ctx, &A->dinv, sizeof(double) * len)); /* another recurrence may have made it already */
   if (jac) OHP_TRY(ohp_extract_dinv(A));
   const int smem = tma_smem_bytes(PS);
   OHP_CUDA(cudaFuncSetAttribute(k_cg_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); /* per device */

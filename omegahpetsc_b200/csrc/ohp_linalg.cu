@@ -2495,7 +2495,8 @@ extern "C" int ohp_ksp_cg(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options
   double *P0 = p2p ? pd.p[0][ctx->rank] : A->p, *P1 = p2p ? pd.p[1][ctx->rank] : A->p1;
   const bool jac = (o->pc == OHP_PC_JACOBI);
   if (jac) {
-    if (!A->z) { OHP_CUDA(OHP_MALLOC(ctx, &A->z, sizeof(double) * len)); OHP_CUDA(OHP_MALLOC(ctx, &A->dinv, sizeof(double) * len)); }
+    if (!A->z) OHP_CUDA(OHP_MALLOC(ctx, &A->z, sizeof(double) * len));
+    if (!A->dinv) OHP_CUDA(OHP_MALLOC(ctx, &A->dinv, sizeof(double) * len)); /* another recurrence may have made it already */
     k_extract_dinv<<<nblk(n, 256), 256, 0, st>>>(m->rowptr, m->colidx, A->vals, n, A->dinv);
     OHP_CHECK_LAUNCH(ctx);
   }
