@@ -345,3 +345,37 @@ def test_product_boundary_rows_with_constrained_and_permuted_dofs(oracle_mod, bd
     want = oracle_mod.bd_residual(cells, coords, gidx, free.size, u, np.zeros(free.size), bd_set=1)
     got = bd_host(1, cells, coords, gidx, u, bnd)
     assert np.abs(got - want).max() <= 1e-13 * max(1.0, np.abs(want).max())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# golden values of this slice (tests/golden/expected_next_rows.json, written by tests/golden/make_golden_next_rows.py)
+# ---------------------------------------------------------------------------------------------------------------
+def test_oracle_against_recorded_next_row_values(oracle_mod):
+    import hashlib
+    import json
+    from conftest import GOLDEN, load_osh_oracle
+    with open(os.path.join(GOLDEN, "expected_next_rows.json")) as f:
+        exp = json.load(f)
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    for name in ("T23", "T24k", "box2d_33x17", "box3d_5x4x3"):
+        if name.startswith("T"):
+            cells, coords, _ = load_osh_oracle({"T23": "23elm.osh", "T24k": "24k.osh"}[name])
+        else:
+            cells, coords = synthetic_meshes()[name]
+        e = exp[name]
+        nV = coords.shape[0]
+        gid = np.arange(nV, dtype=np.int32)
+        rowptr, colidx = oracle_mod.pattern(cells, gid, nV)
+        assert (nV, colidx.size) == (e["natural_N"], e["natural_nnz"])
+        assert sha(rowptr.astype(np.int32)) == e["natural_sha_rowptr"] and sha(colidx.astype(np.int64)) == e["natural_sha_colidx"]
+        F0 = oracle_mod.bd_residual(cells, coords, gid, nV, np.zeros(nV), oracle_mod.residual(0, cells, coords, gid, nV, np.zeros(nV)))
+        assert np.linalg.norm(F0) == pytest.approx(e["natural_F0_norm"], rel=1e-12)
+        gidx, N, rp, ci, vals, F = _system(oracle_mod, cells, coords)
+        for k in (1, 4, 8, 16):
+            r = oracle_mod.pcg(rp, ci, vals, F, rtol=1e-9, pc=2, cheb_its=k, maxit=100000)
+            g = e["chebyshev_k%d" % k]
+            assert (r["its"], r["reason"]) == (g["its"], g["reason"]) and r["emax"] == pytest.approx(g["emax"], rel=1e-12)
+            assert np.linalg.norm(r["x"]) == pytest.approx(g["x_norm"], rel=1e-9)
+    # T24k with the polynomial of degree 1 is Jacobi-preconditioned CG: the count recorded in expected.json
+    with open(os.path.join(GOLDEN, "expected.json")) as f:
+        assert exp["T24k"]["chebyshev_k1"]["its"] == json.load(f)["T24k"]["cg_its_jacobi"]

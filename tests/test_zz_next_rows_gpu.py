@@ -225,3 +225,31 @@ def test_facade_neumann_and_polynomial_preconditioner(ctx, oracle_mod):
     assert abs(get(poly, "L_2 Error:") - get(plain, "L_2 Error:")) < 1e-6  # nodally exact up to the solver tolerance, both
     bad = subprocess.run([_example(), "-mesh", "box", "-pc_type", "ksp", "-ksp_ksp_type", "gmres"], capture_output=True, text=True, timeout=600)
     assert bad.returncode == 56
+
+
+def test_recorded_values_T24k(ctx):
+    """the recorded values of tests/golden/expected_next_rows.json on the reference's XGC fixture, read from its .osh file"""
+    import hashlib
+    import json
+    from conftest import GOLDEN, golden_mesh_path
+    with open(os.path.join(GOLDEN, "expected_next_rows.json")) as f:
+        e = json.load(f)["T24k"]
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    m = ohp.Mesh.from_osh(ctx, golden_mesh_path("24k.osh")).set_bc_type(ohp.BC_NATURAL).setup()
+    rp, ci = m.csr()
+    assert (m.info().n_owned, m.info().nnz) == (e["natural_N"], e["natural_nnz"])
+    assert sha(rp) == e["natural_sha_rowptr"] and sha(ci) == e["natural_sha_colidx"]
+    u, F = m.create_global_vector().set(0.0), m.create_global_vector()
+    assert m.residual(0, u, F).norm() == pytest.approx(e["natural_F0_norm"], rel=1e-11)
+    m.destroy()
+    m = ohp.Mesh.from_osh(ctx, golden_mesh_path("24k.osh")).setup()
+    u, F, J, x = m.create_global_vector().set(0.0), m.create_global_vector(), m.create_matrix(), m.create_global_vector()
+    m.residual(0, u, F)
+    m.jacobian(0, u, J)
+    for k in (4, 16):
+        g = e["chebyshev_k%d" % k]
+        r = ohp.ksp_cg(J, F, x, ohp.ksp_options(rtol=1e-9, pc=ohp.PC_CHEBYSHEV, cheb_its=k))
+        assert r["reason"] == g["reason"] and _close_its(r["its"], g["its"])
+        assert r["cheb_emax"] == pytest.approx(g["emax"], rel=1e-8)
+        assert x.norm() == pytest.approx(g["x_norm"], rel=1e-7)
+    m.destroy()
