@@ -5,7 +5,7 @@
  *
  * The loop is written against an `Ops` policy (vectors are small integer handles) so that the SAME control flow that
  * drives the device kernels in ohp_pcg.cu can be instantiated over plain host arrays by the CPU unit test
- * (tests/host/pcg_host.cpp) and compared with the CPU restatement of the tests without a GPU.  Nothing here touches memory itself.
+ * (tests/host/pcg_host.cpp) and compared with the tests' CPU restatement without a GPU.  Nothing here touches memory itself.
  *
  * Restated [PETSc-internal]:
  *   KSPSolve_CG + KSPConvergedDefault (as ohp_ksp_cg: zero initial guess, preconditioned norm, reasons 2/3/-3/-4/-8/-9),
@@ -115,7 +115,7 @@ template <class Ops> int chebyshev_apply(Ops &ops, int its, double emin, double 
   const double scale = 2.0 / (emax + emin), alpha = 1.0 - scale * emin, mu = 1.0 / alpha, omegaprod = 2.0 / alpha;
   double c_km1 = 1.0, c_k = mu;
   int ykm1 = V_Y0, yk = V_Y1, ykp1 = V_Z;
-  /* y_0 = 0 is never read: the first rotation below passes first == true */
+  /* y_0 = 0 is never read or stored: the first step below passes "no y_{k-1}" instead */
   OHP_PCG_TRY(ops.cheb_first(yk, V_R, scale));
   bool km1_is_zero = true;
   for (int k = 1; k < its; ++k) {
