@@ -343,7 +343,8 @@ int ohp_l2_error(ohp_mesh mesh, int problem, ohp_vec u, double *err);
 /* OHP_PC_CHEBYSHEV ("preconditioning beyond Jacobi"): the Chebyshev polynomial in D^-1 A that PETSc
  * builds with -pc_type ksp -ksp_ksp_type chebyshev -ksp_pc_type jacobi -ksp_ksp_max_it <cheb_its> [PETSc-internal
  * KSPSolve_Chebyshev inside PCApply_KSP], applied without any reduction; the outer CG then runs in the general
- * host-driven loop (csrc/ohp_pcg.cu) instead of the fused recurrences. */
+ * host-driven loop (csrc/ohp_pcg.cu) instead of the fused recurrences (so does every solve on a matrix with a null
+ * space; `ksp_type` is not consulted there: the loop is plain preconditioned CG). */
 enum { OHP_PC_NONE = 0, OHP_PC_JACOBI = 1, OHP_PC_CHEBYSHEV = 2 };
 /* -ksp_type: cg (the library picks the recurrence -- classic, single-reduction or pipelined -- from the global problem
  * size and the transport; all give CG's iterates in exact arithmetic) or pipecg (PETSc's KSPPIPECG, Ghysels-Vanroose:
