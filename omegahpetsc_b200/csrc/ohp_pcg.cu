@@ -137,6 +137,9 @@ int ohp_pcg_solve(ohp_mat A, ohp_vec b, ohp_vec x, const ohp_ksp_options *o, ohp
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (rc == kErrInterval)
+    OHP_FAIL(OHP_ERR_ARG_WRONG, "ohp_ksp_cg: Chebyshev interval [%g, %g] (cheb_emin, cheb_emax; <= 0 means derived) must satisfy 0 < emin < emax",
+             po.emin, po.emax);
   if (rc) return rc;
   res->its = pr.its; res->reason = pr.reason; res->rnorm = pr.rnorm; res->rnorm0 = pr.rnorm0;
   res->spmv_ms = 0.f; res->spmv_samples = 0; res->total_ms = ms; res->algo = OHP_ALGO_GENERAL_PCG;

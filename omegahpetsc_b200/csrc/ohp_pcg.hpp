@@ -24,6 +24,7 @@
 namespace ohp_pcg {
 
 enum { PC_NONE = 0, PC_JACOBI = 1, PC_CHEBYSHEV = 2 };
+enum { kErrInterval = 62 }; /* PETSC_ERR_ARG_WRONG: the Chebyshev interval is empty or not positive */
 /* vector handles every Ops implementation provides */
 enum { V_X = 0, V_B, V_R, V_Z, V_P, V_W, V_Y0, V_Y1, V_T, V_COUNT };
 
@@ -152,6 +153,7 @@ template <class Ops> int solve(Ops &ops, const Options &o, Result *res) {
     double est = 0.0;
     if (!(emax > 0.0)) OHP_PCG_TRY(estimate_emax(ops, 10, &est, &spmvs));
     chebyshev_interval(o.cheb_its < 1 ? 1 : o.cheb_its, est, &emin, &emax);
+    if (!(emin > 0.0) || !(emax > emin)) return kErrInterval; /* 0 < emin < emax or the recurrence has no meaning */
   }
   res->emin = emin; res->emax = emax;
   int reason = 0, i = 0;

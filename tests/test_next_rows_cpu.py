@@ -269,6 +269,20 @@ def test_product_control_flow_edge_cases(oracle_mod, pcg_host):
     assert (h["its"], h["reason"]) == (3, -3)
 
 
+def test_product_control_flow_rejects_an_empty_interval(oracle_mod, pcg_host):
+    cells, coords = oracle_mod.box2d(5, 5)
+    gidx, N, rp, ci, vals, F = _system(oracle_mod, cells, coords)
+    L = pcg_host.lib
+    x, eig, hist = np.zeros(N), np.zeros(2), np.zeros(8)
+    its, reason, spmvs, rnorm = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_double()
+    for emin, emax in ((2.0, 1.0), (1.0, 1.0), (5.0, 0.0)):  # reversed, empty, lower end above the estimated upper end
+        rc = L.pcg_host_solve(N, _p(rp, c_i32p), _p(ci, c_i32p), _p(vals, c_f64p), _p(F, c_f64p), _p(x, c_f64p),
+                              ctypes.c_double(1e-9), ctypes.c_double(1e-50), ctypes.c_double(1e5), 100, 2, 4,
+                              ctypes.c_double(emin), ctypes.c_double(emax), 0, ctypes.byref(its), ctypes.byref(reason),
+                              ctypes.byref(rnorm), _p(eig, c_f64p), _p(hist, c_f64p), hist.size, ctypes.byref(spmvs))
+        assert rc == 62, (emin, emax, rc)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # the product's natural-boundary row function (include/ohp_fem.cuh: bd_residual_row, __host__ __device__) on host arrays
 # ---------------------------------------------------------------------------------------------------------------
