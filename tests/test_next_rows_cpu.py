@@ -393,3 +393,27 @@ def test_oracle_against_recorded_next_row_values(oracle_mod):
     # T24k with the polynomial of degree 1 is Jacobi-preconditioned CG: the count recorded in expected.json
     with open(os.path.join(GOLDEN, "expected.json")) as f:
         assert exp["T24k"]["chebyshev_k1"]["its"] == json.load(f)["T24k"]["cg_its_jacobi"]
+
+
+@pytest.mark.parametrize("dim,seed", [(2, 1), (2, 2), (3, 3), (3, 4)])
+def test_product_boundary_rows_on_unstructured_delaunay_meshes(oracle_mod, bd_host, dim, seed):
+    """irregular stars, boundary vertices with many boundary facets, cells of either orientation (the facet normal is taken
+    from the opposite vertex, so the orientation of the cell must not matter): three independent computations agree"""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(seed)
+    pts = rng.random((60 if dim == 2 else 40, dim))
+    cells = Delaunay(pts).simplices.astype(np.int32)
+    used = np.unique(cells)
+    remap = np.full(pts.shape[0], -1, np.int32)
+    remap[used] = np.arange(used.size, dtype=np.int32)
+    cells, coords = remap[cells], pts[used]
+    nV = coords.shape[0]
+    bnd = oracle_mod.mark_boundary(cells, nV)
+    gidx = np.arange(nV, dtype=np.int32)
+    want = oracle_mod.bd_residual(cells, coords, gidx, nV, np.zeros(nV), np.zeros(nV))
+    assert np.abs(want - _independent_bd(cells, coords)).max() <= 1e-12 * np.abs(want).max()
+    for bd_set in (0, 1):
+        u = np.cos(2 * coords[:, 0]) + coords[:, -1] ** 2
+        ref = oracle_mod.bd_residual(cells, coords, gidx, nV, u, np.zeros(nV), bd_set=bd_set)
+        got = bd_host(bd_set, cells, coords, gidx, u, bnd)
+        assert np.abs(got - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
