@@ -41,6 +41,7 @@ WORKLOADS = {
     # config 4 with the vertices renumbered along a Morton (Z-order) curve: Omega_h::build_box reorders its
     # vertices along a space-filling curve (ex12.cpp:805), so this is the ordering-robustness variant
     "box2d_2896_morton": (2, (2896, 2896)),
+    "box2d_2896_hilbert": (2, (2896, 2896)),   # the curve Omega_h::build_box sorts by (ex12.cpp:805); generator only, not measured in round 2
 }
 # solution tolerance of the `check` object: CG stops at ||r|| <= 1e-9 ||b||; the manufactured solution is nodally
 # exact on these boxes, so the nodal error is the algebraic error of the solve
@@ -64,6 +65,8 @@ def make_mesh(workload, n_override, pinned=False):
         cells, coords = meshgen.box2d(*sizes, pinned=pinned)
         if workload.endswith("_morton"):
             cells, coords = meshgen.morton_reorder(cells, coords, sizes, pinned=pinned)
+        if workload.endswith("_hilbert"):
+            cells, coords = meshgen.hilbert_reorder(cells, coords, sizes, pinned=pinned)
         return (cells, coords), sizes
     return meshgen.box3d(*sizes, pinned=pinned), sizes
 

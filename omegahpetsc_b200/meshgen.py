@@ -53,6 +53,38 @@ def _part1by1(x):
     return x
 
 
+def hilbert_index(i, j, bits):
+    """Distance of the grid points (i, j), 0 <= i, j < 2**bits, along the Hilbert curve of that order (the classic
+    quadrant-rotation recurrence, vectorised over the points)."""
+    x, y = i.astype(np.int64).copy(), j.astype(np.int64).copy()
+    d = np.zeros(x.shape, dtype=np.int64)
+    s = np.int64(1) << np.int64(bits - 1)
+    while s > 0:
+        rx = ((x & s) > 0).astype(np.int64)
+        ry = ((y & s) > 0).astype(np.int64)
+        d += s * s * ((3 * rx) ^ ry)
+        # rotate the quadrant so that the curve enters and leaves it at the right corners
+        flip = (ry == 0) & (rx == 1)
+        x = np.where(flip, s - 1 - x, x)
+        y = np.where(flip, s - 1 - y, y)
+        swap = ry == 0
+        x, y = np.where(swap, y, x), np.where(swap, x, y)
+        x &= s - 1
+        y &= s - 1
+        s >>= np.int64(1)
+    return d
+
+
+def hilbert_reorder(cells, coords, sizes, pinned=False):
+    """The same renumbering along a HILBERT curve, the curve Omega_h::build_box itself sorts by (ex12.cpp:805,
+    Omega_h-internal): consecutive vertices are always grid neighbours, which a Morton curve does not guarantee."""
+    nx, ny = sizes
+    i = np.rint(coords[:, 0] * nx).astype(np.int64)
+    j = np.rint(coords[:, 1] * ny).astype(np.int64)
+    bits = max(1, int(max(nx, ny)).bit_length())
+    return _reorder_by_key(cells, coords, hilbert_index(i, j, bits), pinned)
+
+
 def morton_reorder(cells, coords, sizes, pinned=False):
     """Renumber the vertices (and sort the cells) of a 2-D box along a Morton (Z-order) curve.  Stands in for the
     space-filling-curve reordering of Omega_h::build_box (ex12.cpp:805): the mesh is the same, the numbering
@@ -61,6 +93,10 @@ def morton_reorder(cells, coords, sizes, pinned=False):
     i = np.rint(coords[:, 0] * nx).astype(np.int64)
     j = np.rint(coords[:, 1] * ny).astype(np.int64)
     key = _part1by1(i) | (_part1by1(j) << np.uint64(1))
+    return _reorder_by_key(cells, coords, key, pinned)
+
+
+def _reorder_by_key(cells, coords, key, pinned):
     order = np.argsort(key, kind="stable")              # new vertex k = old vertex order[k]
     new_of_old = np.empty(order.size, dtype=np.int32)
     new_of_old[order] = np.arange(order.size, dtype=np.int32)

@@ -78,3 +78,44 @@ def test_morton_workload_is_the_same_mesh_renumbered():
     rp, ci = oracle.pattern(c2, g, N)
     rows = np.repeat(np.arange(N), np.diff(rp))
     assert np.abs(ci - rows).max() > 3 * 25   # no longer banded by the grid width
+
+
+def test_hilbert_workload_is_the_same_mesh_renumbered_along_a_continuous_curve():
+    import numpy as np
+    import oracle
+    from omegahpetsc_b200 import meshgen
+    # the curve itself: a bijection on the 2^b x 2^b grid whose consecutive points are grid neighbours
+    for bits in (1, 2, 3, 5):
+        n = 1 << bits
+        i, j = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+        d = meshgen.hilbert_index(i.reshape(-1), j.reshape(-1), bits)
+        assert np.array_equal(np.sort(d), np.arange(n * n))
+        order = np.argsort(d)
+        step = np.abs(np.diff(i.reshape(-1)[order])) + np.abs(np.diff(j.reshape(-1)[order]))
+        assert (step == 1).all()
+    # the workload: same vertices, same triangles, positive orientation kept, numbering no longer banded
+    c, x = meshgen.box2d(24, 17)
+    c2, x2 = meshgen.hilbert_reorder(c, x, (24, 17))
+    assert sorted(map(tuple, np.round(x2, 12))) == sorted(map(tuple, np.round(x, 12)))
+    tri = lambda cc, xx: sorted(tuple(sorted(map(tuple, np.round(xx[t], 12)))) for t in cc)
+    assert tri(c, x) == tri(c2, x2)
+    X = x2[c2]
+    area2 = (X[:, 1, 0] - X[:, 0, 0]) * (X[:, 2, 1] - X[:, 0, 1]) - (X[:, 1, 1] - X[:, 0, 1]) * (X[:, 2, 0] - X[:, 0, 0])
+    assert (area2 > 0).all()
+    b = oracle.mark_boundary(c2, x2.shape[0])
+    g, N = oracle.numbering(b)
+    rp, ci = oracle.pattern(c2, g, N)
+    rows = np.repeat(np.arange(N), np.diff(rp))
+    assert np.abs(ci - rows).max() > 3 * 25
+    # the operator is the same up to the permutation: same CG iteration count, same solution at the same points
+    vals = oracle.jacobian(0, c2, x2, g, N, np.zeros(N), rp, ci)
+    F = oracle.residual(0, c2, x2, g, N, np.zeros(N))
+    b0 = oracle.mark_boundary(c, x.shape[0])
+    g0, N0 = oracle.numbering(b0)
+    rp0, ci0 = oracle.pattern(c, g0, N0)
+    r0 = oracle.cg(rp0, ci0, oracle.jacobian(0, c, x, g0, N0, np.zeros(N0), rp0, ci0), oracle.residual(0, c, x, g0, N0, np.zeros(N0)), rtol=1e-10)
+    r2 = oracle.cg(rp, ci, vals, F, rtol=1e-10)
+    assert N == N0 and abs(r2["its"] - r0["its"]) <= 1
+    key = lambda xx, gg: {tuple(np.round(p, 12)): k for p, k in zip(xx, gg) if k >= 0}
+    k0, k2 = key(x, g0), key(x2, g)
+    assert max(abs(r0["x"][k0[p]] - r2["x"][k2[p]]) for p in k0) < 1e-8

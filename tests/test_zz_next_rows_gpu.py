@@ -253,3 +253,30 @@ def test_recorded_values_T24k(ctx):
         assert r["cheb_emax"] == pytest.approx(g["emax"], rel=1e-8)
         assert x.norm() == pytest.approx(g["x_norm"], rel=1e-7)
     m.destroy()
+
+
+def test_hilbert_ordering_like_build_box(ctx, oracle_mod):
+    """The ordering Omega_h::build_box itself produces (ex12.cpp:805: vertices sorted along a Hilbert curve): the same bar as
+    the Morton-ordered mesh of test_gpu_parity.py -- bit-exact numbering and pattern, SpMV on the 32-bit column stream, the
+    Newton solve nodally exact."""
+    from omegahpetsc_b200 import meshgen
+    n = 700
+    c0, x0 = meshgen.box2d(n, n)
+    cells, coords = meshgen.hilbert_reorder(c0, x0, (n, n))
+    bnd = oracle_mod.mark_boundary(cells, coords.shape[0])
+    gidx, N = oracle_mod.numbering(bnd)
+    rowptr, colidx = oracle_mod.pattern(cells, gidx, N)
+    rows = np.repeat(np.arange(N), np.diff(rowptr))
+    assert (np.abs(colidx - rows) > 32767).any(), "this mesh must have offsets beyond 16 bits"
+    m = ohp.Mesh(ctx, cells, coords).setup()
+    rp, ci = m.csr()
+    assert np.array_equal(m.numbering(), gidx.astype(np.int64)) and np.array_equal(rp, rowptr) and np.array_equal(ci, colidx.astype(np.int64))
+    J, u, y = m.create_matrix(), m.create_global_vector(), m.create_global_vector()
+    m.jacobian(0, u, J)
+    xh = np.random.default_rng(3).standard_normal(N)
+    J.mult(u.from_host(xh), y)
+    yo = oracle_mod.spmv(rowptr, colidx, J.values(), xh)
+    assert np.abs(y.to_host() - yo).max() <= 1e-13 * np.abs(yo).max()
+    res = m.snes_solve(0, J, u.set(0.0), ksp=ohp.ksp_options(rtol=1e-10, max_it=100000))
+    assert res["reason"] == 3 and np.abs(u.to_host() - (coords ** 2).sum(axis=1)[gidx >= 0]).max() < 1e-7
+    m.destroy()
